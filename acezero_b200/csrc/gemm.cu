@@ -1,0 +1,382 @@
+// tcgen05 + TMA GEMM for sm_100a. See gemm.cuh for the operand conventions.
+//
+// One CTA computes one 128 x BN output tile: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread UMMA
+// issuer, warps 2..5 = epilogue (TMEM -> registers -> global). A ring of kStages shared-memory stages is handed
+// between producer and issuer with full/empty mbarriers; tcgen05.commit releases stages and publishes the
+// accumulator to the epilogue warps.
+#include "gemm.cuh"
+
+namespace acez {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle row
+static constexpr int kThreads = 192;
+static constexpr uint32_t kSw128 = 2;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kAStage = BM * BK * 2;
+  static constexpr int kBStage = BN * BK * 2;
+  static constexpr int kStage = kAStage + kBStage;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kOnesBytes = 16 * BK * 2;  // 16 x 64 tile of 1.0 for the bias-gradient column
+  static constexpr int kSmem = kStages * kStage + kOnesBytes + BN * 4 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr bool kBiasCol = (EPI == EPI_WGRAD);
+  constexpr uint32_t kTmemCols = kBiasCol ? (BN >= 256 ? 512 : 2 * BN) : (BN < 32 ? 32 : BN);
+  static_assert(!(kBiasCol && BN > 256), "tmem");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kAStage;
+  uint8_t* sOnes = smem + kStages * Cfg::kStage;
+  float* sBias = reinterpret_cast<float*>(sOnes + Cfg::kOnesBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + BN);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int z = blockIdx.z;
+  const int k_blocks = args.k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (kBiasCol && warp >= 2) {
+    // ones tile: layout irrelevant (all entries equal)
+    __half2* o = reinterpret_cast<__half2*>(sOnes);
+    for (int i = threadIdx.x - 64; i < Cfg::kOnesBytes / 4; i += 128) o[i] = __floats2half2_rn(1.f, 1.f);
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+  }
+  if (EPI == EPI_FWD && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      const int n = n0 + i;
+      // autocast casts the fp32 bias to fp16 before the conv adds it
+      sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(args.bias[n])) : 0.f;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStage);
+        uint8_t* a_dst = sA + stage * Cfg::kAStage;
+        uint8_t* b_dst = sB + stage * Cfg::kBStage;
+        if (A_MN) {
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i) tma_load_3d(a_dst + i * 8192, &tmA, &full_bar[stage], m0 + 64 * i, kb * BK, z);
+        } else {
+          tma_load_3d(a_dst, &tmA, &full_bar[stage], kb * BK, m0, z);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) tma_load_3d(b_dst + i * 8192, &tmB, &full_bar[stage], n0 + 64 * i, kb * BK, z);
+        } else {
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * BK, n0, z);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, A_MN, B_MN);
+    constexpr uint32_t idesc_ones = make_idesc_f16(BM, 16, A_MN, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(sA + stage * Cfg::kAStage);
+        const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBStage);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * args.a_kstep, args.a_lbo, args.a_sbo, kSw128);
+          const uint64_t db = make_smem_desc(b_addr + k * args.b_kstep, args.b_lbo, args.b_sbo, kSw128);
+          umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (kBiasCol && n0 == 0 && args.bias_grad != nullptr) {
+            const uint64_t d1 = make_smem_desc(smem_u32(sOnes) + k * 32, 0, 1024, kSw128);
+            umma_f16(tmem_base + BN, da, d1, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        tcgen05_commit(&empty_bar[stage]);                     // stage free once the MMAs above retire
+        if (kb == k_blocks - 1) tcgen05_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ------------------------------ epilogue (4 warps <-> 4 TMEM lane quarters) ------------------------------
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < args.M;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    bool bad = false;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      const int ncol = n0 + c * 32;
+      if (!row_ok || ncol >= args.N) continue;
+      if (EPI == EPI_WGRAD) {
+        float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride +
+                                                (long long)row * args.ldo32 + ncol);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      } else {
+        const long long off = (long long)row * args.ldo + ncol;
+        uint4 o[4], o2[4];
+        if (EPI == EPI_FWD) {
+          uint4 r[4];
+          if (args.resid != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(args.resid + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = rp[j];
+          }
+          __half2* oh = reinterpret_cast<__half2*>(o);
+          __half2* o2h = reinterpret_cast<__half2*>(o2);
+          const __half2* rh = reinterpret_cast<const __half2*>(r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(v[2 * j]) + sBias[c * 32 + 2 * j];
+            float b = __uint_as_float(v[2 * j + 1]) + sBias[c * 32 + 2 * j + 1];
+            if (args.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            const __half2 h = __floats2half2_rn(a, b);
+            oh[j] = h;
+            if (args.resid != nullptr) o2h[j] = __hadd2(rh[j], h);
+          }
+        } else {  // EPI_DGRAD
+          uint4 mk[4], ad[4];
+          const uint4* mp = reinterpret_cast<const uint4*>(args.mask + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mk[j] = mp[j];
+          if (args.addend != nullptr) {
+            const uint4* ap = reinterpret_cast<const uint4*>(args.addend + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ad[j] = ap[j];
+          }
+          __half2* oh = reinterpret_cast<__half2*>(o);
+          __half2* o2h = reinterpret_cast<__half2*>(o2);
+          const __half2* mh = reinterpret_cast<const __half2*>(mk);
+          const __half2* ah = reinterpret_cast<const __half2*>(ad);
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+            __half2 h = __floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (args.addend != nullptr) h = __hadd2(h, ah[j]);
+            o2h[j] = h;
+            const float2 hf = __half22float2(h);
+            bad |= !(isfinite(hf.x) && isfinite(hf.y));
+            const __half2 gt = __hgt2(mh[j], zero2);  // 1.0 where mask > 0
+            oh[j] = __hmul2(h, gt);
+            // inf * 0 would give nan: force exact zero where masked
+            const float2 g = __half22float2(gt);
+            if (g.x == 0.f) oh[j].x = __float2half_rn(0.f);
+            if (g.y == 0.f) oh[j].y = __float2half_rn(0.f);
+          }
+        }
+        if (args.out != nullptr) {
+          uint4* op = reinterpret_cast<uint4*>(args.out + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = o[j];
+        }
+        if (args.out2 != nullptr && (EPI == EPI_DGRAD || args.resid != nullptr)) {
+          uint4* o2p = reinterpret_cast<uint4*>(args.out2 + off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o2p[j] = o2[j];
+        }
+      }
+    }
+    if (kBiasCol && n0 == 0 && args.bias_grad != nullptr) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + BN, v);
+      tmem_ld_wait();
+      if (row_ok) args.bias_grad[(long long)z * args.bias_grad_zstride + row] = __uint_as_float(v[0]);
+    }
+    if (EPI == EPI_DGRAD && args.nonfinite != nullptr) {
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int encode_operand(CUtensorMap* tm, const __half* base, int mn_major, int rows_mn, int K, int ld, int batch,
+                          long long zstride, int tile_mn) {
+  // K-major : memory [batch][rows_mn][ld], inner = K,       box {64, tile_mn, 1}
+  // MN-major: memory [batch][K][ld],       inner = rows_mn, box {64, 64, 1}
+  uint64_t dims[3];
+  uint64_t strides[2];
+  uint32_t box[3];
+  if (!mn_major) {
+    dims[0] = (uint64_t)K; dims[1] = (uint64_t)rows_mn; dims[2] = (uint64_t)batch;
+    box[0] = 64; box[1] = (uint32_t)tile_mn; box[2] = 1;
+  } else {
+    dims[0] = (uint64_t)rows_mn; dims[1] = (uint64_t)K; dims[2] = (uint64_t)batch;
+    box[0] = 64; box[1] = 64; box[2] = 1;
+  }
+  strides[0] = (uint64_t)ld * 2;
+  strides[1] = (uint64_t)(batch > 1 ? zstride : (long long)dims[1] * ld) * 2;
+  return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int gemm_prepare(GemmLaunch* L, const GemmProblem& p) {
+  ACEZ_REQUIRE(p.M > 0 && p.N > 0 && p.K > 0 && p.batch >= 1, "gemm: bad shape %d %d %d x%d", p.M, p.N, p.K, p.batch);
+  ACEZ_REQUIRE(p.K % BK == 0, "gemm: K=%d must be a multiple of %d", p.K, BK);
+  ACEZ_REQUIRE(p.lda % 8 == 0 && p.ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 elements");
+  int bn = p.bn;
+  if (bn == 0) bn = (p.N % 256 == 0 && p.epi != EPI_WGRAD) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+  ACEZ_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: unsupported BN=%d", bn);
+  ACEZ_REQUIRE(p.N % 32 == 0, "gemm: N=%d must be a multiple of 32", p.N);
+  L->bn = bn;
+  L->a_mn = p.a_mn;
+  L->b_mn = p.b_mn;
+  L->epi = p.epi;
+  L->batch = p.batch;
+  GemmArgs a{};
+  a.M = p.M;
+  a.N = p.N;
+  a.k_blocks = p.K / BK;
+  // K-major, SWIZZLE_128B: 8-row groups 1024 B apart, k-step of 16 elements = 32 B inside the swizzle row.
+  // MN-major, SWIZZLE_128B: 64-element MN atoms 64 rows * 128 B = 8192 B apart (LBO), 8-row K groups 1024 B apart
+  // (SBO), k-step of 16 rows = 2048 B.
+  a.a_lbo = p.a_mn ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = p.a_mn ? 2048 : 32;
+  a.b_lbo = p.b_mn ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = p.b_mn ? 2048 : 32;
+  L->args = a;
+  int rc = encode_operand(&L->tmA, p.A, p.a_mn, p.M, p.K, p.lda, p.batch, p.a_zstride, BM);
+  if (rc) return rc;
+  return encode_operand(&L->tmB, p.B, p.b_mn, p.N, p.K, p.ldb, p.batch, p.b_zstride, bn);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmem));
+    configured = true;
+  }
+  dim3 grid((L.args.N + BN - 1) / BN, (L.args.M + BM - 1) / BM, L.batch);
+  kern<<<grid, kThreads, GemmCfg<BN>::kSmem, stream>>>(L.tmA, L.tmB, L.args);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+#define ACEZ_GEMM_CASE(BN_, AMN_, BMN_, EPI_) \
+  if (L.bn == BN_ && L.a_mn == AMN_ && L.b_mn == BMN_ && L.epi == EPI_) return launch_variant<BN_, AMN_, BMN_, EPI_>(L, stream);
+  ACEZ_GEMM_CASE(256, false, false, EPI_FWD)
+  ACEZ_GEMM_CASE(128, false, false, EPI_FWD)
+  ACEZ_GEMM_CASE(64, false, false, EPI_FWD)
+  ACEZ_GEMM_CASE(256, false, true, EPI_DGRAD)
+  ACEZ_GEMM_CASE(128, false, true, EPI_DGRAD)
+  ACEZ_GEMM_CASE(128, true, true, EPI_WGRAD)
+  // generic fp32-output variants (tests / probing of operand layouts)
+  ACEZ_GEMM_CASE(128, false, false, EPI_WGRAD)
+  ACEZ_GEMM_CASE(128, false, true, EPI_WGRAD)
+  ACEZ_GEMM_CASE(128, true, false, EPI_WGRAD)
+#undef ACEZ_GEMM_CASE
+  set_error("gemm: no kernel variant for bn=%d a_mn=%d b_mn=%d epi=%d", L.bn, L.a_mn, L.b_mn, L.epi);
+  return ACEZ_ERR_UNSUPPORTED;
+}
+
+}  // namespace acez
+
+// ----------------------------------------------------------------------------------------------
+// C ABI: generic GEMM entry (tests, probing)
+// ----------------------------------------------------------------------------------------------
+
+extern "C" int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream) {
+  using namespace acez;
+  ACEZ_REQUIRE(d != nullptr, "gemm: null desc");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  GemmProblem p{};
+  p.A = reinterpret_cast<const __half*>(d->A);
+  p.B = reinterpret_cast<const __half*>(d->B);
+  p.a_mn = d->a_mn_major;
+  p.b_mn = d->b_mn_major;
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.batch = d->batch > 0 ? d->batch : 1;
+  p.a_zstride = d->a_zstride; p.b_zstride = d->b_zstride;
+  p.lda = d->lda; p.ldb = d->ldb;
+  p.bn = d->bn;
+  p.epi = d->epilogue;
+  GemmLaunch L;
+  rc = gemm_prepare(&L, p);
+  if (rc) return rc;
+  GemmArgs& a = L.args;
+  a.bias = d->bias;
+  a.resid = reinterpret_cast<const __half*>(d->resid);
+  a.mask = reinterpret_cast<const __half*>(d->mask);
+  a.addend = reinterpret_cast<const __half*>(d->addend);
+  a.out = reinterpret_cast<__half*>(d->out);
+  a.out2 = reinterpret_cast<__half*>(d->out2);
+  a.ldo = d->ldo;
+  a.relu = d->relu;
+  a.nonfinite = d->nonfinite;
+  a.out32 = d->out32;
+  a.out32_zstride = d->out32_zstride;
+  a.ldo32 = d->ldo32;
+  a.bias_grad = d->bias_grad;
+  a.bias_grad_zstride = d->bias_grad_zstride;
+  if (d->a_lbo) a.a_lbo = d->a_lbo;
+  if (d->a_sbo) a.a_sbo = d->a_sbo;
+  if (d->a_kstep) a.a_kstep = d->a_kstep;
+  if (d->b_lbo) a.b_lbo = d->b_lbo;
+  if (d->b_sbo) a.b_sbo = d->b_sbo;
+  if (d->b_kstep) a.b_kstep = d->b_kstep;
+  if (d->epilogue == ACEZ_EPI_F32) {
+    ACEZ_REQUIRE(d->out32 != nullptr && d->ldo32 % 4 == 0, "gemm: fp32 epilogue needs out32 with ldo32 %% 4 == 0");
+  } else {
+    ACEZ_REQUIRE((d->out != nullptr || d->out2 != nullptr) && d->ldo % 8 == 0, "gemm: fp16 epilogue needs out with ldo %% 8 == 0");
+    ACEZ_REQUIRE(d->epilogue != ACEZ_EPI_DGRAD || d->mask != nullptr, "gemm: dgrad epilogue needs a mask");
+  }
+  return gemm_launch(L, reinterpret_cast<cudaStream_t>(stream));
+}

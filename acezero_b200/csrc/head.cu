@@ -1,0 +1,652 @@
+// ACE head (reference ace_network.py:62-149) forward / backward on sm_100a, plus the fused "tail" kernel that
+// joins fc3, the homogeneous de-normalisation (ace_network.py:139-147) and the reprojection loss + backward
+// (ace_trainer.py:521-613) into one pass over the last hidden activation.
+//
+// Data layout in HBM (all caller-owned; see acez_head_workspace_bytes):
+//   params / grads : flat fp32, per hidden layer W[512,512] then b[512]; fc3 W[C3,512], b[C3] last
+//   W16            : [L][512][512] fp16 shadow of the hidden-layer weights (autocast's cast of the conv weights)
+//   W3h            : [4][512] fp16 shadow of fc3
+//   ACT            : [L+1][max_rows][512] fp16; ACT[l] is the input of hidden layer l, ACT[L] feeds fc3
+//   XTRA           : [nres][max_rows][512] fp16 post-ReLU output of the last conv of each residual block (ReLU mask)
+//   DZ             : [L][max_rows][512] fp16 gradient w.r.t. the pre-activation of each hidden layer (x grad_scale)
+//   GRES           : [max_rows][512] fp16 running skip-path gradient
+#include <vector>
+
+#include "gemm.cuh"
+#include "repro_loss.cuh"
+
+namespace acez {
+
+static constexpr int kC = 512;  // head width, hard-coded in the reference (ace_network.py:76)
+static constexpr size_t kLayerStride = (size_t)kC * kC + kC;
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace acez
+
+struct acez_head_plan {
+  acez_head_config cfg;
+  int L, nres, C3;
+  size_t n_params;
+  float* params;
+  float* grads;
+  __half* W16;
+  __half* W3h;
+  __half* ACT;
+  __half* XTRA;
+  __half* DZ;
+  __half* GRES;
+  size_t act_stride;  // max_rows * 512
+  int prepared_rows;
+  int prepared_training;
+  std::vector<acez::GemmLaunch> fwd;
+  std::vector<acez::GemmLaunch> dgrad;
+  acez::GemmLaunch wgrad;
+};
+
+namespace acez {
+
+struct HeadLayout {
+  size_t w16, w3h, act, xtra, dz, gres, total;
+};
+
+static HeadLayout head_layout(const acez_head_config& cfg) {
+  const int nres = cfg.num_res_blocks;
+  const int L = 3 * nres + 2;
+  const size_t rows = (size_t)cfg.max_rows;
+  HeadLayout o{};
+  size_t off = 0;
+  o.w16 = off; off = align_up(off + (size_t)L * kC * kC * 2, 1024);
+  o.w3h = off; off = align_up(off + 4 * kC * 2, 1024);
+  o.act = off; off = align_up(off + (size_t)(L + 1) * rows * kC * 2, 1024);
+  if (cfg.training) {
+    o.xtra = off; off = align_up(off + (size_t)nres * rows * kC * 2, 1024);
+    o.dz = off; off = align_up(off + (size_t)L * rows * kC * 2, 1024);
+    o.gres = off; off = align_up(off + rows * kC * 2, 1024);
+  }
+  o.total = off;
+  return o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// small kernels
+// ----------------------------------------------------------------------------------------------
+__global__ void cast_weights_kernel(const float* __restrict__ params, __half* __restrict__ W16,
+                                    __half* __restrict__ W3h, int L, int C3) {
+  const size_t n_hidden = (size_t)L * kC * kC;
+  const size_t n_total = n_hidden + (size_t)4 * kC;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_hidden) {
+      const size_t l = i / ((size_t)kC * kC), r = i % ((size_t)kC * kC);
+      W16[i] = __float2half_rn(params[l * kLayerStride + r]);
+    } else {
+      const size_t r = i - n_hidden;  // [4][512]
+      const size_t row = r / kC;
+      W3h[r] = (row < (size_t)C3) ? __float2half_rn(params[(size_t)L * kLayerStride + r]) : __float2half_rn(0.f);
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ idx, int rows,
+                                   int row_bytes, uint8_t* __restrict__ dst) {
+  // one warp per row, 16-byte vectors when the row size allows
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const uint8_t* s = src + (size_t)idx[warp] * row_bytes;
+  uint8_t* d = dst + (size_t)warp * row_bytes;
+  if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    for (int o = lane * 16; o < row_bytes; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
+  } else if ((row_bytes & 3) == 0) {
+    for (int o = lane * 4; o < row_bytes; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+  } else {
+    for (int o = lane * 2; o < row_bytes; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1] and the fc3 gradient)
+// one warp per row; lane owns columns [16*lane, 16*lane+16)
+// ----------------------------------------------------------------------------------------------
+struct TailArgs {
+  int rows, C3, use_homogeneous, training;
+  float mean[3], h_beta, max_inv_scale, min_inv_scale;
+  const __half* x;      // ACT[L]  [rows,512]
+  const __half* W3h;    // [4,512] fp16
+  const float* b3;      // [C3] fp32
+  float* sc_out;        // [rows,3] nullable
+  // training
+  acez_loss_params lp;
+  const float* grad_scale_dev;  // nullable: overrides lp.grad_scale (GradScaler state lives on the device)
+  const float* tpx; const float* Pin; const float* A; const float* T; const float* K; const float* Kinv; const float* G;
+  float* d_P; float* d_Kdiag;
+  __half* dz;           // DZ[L-1] [rows,512]
+  float* gW3;           // grads of fc3 weight [C3,512] (atomically accumulated; caller zeroes)
+  float* gb3;           // [C3]
+  float* stats;         // [4]
+  int* nonfinite;
+};
+
+static constexpr int kTailThreads = 256;
+
+__global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
+  __shared__ float sW[4][kC];       // fc3 weights as float (from the fp16 shadow)
+  __shared__ float sG[4][kC];       // block-level accumulation of dW3
+  __shared__ float sRed[4][kTailThreads / 32];
+  __shared__ float sGb[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 4 * kC; i += kTailThreads) {
+    (&sW[0][0])[i] = __half2float(a.W3h[i]);
+    (&sG[0][0])[i] = 0.f;
+  }
+  if (tid < 4) sGb[tid] = 0.f;
+  __syncthreads();
+  float b3[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b3[j] = (j < a.C3) ? __half2float(__float2half_rn(a.b3[j])) : 0.f;
+
+  acez_loss_params lp = a.lp;
+  if (a.training && a.grad_scale_dev != nullptr) lp.grad_scale = *a.grad_scale_dev;
+
+  float accW[4][16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) accW[j][k] = 0.f;
+  float accB[4] = {0.f, 0.f, 0.f, 0.f};
+  float loss_sum = 0.f, inl_sum = 0.f, valid_sum = 0.f;
+  bool bad = false, bad_g = false;
+
+  const int warps_total = gridDim.x * (kTailThreads / 32);
+  for (int row = blockIdx.x * (kTailThreads / 32) + warp; row < a.rows; row += warps_total) {
+    // ---- load this lane's 16 activations ----
+    const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * kC + lane * 16);
+    uint4 xr[2] = {xp[0], xp[1]};
+    const __half2* xh = reinterpret_cast<const __half2*>(xr);
+    float xf[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 f = __half22float2(xh[k]);
+      xf[2 * k] = f.x; xf[2 * k + 1] = f.y;
+    }
+    // ---- fc3: 4 dot products (fp32 accumulate, fp16 output as the autocast conv produces) ----
+    float s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) d = fmaf(xf[k], sW[j][lane * 16 + k], d);
+      d = warp_sum(d);
+      s[j] = __half2float(__float2half_rn(d + b3[j]));
+    }
+    // ---- homogeneous -> 3-D (ace_network.py:139-147), fp32 ----
+    float X[3], h = 1.f, sig = 0.f;
+    bool h_pass = true;
+    if (a.use_homogeneous) {
+      const float bx = a.h_beta * s[3];
+      float sp;
+      if (bx > 20.f) { sp = s[3]; sig = 1.f; }               // torch softplus threshold
+      else { sp = log1pf(expf(bx)) / a.h_beta; sig = 1.f / (1.f + expf(-bx)); }
+      h = sp + a.max_inv_scale;
+      h_pass = h <= a.min_inv_scale;                          // clamp_(max=) backward mask
+      h = fminf(h, a.min_inv_scale);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) X[i] = s[i] / h + a.mean[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) X[i] = s[i] + a.mean[i];
+    }
+    if (a.sc_out != nullptr && lane < 3) a.sc_out[(size_t)row * 3 + lane] = X[lane];
+    if (!a.training) continue;
+
+    // ---- reprojection loss + backward (all lanes redundantly; inputs are warp-broadcast loads) ----
+    float P[12];
+    if (a.Pin != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) P[k] = a.Pin[12 * (size_t)row + k];
+    } else {
+      compose_pose(a.A + 12 * (size_t)row, a.T + 16 * (size_t)row, P);
+    }
+    float Kr[9], Ki[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { Kr[k] = a.K[9 * (size_t)row + k]; Ki[k] = a.Kinv[9 * (size_t)row + k]; }
+    RowLoss o;
+    repro_row(lp, X, P, Kr, Ki, a.tpx[2 * (size_t)row], a.tpx[2 * (size_t)row + 1],
+              (lp.use_depth && a.G) ? a.G + 3 * (size_t)row : nullptr, o);
+    if (lane == 0) {
+      loss_sum += o.loss / (float)lp.divisor;
+      inl_sum += o.inlier ? 1.f : 0.f;
+      valid_sum += o.valid ? 1.f : 0.f;
+      bad |= !isfinite(o.loss);
+      if (a.d_Kdiag != nullptr) { a.d_Kdiag[2 * (size_t)row] = o.gK00; a.d_Kdiag[2 * (size_t)row + 1] = o.gK11; }
+    }
+    if (a.d_P != nullptr && lane < 12) {
+      const int r = lane >> 2, c = lane & 3;
+      a.d_P[12 * (size_t)row + lane] = o.gc[r] * (c < 3 ? X[c] : 1.f);
+    }
+    // ---- back through the de-homogenisation to the 4 fc3 outputs; rounded to fp16 like autograd's cast ----
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.use_homogeneous) {
+      const float ih = 1.f / h;
+      float gh = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { g[i] = o.gX[i] * ih; gh -= o.gX[i] * s[i] * ih * ih; }
+      g[3] = h_pass ? gh * sig : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) g[i] = o.gX[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g[j] = __half2float(__float2half_rn(g[j]));
+      bad_g |= !isfinite(g[j]);
+    }
+    // ---- dX8 = g W3 (fp16 result), masked by ReLU of x8 -> DZ[L-1]; accumulate dW3, db3 ----
+    uint4 outv[2];
+    __half2* oh = reinterpret_cast<__half2*>(outv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        d0 = fmaf(g[j], sW[j][lane * 16 + 2 * k], d0);
+        d1 = fmaf(g[j], sW[j][lane * 16 + 2 * k + 1], d1);
+      }
+      __half2 hv = __floats2half2_rn(d0, d1);
+      const float2 hf = __half22float2(hv);
+      bad_g |= !(isfinite(hf.x) && isfinite(hf.y));
+      if (!(xf[2 * k] > 0.f)) hv.x = __float2half_rn(0.f);
+      if (!(xf[2 * k + 1] > 0.f)) hv.y = __float2half_rn(0.f);
+      oh[k] = hv;
+    }
+    uint4* dzp = reinterpret_cast<uint4*>(a.dz + (size_t)row * kC + lane * 16);
+    dzp[0] = outv[0];
+    dzp[1] = outv[1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) accW[j][k] = fmaf(g[j], xf[k], accW[j][k]);
+      accB[j] += g[j];
+    }
+  }
+  if (!a.training) return;
+
+  // ---- block reduction of dW3 / db3 / stats, then one round of global atomics per block ----
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) atomicAdd(&sG[j][lane * 16 + k], accW[j][k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&sGb[j], accB[j]);
+    sRed[0][warp] = loss_sum; sRed[1][warp] = inl_sum; sRed[2][warp] = valid_sum;
+  }
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);
+  const int any_bad_g = __syncthreads_or(bad_g ? 1 : 0);
+  for (int i = tid; i < a.C3 * kC; i += kTailThreads) atomicAdd(&a.gW3[i], (&sG[0][0])[i]);
+  if (tid < a.C3) atomicAdd(&a.gb3[tid], sGb[tid]);
+  if (tid == 0) {
+    float l = 0.f, n = 0.f, v = 0.f;
+    for (int k = 0; k < kTailThreads / 32; ++k) { l += sRed[0][k]; n += sRed[1][k]; v += sRed[2][k]; }
+    atomicAdd(&a.stats[0], l);
+    atomicAdd(&a.stats[1], n);
+    atomicAdd(&a.stats[2], v);
+    if (any_bad) a.stats[3] = 1.f;
+    if (any_bad_g && a.nonfinite != nullptr) atomicOr(a.nonfinite, 1);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// GradScaler inf check + AdamW + GradScaler.update, all on the device (no host sync)
+//   scaler_state: [0] scale S, [1] growth tracker, [2] optimizer step count t
+// ----------------------------------------------------------------------------------------------
+__global__ void grad_check_kernel(const float* __restrict__ g, size_t n, int* __restrict__ found_inf) {
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    // under autocast the weight gradient is materialised in fp16: |g| > 65504 overflows to inf there
+    bad |= !isfinite(v) || fabsf(v) > 65504.f;
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(found_inf, 1);
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, const float* __restrict__ hyper,
+                             const float* __restrict__ scaler_state, const int* __restrict__ found_inf,
+                             int use_scaler, __half* __restrict__ W16, __half* __restrict__ W3h, int L, int C3) {
+  if (use_scaler && *found_inf != 0) return;  // GradScaler.step skips optimizer.step() on inf/nan
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+  const float inv_scale = use_scaler ? 1.f / scaler_state[0] : 1.f;
+  const float t = scaler_state[2] + 1.f;  // this step's index (torch: state['step'] += 1 before use)
+  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+  const float step_size = lr / bc1;
+  const float bc2_sqrt = sqrtf(bc2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    if (use_scaler) gi = __half2float(__float2half_rn(gi));  // fp16 weight gradient of the autocast conv
+    gi *= inv_scale;                                          // GradScaler.unscale_
+    float pi = p[i];
+    pi *= (1.f - lr * wd);                             // decoupled weight decay (torch adamw)
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    if (W16 != nullptr) {  // refresh the fp16 shadow the next forward reads
+      const size_t l = i / kLayerStride, r = i % kLayerStride;
+      if (l < (size_t)L) {
+        if (r < (size_t)kC * kC) W16[l * (size_t)kC * kC + r] = __float2half_rn(pi);
+      } else if (r < (size_t)C3 * kC) {
+        W3h[r] = __float2half_rn(pi);
+      }
+    }
+  }
+}
+
+// torch.cuda.amp.GradScaler.update(): backoff 0.5 on inf, growth x2 every 2000 clean steps
+__global__ void scaler_update_kernel(float* __restrict__ st, const int* __restrict__ found_inf, int use_scaler) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (use_scaler && *found_inf != 0) {
+    st[0] *= 0.5f;
+    st[1] = 0.f;
+  } else {
+    st[2] += 1.f;
+    if (use_scaler) {
+      st[1] += 1.f;
+      if (st[1] >= 2000.f) { st[0] *= 2.f; st[1] = 0.f; }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// plan
+// ----------------------------------------------------------------------------------------------
+static int head_prepare(acez_head_plan* h, int rows, int training) {
+  if (h->prepared_rows == rows && h->prepared_training >= training) return ACEZ_OK;
+  const int L = h->L;
+  h->fwd.assign(L, GemmLaunch{});
+  for (int l = 0; l < L; ++l) {
+    GemmProblem p{};
+    p.A = h->ACT + (size_t)l * h->act_stride;
+    p.B = h->W16 + (size_t)l * kC * kC;
+    p.a_mn = 0; p.b_mn = 0;
+    p.M = rows; p.N = kC; p.K = kC; p.batch = 1;
+    p.lda = kC; p.ldb = kC;
+    p.bn = 0;
+    p.epi = EPI_FWD;
+    int rc = gemm_prepare(&h->fwd[l], p);
+    if (rc) return rc;
+    GemmArgs& a = h->fwd[l].args;
+    a.bias = h->params + (size_t)l * kLayerStride + (size_t)kC * kC;
+    a.relu = 1;
+    a.ldo = kC;
+    const bool res_end = (l % 3 == 2) && (l < 3 * h->nres);
+    if (res_end) {
+      const int k = l / 3;
+      // x -> XTRA[k] (ReLU mask for the backward), res = ACT[l-2] + x -> ACT[l+1]   (ace_network.py:126,133)
+      a.out = (h->XTRA != nullptr) ? h->XTRA + (size_t)k * h->act_stride : nullptr;  // nullptr: x is not kept
+      a.resid = h->ACT + (size_t)(l - 2) * h->act_stride;
+      a.out2 = h->ACT + (size_t)(l + 1) * h->act_stride;
+    } else {
+      a.out = h->ACT + (size_t)(l + 1) * h->act_stride;
+    }
+  }
+  if (training) {
+    h->dgrad.assign(L, GemmLaunch{});
+    for (int l = L - 1; l >= 1; --l) {
+      // gradient w.r.t. ACT[l] = DZ[l] * W_l, then through the ReLU of the layer that produced ACT[l]
+      GemmProblem p{};
+      p.A = h->DZ + (size_t)l * h->act_stride;
+      p.B = h->W16 + (size_t)l * kC * kC;  // [out, in] row-major: contraction over rows -> MN-major B
+      p.a_mn = 0; p.b_mn = 1;
+      p.M = rows; p.N = kC; p.K = kC; p.batch = 1;
+      p.lda = kC; p.ldb = kC;
+      p.bn = 0;
+      p.epi = EPI_DGRAD;
+      int rc = gemm_prepare(&h->dgrad[l], p);
+      if (rc) return rc;
+      GemmArgs& a = h->dgrad[l].args;
+      a.ldo = kC;
+      a.out = h->DZ + (size_t)(l - 1) * h->act_stride;
+      a.nonfinite = nullptr;  // patched per call
+      const bool is_res = (l % 3 == 0) && (l <= 3 * h->nres);
+      if (is_res) {
+        const int k = l / 3;  // ACT[l] = res_k = res_{k-1} + x_{l-1}
+        a.mask = h->XTRA + (size_t)(k - 1) * h->act_stride;
+        a.addend = (k < h->nres) ? h->GRES : nullptr;   // skip gradient from res_{k+1}
+        a.out2 = (k >= 2) ? h->GRES : nullptr;          // res_{k-1} needs it (res_0 = features has no grad)
+      } else {
+        a.mask = h->ACT + (size_t)l * h->act_stride;
+      }
+    }
+    // all weight gradients in one launch: grid.z = layer, no split-K, plain fp32 stores
+    GemmProblem p{};
+    p.A = h->DZ; p.B = h->ACT;
+    p.a_mn = 1; p.b_mn = 1;
+    p.M = kC; p.N = kC; p.K = (rows + 63) / 64 * 64; p.batch = L;
+    p.a_zstride = (long long)h->act_stride; p.b_zstride = (long long)h->act_stride;
+    p.lda = kC; p.ldb = kC;
+    p.bn = 128;
+    p.epi = EPI_WGRAD;
+    int rc = gemm_prepare(&h->wgrad, p);
+    if (rc) return rc;
+    // contraction rows beyond `rows` must read as zero: rebuild the maps with the true row count so TMA zero-fills
+    {
+      uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, (uint64_t)L};
+      uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)h->act_stride * 2};
+      uint32_t box[3] = {64, 64, 1};
+      rc = make_tensor_map(&h->wgrad.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->DZ, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tensor_map(&h->wgrad.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->ACT, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    GemmArgs& a = h->wgrad.args;
+    a.out32 = h->grads;
+    a.out32_zstride = (long long)kLayerStride;
+    a.ldo32 = kC;
+    a.bias_grad = h->grads + (size_t)kC * kC;
+    a.bias_grad_zstride = (long long)kLayerStride;
+  }
+  h->prepared_rows = rows;
+  h->prepared_training = training;
+  return ACEZ_OK;
+}
+
+static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
+  t.rows = rows;
+  t.C3 = h->C3;
+  t.use_homogeneous = h->cfg.use_homogeneous;
+  for (int i = 0; i < 3; ++i) t.mean[i] = h->cfg.mean[i];
+  t.h_beta = h->cfg.h_beta;
+  t.max_inv_scale = h->cfg.max_inv_scale;
+  t.min_inv_scale = h->cfg.min_inv_scale;
+  t.x = h->ACT + (size_t)h->L * h->act_stride;
+  t.W3h = h->W3h;
+  t.b3 = h->params + (size_t)h->L * kLayerStride + (size_t)h->C3 * kC;
+}
+
+static int tail_grid(int rows) {
+  const int per_block = kTailThreads / 32;
+  int g = (rows + per_block - 1) / per_block;
+  const int cap = 2 * sm_count();
+  return g < cap ? (g < 1 ? 1 : g) : cap;
+}
+
+}  // namespace acez
+
+// ----------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------
+using namespace acez;
+
+extern "C" size_t acez_head_param_count(const acez_head_config* cfg) {
+  if (!cfg || cfg->num_res_blocks < 1) return 0;
+  const int L = 3 * cfg->num_res_blocks + 2;
+  const int C3 = cfg->use_homogeneous ? 4 : 3;
+  return (size_t)L * kLayerStride + (size_t)C3 * kC + C3;
+}
+
+extern "C" size_t acez_head_workspace_bytes(const acez_head_config* cfg) {
+  if (!cfg || cfg->num_res_blocks < 1 || cfg->max_rows < 1) return 0;
+  return head_layout(*cfg).total + 1024;
+}
+
+extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params, float* grads, void* workspace,
+                                     size_t workspace_bytes, acez_head_plan** out) {
+  ACEZ_REQUIRE(cfg && params && workspace && out, "head_plan_create: null argument");
+  ACEZ_REQUIRE(cfg->num_res_blocks >= 1 && cfg->num_res_blocks <= 16, "head_plan_create: num_res_blocks out of range");
+  ACEZ_REQUIRE(cfg->max_rows >= 1, "head_plan_create: max_rows must be positive");
+  ACEZ_REQUIRE(!cfg->training || grads != nullptr, "head_plan_create: training plan needs a gradient buffer");
+  ACEZ_REQUIRE(workspace_bytes >= acez_head_workspace_bytes(cfg), "head_plan_create: workspace too small (%zu < %zu)",
+               workspace_bytes, acez_head_workspace_bytes(cfg));
+  acez_head_plan* h = new acez_head_plan();
+  h->cfg = *cfg;
+  h->nres = cfg->num_res_blocks;
+  h->L = 3 * h->nres + 2;
+  h->C3 = cfg->use_homogeneous ? 4 : 3;
+  h->n_params = acez_head_param_count(cfg);
+  h->params = params;
+  h->grads = grads;
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 1024));
+  const HeadLayout lo = head_layout(*cfg);
+  h->W16 = reinterpret_cast<__half*>(base + lo.w16);
+  h->W3h = reinterpret_cast<__half*>(base + lo.w3h);
+  h->ACT = reinterpret_cast<__half*>(base + lo.act);
+  h->XTRA = cfg->training ? reinterpret_cast<__half*>(base + lo.xtra) : nullptr;
+  h->DZ = cfg->training ? reinterpret_cast<__half*>(base + lo.dz) : nullptr;
+  h->GRES = cfg->training ? reinterpret_cast<__half*>(base + lo.gres) : nullptr;
+  h->act_stride = (size_t)cfg->max_rows * kC;
+  h->prepared_rows = -1;
+  h->prepared_training = 0;
+  *out = h;
+  return ACEZ_OK;
+}
+
+extern "C" void acez_head_plan_destroy(acez_head_plan* plan) { delete plan; }
+
+extern "C" int acez_head_sync_weights(acez_head_plan* h, acez_stream_t stream) {
+  ACEZ_REQUIRE(h != nullptr, "head_sync_weights: null plan");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cast_weights_kernel<<<4 * sm_count(), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(h->params, h->W16, h->W3h,
+                                                                                          h->L, h->C3);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" void* acez_head_input_ptr(acez_head_plan* h) { return h ? h->ACT : nullptr; }
+
+static int head_run_forward(acez_head_plan* h, const void* features, int rows, int training, cudaStream_t s) {
+  ACEZ_REQUIRE(rows >= 1 && rows <= h->cfg.max_rows, "head: rows=%d outside [1, %d]", rows, h->cfg.max_rows);
+  int rc = head_prepare(h, rows, training);
+  if (rc) return rc;
+  if (features != nullptr && features != h->ACT)
+    ACEZ_CUDA(cudaMemcpyAsync(h->ACT, features, (size_t)rows * kC * 2, cudaMemcpyDeviceToDevice, s));
+  for (int l = 0; l < h->L; ++l) {
+    rc = gemm_launch(h->fwd[l], s);
+    if (rc) return rc;
+  }
+  return ACEZ_OK;
+}
+
+extern "C" int acez_head_forward(acez_head_plan* h, const void* features, int rows, float* sc_out,
+                                 acez_stream_t stream) {
+  ACEZ_REQUIRE(h != nullptr && sc_out != nullptr, "head_forward: null argument");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  rc = head_run_forward(h, features, rows, 0, s);
+  if (rc) return rc;
+  TailArgs t{};
+  fill_tail_common(h, rows, t);
+  t.training = 0;
+  t.sc_out = sc_out;
+  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_loss_params* lp,
+                                       const acez_train_batch* b, float* stats, int* nonfinite,
+                                       acez_stream_t stream) {
+  ACEZ_REQUIRE(h && lp && b && stats && nonfinite, "head_train_fwd_bwd: null argument");
+  ACEZ_REQUIRE(h->cfg.training && h->grads, "head_train_fwd_bwd: plan was not created for training");
+  ACEZ_REQUIRE(b->target_px_b2 && b->K_b33 && b->Kinv_b33, "head_train_fwd_bwd: missing batch tensors");
+  ACEZ_REQUIRE(b->P_b34 || (b->aug_inv_b34 && b->pose_inv_b44), "head_train_fwd_bwd: need P_b34 or aug_inv+pose_inv");
+  ACEZ_REQUIRE(!lp->use_depth || b->target_crds_b3, "head_train_fwd_bwd: use_depth needs target_crds_b3");
+  ACEZ_REQUIRE(lp->divisor > 0, "head_train_fwd_bwd: divisor must be positive");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  rc = head_run_forward(h, b->features, rows, 1, s);
+  if (rc) return rc;
+  const int L = h->L;
+  float* gW3 = h->grads + (size_t)L * kLayerStride;
+  ACEZ_CUDA(cudaMemsetAsync(gW3, 0, ((size_t)h->C3 * kC + h->C3) * sizeof(float), s));
+  ACEZ_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
+  ACEZ_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), s));
+  TailArgs t{};
+  fill_tail_common(h, rows, t);
+  t.training = 1;
+  t.sc_out = b->sc_out_b3;
+  t.lp = *lp;
+  t.tpx = b->target_px_b2; t.Pin = b->P_b34; t.A = b->aug_inv_b34; t.T = b->pose_inv_b44;
+  t.K = b->K_b33; t.Kinv = b->Kinv_b33; t.G = b->target_crds_b3;
+  t.d_P = b->d_P_b34; t.d_Kdiag = b->d_Kdiag_b2;
+  t.grad_scale_dev = b->grad_scale_dev;
+  t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
+  t.gW3 = gW3;
+  t.gb3 = gW3 + (size_t)h->C3 * kC;
+  t.stats = stats;
+  t.nonfinite = nonfinite;
+  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
+  ACEZ_CUDA(cudaGetLastError());
+  for (int l = L - 1; l >= 1; --l) {
+    h->dgrad[l].args.nonfinite = nonfinite;
+    rc = gemm_launch(h->dgrad[l], s);
+    if (rc) return rc;
+  }
+  return gemm_launch(h->wgrad, s);
+}
+
+extern "C" int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_bytes, void* dst,
+                                acez_stream_t stream) {
+  ACEZ_REQUIRE(src && idx && dst && rows >= 0 && row_bytes > 0 && (row_bytes & 1) == 0, "gather_rows: bad arguments");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  if (rows == 0) return ACEZ_OK;
+  const int threads = 256;
+  const int grid = (rows * 32 + threads - 1) / threads;
+  gather_rows_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(src), idx, rows, row_bytes, reinterpret_cast<uint8_t*>(dst));
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                               const float* hyper_dev, float* scaler_state_dev, int* found_inf_dev, int use_scaler,
+                               acez_head_plan* plan, acez_stream_t stream) {
+  ACEZ_REQUIRE(params && grads && exp_avg && exp_avg_sq && hyper_dev && scaler_state_dev && found_inf_dev,
+               "adamw_step: null argument");
+  ACEZ_REQUIRE(plan == nullptr || (plan->params == params && plan->n_params == n),
+               "adamw_step: plan does not own this parameter buffer");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = 8 * sm_count();
+  if (use_scaler) {
+    grad_check_kernel<<<grid, 256, 0, s>>>(grads, n, found_inf_dev);
+    ACEZ_CUDA(cudaGetLastError());
+  }
+  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, hyper_dev, scaler_state_dev, found_inf_dev,
+                                    use_scaler, plan ? plan->W16 : nullptr, plan ? plan->W3h : nullptr,
+                                    plan ? plan->L : 0, plan ? plan->C3 : 0);
+  ACEZ_CUDA(cudaGetLastError());
+  scaler_update_kernel<<<1, 32, 0, s>>>(scaler_state_dev, found_inf_dev, use_scaler);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}

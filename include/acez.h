@@ -1,0 +1,259 @@
+/*
+ * acez.h — C ABI of libacez.so, the sm_100a (B200) implementation of the ACE Zero hot path.
+ *
+ * This is the drop-in boundary for the one native operator of the reference (the `dsacstar` pybind11 module,
+ * reference dsacstar/dsacstar.cpp:898-899, built by dsacstar/setup.py:28-38) and for the PyTorch library calls the
+ * reference's training / registration loops make on the hot path (ace_trainer.py:499-640, ace_network.py:41-149,
+ * ace_loss.py:39-90, ace_schedule.py:106-126, register_mapping.py:201-251).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, `int` status return (0 = ok), no exceptions, no torch types;
+ *   - every buffer is caller-owned (the Python side allocates them with torch); the library never allocates
+ *     device memory. Opaque `*_plan` handles hold only host-side metadata (TMA tensor maps, pointers);
+ *   - `acez_stream_t` is a `cudaStream_t`; all work is enqueued on it, nothing synchronises the host
+ *     unless documented;
+ *   - there is no CPU path: without an sm_100a device every compute entry returns ACEZ_ERR_NO_DEVICE /
+ *     ACEZ_ERR_UNSUPPORTED and sets acez_last_error().
+ */
+#ifndef ACEZ_H_
+#define ACEZ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACEZ_VERSION 100
+
+#define ACEZ_OK 0
+#define ACEZ_ERR_INVALID 1
+#define ACEZ_ERR_CUDA 2
+#define ACEZ_ERR_UNSUPPORTED 3
+#define ACEZ_ERR_NO_DEVICE 4
+
+typedef void* acez_stream_t; /* cudaStream_t */
+
+int acez_version(void);
+/* Thread-local message of the last failing call. */
+const char* acez_last_error(void);
+/* 0 iff a compute-capability-10.x device is current. */
+int acez_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generic fp16 tensor-core GEMM (tcgen05 + TMA). Building block of the head and encoder; exported for the parity
+ * tests. D[z] = A[z] * B[z]; K-major operand = [rows, K] row-major, MN-major operand = [K, rows] row-major.
+ * Replaces: cuDNN/cuBLAS dispatches of nn.Conv2d(…,1,1,0) in reference ace_network.py:122-137.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ACEZ_EPI_FWD 0   /* out = fp16(act(acc + fp16(bias))), out2 = fp16(resid + out) */
+#define ACEZ_EPI_DGRAD 1 /* v = fp16(acc) (+ addend); out2 = v; out = mask > 0 ? v : 0 */
+#define ACEZ_EPI_F32 2   /* out32 = acc; optional bias_grad[m] = sum_k A[m,k] */
+
+typedef struct acez_gemm_desc {
+  const void* A; /* fp16 */
+  const void* B; /* fp16 */
+  int a_mn_major, b_mn_major;
+  int M, N, K, batch;
+  long long a_zstride, b_zstride; /* elements, used when batch > 1 */
+  int lda, ldb;                   /* elements */
+  int bn;                         /* 0 = auto, else 64 / 128 / 256 */
+  int epilogue;
+  const float* bias;  /* [N] fp32, nullable */
+  const void* resid;  /* fp16 [M,ldo], nullable */
+  const void* mask;   /* fp16 [M,ldo], ACEZ_EPI_DGRAD */
+  const void* addend; /* fp16 [M,ldo], nullable */
+  void* out;          /* fp16 [M,ldo] */
+  void* out2;         /* fp16 [M,ldo], nullable */
+  int ldo;
+  int relu;
+  int* nonfinite; /* nullable */
+  float* out32;   /* ACEZ_EPI_F32: [batch][M,ldo32] */
+  long long out32_zstride;
+  int ldo32;
+  float* bias_grad; /* nullable, [batch][M] */
+  long long bias_grad_zstride;
+  /* 0 = library defaults; non-zero values override the UMMA shared-memory descriptor constants (test probing) */
+  unsigned a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+} acez_gemm_desc;
+
+int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused reprojection loss + backward.
+ * Replaces: reference ace_trainer.py:521-613 (pose compose, projection, masks, loss) + ace_loss.py:39-90 and
+ * the autograd backward of that graph (ace_schedule.py:106-107), ~40 ATen kernels and 3 host syncs.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ACEZ_LOSS_TANH 0    /* w * tanh(r / w); dyntanh = same with the host-computed per-iteration weight */
+#define ACEZ_LOSS_L1 1      /* r where r <= soft_clamp */
+#define ACEZ_LOSS_L1_SQRT 2 /* + sqrt(soft_clamp * r) above */
+#define ACEZ_LOSS_L1_LOG 3  /* + log(1 + soft_clamp * r) above */
+
+typedef struct acez_loss_params {
+  int loss_type;
+  float loss_weight;   /* tanh weight (ace_loss.py:53-69) or soft_clamp for the l1 family (ace_loss.py:72-90) */
+  float depth_min;     /* 0.1  train_ace.py depth_min  */
+  float depth_max;     /* 1000 */
+  float hard_clamp;    /* 1000 repro_loss_hard_clamp */
+  float inlier_px;     /* 10   learning_rate_cooldown_trigger_px_threshold */
+  float depth_target;  /* 10 */
+  int use_depth;       /* GT scene coordinates present (ace_trainer.py:567-574, 602-609) */
+  float grad_scale;    /* GradScaler scale S (ace_schedule.py:107); gradients are emitted multiplied by it */
+  int divisor;         /* batch size b of `loss /= batch_size` (ace_trainer.py:613); the GLOBAL b under data parallel */
+} acez_loss_params;
+
+/* stats[0] += sum of per-row losses / divisor (unscaled), stats[1] += #valid rows with r < inlier_px,
+ * stats[2] += #valid rows, stats[3] = 1 if any non-finite loss term was seen. Caller zeroes stats. */
+int acez_repro_loss_fwd_bwd(const acez_loss_params* p, int rows,
+                            const float* sc_b3,          /* predicted scene coordinates */
+                            const float* target_px_b2,   /* pixel targets */
+                            const float* P_b34,          /* nullable: composed world->cam; else aug_inv * pose_inv */
+                            const float* aug_inv_b34, const float* pose_inv_b44,
+                            const float* K_b33, const float* Kinv_b33,
+                            const float* target_crds_b3, /* nullable unless use_depth */
+                            float* d_sc_b3,              /* out */
+                            float* d_P_b34,              /* out, nullable */
+                            float* d_Kdiag_b2,           /* out, nullable: dL/dK00, dL/dK11 per row */
+                            float* stats, acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ACE head (ace_network.Head, reference ace_network.py:62-149): plan-based forward / training step.
+ * Flat fp32 parameter layout (shared by params, grads, exp_avg, exp_avg_sq):
+ *   for each hidden layer l in [res3_conv1, res3_conv2, res3_conv3, {i}c0, {i}c1, {i}c2 ..., fc1, fc2]:
+ *        W_l [512,512] row-major (out, in), then b_l [512]
+ *   then fc3: W [C3,512], b [C3]   (C3 = 4 homogeneous, else 3)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct acez_head_plan acez_head_plan;
+
+typedef struct acez_head_config {
+  int num_res_blocks;   /* 1 + num_head_blocks */
+  int use_homogeneous;
+  int max_rows;         /* capacity of one forward / training batch (multiple of 128 recommended) */
+  int training;         /* allocate backward buffers */
+  float mean[3];
+  float h_beta;         /* ace_network.py:113 */
+  float max_inv_scale;  /* ace_network.py:112 */
+  float min_inv_scale;  /* ace_network.py:114 */
+} acez_head_config;
+
+size_t acez_head_param_count(const acez_head_config* cfg);
+size_t acez_head_workspace_bytes(const acez_head_config* cfg);
+
+int acez_head_plan_create(const acez_head_config* cfg, float* params, float* grads /* nullable unless training */,
+                          void* workspace, size_t workspace_bytes, acez_head_plan** out);
+void acez_head_plan_destroy(acez_head_plan* plan);
+
+/* fp32 master weights -> fp16 shadow copies the GEMMs read (autocast's weight cast). */
+int acez_head_sync_weights(acez_head_plan* plan, acez_stream_t stream);
+/* Device pointer of the plan's input activation buffer [max_rows,512] fp16 (gather target). */
+void* acez_head_input_ptr(acez_head_plan* plan);
+
+/* Forward only (registration; ace_network.py:120-149 under autocast): features -> scene coordinates.
+ * features: fp16 [rows,512] (nullable = already in the plan's input buffer); sc_out: fp32 [rows,3]. */
+int acez_head_forward(acez_head_plan* plan, const void* features, int rows, float* sc_out, acez_stream_t stream);
+
+typedef struct acez_train_batch {
+  const void* features;        /* fp16 [rows,512]; nullable = already in the plan's input buffer */
+  const float* target_px_b2;
+  const float* P_b34;          /* nullable (see acez_repro_loss_fwd_bwd) */
+  const float* aug_inv_b34;
+  const float* pose_inv_b44;
+  const float* K_b33;
+  const float* Kinv_b33;
+  const float* target_crds_b3; /* nullable */
+  float* d_P_b34;              /* nullable out */
+  float* d_Kdiag_b2;           /* nullable out */
+  float* sc_out_b3;            /* nullable out: predicted scene coordinates (fp32) */
+  const float* grad_scale_dev; /* nullable: device scalar overriding loss_params.grad_scale (= scaler_state[0]) */
+} acez_train_batch;
+
+/* One head forward + reprojection loss + full backward into `grads` (overwritten, scaled by grad_scale).
+ * stats: [4] floats as in acez_repro_loss_fwd_bwd, zeroed by the call. nonfinite (int, device) is zeroed and set
+ * to 1 if any activation gradient overflowed fp16. Replaces ace_trainer.py:516-627. */
+int acez_head_train_fwd_bwd(acez_head_plan* plan, int rows, const acez_loss_params* lp, const acez_train_batch* batch,
+                            float* stats, int* nonfinite, acez_stream_t stream);
+
+/* Gather rows of the patch buffer into a batch (reference ace_trainer.py:485-494, 8 index kernels):
+ * dst[i, :] = src[idx[i], :], row_bytes multiple of 2. */
+int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_bytes, void* dst, acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GradScaler unscale + inf check + AdamW + GradScaler.update, entirely on the device (CUDA-graph capturable, no
+ * host sync). Replaces ace_schedule.py:109-113 (scaler.step(optimizer); scaler.update()) with torch.optim.AdamW
+ * defaults semantics (ace_schedule.py:15,30,63) and torch.cuda.amp.GradScaler defaults (init 65536, x2 / 2000 clean
+ * steps, x0.5 on inf, step skipped on inf).
+ *   hyper_dev        float[5]: lr, beta1, beta2, eps, weight_decay (host-written per iteration)
+ *   scaler_state_dev float[4]: [0] scale S, [1] growth tracker, [2] optimizer step count t (bias correction), [3] -
+ *   found_inf_dev    int: OR-ed with the grads' non-finite / fp16-overflow check; must already hold the activation-
+ *                    gradient overflow flag of acez_head_train_fwd_bwd (same pointer). Not cleared by this call.
+ *   use_scaler       0: plain AdamW (use_half False): no check, no unscale, no skip
+ * Also refreshes the head's fp16 weight shadow when `plan` is non-null.
+ * ---------------------------------------------------------------------------------------------------------- */
+int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                    const float* hyper_dev, float* scaler_state_dev, int* found_inf_dev, int use_scaler,
+                    acez_head_plan* plan, acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * DSAC* pose solver. Replaces the reference's native operator:
+ *   dsacstar.forward_rgb(sceneCoordinates[1,3,H,W] f32 CPU, outPose[4,4] f32 CPU, ransacHypotheses, inlierThreshold,
+ *                        focalLength, ppointX, ppointY, inlierAlpha, maxReproj, subSampling, randomSeed,
+ *                        max_hypotheses_tries) -> int inliers          (dsacstar/dsacstar.cpp:66-186, 898-899)
+ * batched over n images, device pointers, per-image intrinsics.
+ *   - sampling RNG: counter-based, keyed (seed, image index + image_index_base, hypothesis, try, draw) — results do
+ *     not depend on batch composition or GPU count (the reference's mt19937-per-OMP-thread stream is not
+ *     reproducible across machines);
+ *   - injected_idx (nullable) int32 [n, hyps, 4, 2] = (x, y) cell of each of the 4 correspondences: overrides the
+ *     RNG and disables retries (parity tests feed the oracle's minimal sets);
+ *   - out_pose: camera->world 4x4 row-major float (dsacstar.cpp:177-182); out_inliers: size of the inlier set the
+ *     final pose was fitted to (dsacstar.cpp:185).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct acez_dsac_params {
+  int hyps;
+  float inlier_threshold; /* px */
+  float inlier_alpha;
+  float max_reproj;
+  int subsample;          /* 8 */
+  uint64_t seed;
+  int max_tries;
+  int max_refine_steps;   /* reference MAX_REF_STEPS = 100 (dsacstar.cpp:47) */
+  int image_index_base;   /* added to the in-batch image index for RNG keying */
+} acez_dsac_params;
+
+typedef struct acez_dsac_debug { /* all nullable; device pointers */
+  float* hyp_poses;  /* [n, hyps, 6]: rvec(3), tvec(3) scene->camera of every hypothesis */
+  float* hyp_scores; /* [n, hyps] soft inlier scores */
+  int* best;         /* [n] index of the winning hypothesis */
+  int* hyp_tries;    /* [n, hyps] number of tries used */
+  int* refine_rounds;/* [n] accepted refinement rounds */
+} acez_dsac_debug;
+
+size_t acez_dsac_workspace_bytes(int n, int h, int w, int hyps);
+
+int acez_dsac_forward_rgb_batch(const float* sc /* [n,3,h,w] device */, int n, int h, int w,
+                                const float* focal /* [n] */, const float* ppx /* [n] */, const float* ppy /* [n] */,
+                                const acez_dsac_params* p, const int* injected_idx, float* out_pose /* [n,4,4] */,
+                                int* out_inliers /* [n] */, const acez_dsac_debug* dbg, void* workspace,
+                                size_t workspace_bytes, acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ACE encoder (ace_network.Encoder, reference ace_network.py:14-59): 11 convolutions, 1 -> 512 channels at 1/8
+ * resolution. Weights are frozen; the plan packs them to fp16 once.
+ * image: fp16 or fp32 [n,1,H,W]; features out: fp16 NHWC [n, h8, w8, 512] == the reference's `normalize_shape`
+ * row order per image (ace_trainer.py:399-401).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct acez_encoder_plan acez_encoder_plan;
+
+size_t acez_encoder_workspace_bytes(int max_n, int max_h, int max_w);
+/* weights: 22 device pointers in state_dict order (conv1.weight, conv1.bias, ..., res2_skip.weight, res2_skip.bias),
+ * fp32, PyTorch OIHW layout. */
+int acez_encoder_plan_create(const float* const* weights, int max_n, int max_h, int max_w, void* workspace,
+                             size_t workspace_bytes, acez_stream_t stream, acez_encoder_plan** out);
+void acez_encoder_plan_destroy(acez_encoder_plan* plan);
+int acez_encoder_out_hw(int H, int W, int* h8, int* w8);
+int acez_encoder_forward(acez_encoder_plan* plan, const void* image, int image_is_fp16, int n, int H, int W,
+                         void* features_out, acez_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACEZ_H_ */
