@@ -1,0 +1,200 @@
+"""Host side of the ACE head: owns the flat fp32 parameter / gradient / AdamW-state buffers and the plan of
+libacez.so (C ABI `acez_head_*`, `acez_adamw_step`). Mirrors the role of `ace_network.Head` + `ScheduleACE`'s
+optimiser and GradScaler in the reference (ace_network.py:62-149, ace_schedule.py:106-126).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+HEAD_CHANNELS = 512
+LAYER_STRIDE = 512 * 512 + 512
+
+LOSS_TYPES = {"tanh": 0, "dyntanh": 0, "l1": 1, "l1+sqrt": 2, "l1+logl1": 3, "l1+log": 3}
+
+
+def head_layer_names(num_head_blocks):
+    names = ["res3_conv1", "res3_conv2", "res3_conv3"]
+    for b in range(num_head_blocks):
+        names += [f"{b}c0", f"{b}c1", f"{b}c2"]
+    return names + ["fc1", "fc2"]
+
+
+class HeadEngine:
+    """Flat-buffer head. `params` is one fp32 CUDA tensor; `views()` exposes reference-named tensors aliasing it."""
+
+    def __init__(self, num_head_blocks=1, use_homogeneous=True, mean=(0.0, 0.0, 0.0), max_rows=5120, training=False,
+                 homogeneous_min_scale=0.01, homogeneous_max_scale=4.0, device="cuda"):
+        self.lib = _lib.load()
+        _lib.check(self.lib.acez_device_check(), "acez_device_check")
+        self.device = torch.device(device)
+        self.num_head_blocks = num_head_blocks
+        self.use_homogeneous = bool(use_homogeneous)
+        self.max_rows = int(max_rows)
+        self.training = bool(training)
+        self.names = head_layer_names(num_head_blocks)
+        self.L = len(self.names)
+        self.C3 = 4 if use_homogeneous else 3
+        self.max_inv_scale = 1.0 / homogeneous_max_scale
+        self.min_inv_scale = 1.0 / homogeneous_min_scale
+        self.h_beta = math.log(2) / (1.0 - self.max_inv_scale)
+        self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(3).clone()
+        self.cfg = self._config()
+        self.n_params = int(self.lib.acez_head_param_count(C.byref(self.cfg)))
+        assert self.n_params == self.L * LAYER_STRIDE + self.C3 * 512 + self.C3
+        self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
+        self.grads = torch.zeros(self.n_params, device=self.device, dtype=torch.float32) if training else None
+        self.exp_avg = torch.zeros_like(self.params) if training else None
+        self.exp_avg_sq = torch.zeros_like(self.params) if training else None
+        self.plan = None
+        self._build_plan()
+        # device-resident optimiser / GradScaler state (no host sync in the step)
+        self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01], device=self.device, dtype=torch.float32)
+        self.scaler_state = torch.tensor([65536.0, 0.0, 0.0, 0.0], device=self.device, dtype=torch.float32)
+        self.found_inf = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.stats = torch.zeros(4, device=self.device, dtype=torch.float32)
+        self._hyper_host = torch.empty(5, dtype=torch.float32).pin_memory()
+
+    # ------------------------------------------------------------------ plan / buffers
+    def _config(self):
+        cfg = _lib.HeadConfig()
+        cfg.num_res_blocks = 1 + self.num_head_blocks
+        cfg.use_homogeneous = int(self.use_homogeneous)
+        cfg.max_rows = self.max_rows
+        cfg.training = int(self.training)
+        for i in range(3):
+            cfg.mean[i] = float(self.mean[i])
+        cfg.h_beta = self.h_beta
+        cfg.max_inv_scale = self.max_inv_scale
+        cfg.min_inv_scale = self.min_inv_scale
+        return cfg
+
+    def _build_plan(self):
+        if self.plan is not None:
+            self.lib.acez_head_plan_destroy(self.plan)
+            self.plan = None
+        self.cfg = self._config()
+        ws_bytes = int(self.lib.acez_head_workspace_bytes(C.byref(self.cfg)))
+        if getattr(self, "workspace", None) is None or self.workspace.numel() < ws_bytes:
+            self.workspace = torch.empty(ws_bytes, device=self.device, dtype=torch.uint8)
+        plan = C.c_void_p()
+        rc = self.lib.acez_head_plan_create(C.byref(self.cfg), _lib.ptr(self.params), _lib.ptr(self.grads),
+                                            _lib.ptr(self.workspace), ws_bytes, C.byref(plan))
+        _lib.check(rc, "acez_head_plan_create")
+        self.plan = plan
+        in_ptr = self.lib.acez_head_input_ptr(self.plan)
+        self._input_off = in_ptr - self.workspace.data_ptr()
+
+    def resize(self, max_rows):
+        if max_rows > self.max_rows:
+            self.max_rows = int(max_rows)
+            self.workspace = None
+            self._build_plan()
+            self.sync_weights()
+
+    def set_mean(self, mean):
+        self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(3).clone().cpu()
+        self._build_plan()
+
+    def __del__(self):
+        try:
+            if self.plan is not None:
+                self.lib.acez_head_plan_destroy(self.plan)
+        except Exception:
+            pass
+
+    def input_buffer(self, rows):
+        """fp16 [rows,512] view of the plan's input activation buffer (write features here to skip a copy)."""
+        n = rows * 512 * 2
+        return self.workspace[self._input_off:self._input_off + n].view(torch.float16).view(rows, 512)
+
+    # ------------------------------------------------------------------ parameters
+    def views(self):
+        """dict name -> tensor view into `params` with the reference's state_dict names and OIHW shapes."""
+        out = {}
+        for l, n in enumerate(self.names):
+            o = l * LAYER_STRIDE
+            out[n + ".weight"] = self.params[o:o + 512 * 512].view(512, 512, 1, 1)
+            out[n + ".bias"] = self.params[o + 512 * 512:o + LAYER_STRIDE]
+        o = self.L * LAYER_STRIDE
+        out["fc3.weight"] = self.params[o:o + self.C3 * 512].view(self.C3, 512, 1, 1)
+        out["fc3.bias"] = self.params[o + self.C3 * 512:o + self.C3 * 512 + self.C3]
+        return out
+
+    def grad_views(self):
+        out = {}
+        for l, n in enumerate(self.names):
+            o = l * LAYER_STRIDE
+            out[n + ".weight"] = self.grads[o:o + 512 * 512].view(512, 512, 1, 1)
+            out[n + ".bias"] = self.grads[o + 512 * 512:o + LAYER_STRIDE]
+        o = self.L * LAYER_STRIDE
+        out["fc3.weight"] = self.grads[o:o + self.C3 * 512].view(self.C3, 512, 1, 1)
+        out["fc3.bias"] = self.grads[o + self.C3 * 512:o + self.C3 * 512 + self.C3]
+        return out
+
+    def load_state(self, sd):
+        v = self.views()
+        with torch.no_grad():
+            for k, t in v.items():
+                t.copy_(sd[k].to(self.device, torch.float32).reshape(t.shape))
+        if "mean" in sd:
+            self.set_mean(sd["mean"].reshape(3).float().cpu())
+        self.sync_weights()
+
+    def sync_weights(self, stream=None):
+        _lib.check(self.lib.acez_head_sync_weights(self.plan, _lib.stream_ptr(stream)), "acez_head_sync_weights")
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, features, out=None, stream=None):
+        """features: fp16 CUDA [rows,512] (or None = already written to input_buffer). Returns fp32 [rows,3]."""
+        rows = features.shape[0] if features is not None else out.shape[0]
+        if rows > self.max_rows:
+            self.resize(rows)
+        if features is not None:
+            if features.dtype != torch.float16:
+                features = features.half()
+            features = features.contiguous()
+        if out is None:
+            out = torch.empty((rows, 3), device=self.device, dtype=torch.float32)
+        rc = self.lib.acez_head_forward(self.plan, _lib.ptr(features), rows, _lib.ptr(out), _lib.stream_ptr(stream))
+        _lib.check(rc, "acez_head_forward")
+        return out
+
+    # ------------------------------------------------------------------ training
+    def loss_params(self, loss_type, loss_weight, divisor, use_depth=False, depth_min=0.1, depth_max=1000.0,
+                    hard_clamp=1000.0, inlier_px=10.0, depth_target=10.0, grad_scale=1.0):
+        return _lib.LossParams(LOSS_TYPES[loss_type], float(loss_weight), depth_min, depth_max, hard_clamp, inlier_px,
+                               depth_target, int(use_depth), float(grad_scale), int(divisor))
+
+    def train_fwd_bwd(self, rows, lp, target_px, K, Kinv, aug_inv=None, pose_inv=None, P=None, target_crds=None,
+                      features=None, d_P=None, d_Kdiag=None, sc_out=None, use_device_scale=True, stream=None):
+        tb = _lib.TrainBatch()
+        tb.features = features.data_ptr() if features is not None else None
+        tb.target_px_b2 = target_px.data_ptr()
+        tb.P_b34 = P.data_ptr() if P is not None else None
+        tb.aug_inv_b34 = aug_inv.data_ptr() if aug_inv is not None else None
+        tb.pose_inv_b44 = pose_inv.data_ptr() if pose_inv is not None else None
+        tb.K_b33 = K.data_ptr()
+        tb.Kinv_b33 = Kinv.data_ptr()
+        tb.target_crds_b3 = target_crds.data_ptr() if target_crds is not None else None
+        tb.d_P_b34 = d_P.data_ptr() if d_P is not None else None
+        tb.d_Kdiag_b2 = d_Kdiag.data_ptr() if d_Kdiag is not None else None
+        tb.sc_out_b3 = sc_out.data_ptr() if sc_out is not None else None
+        tb.grad_scale_dev = self.scaler_state.data_ptr() if use_device_scale else None
+        rc = self.lib.acez_head_train_fwd_bwd(self.plan, rows, C.byref(lp), C.byref(tb), _lib.ptr(self.stats),
+                                              _lib.ptr(self.found_inf), _lib.stream_ptr(stream))
+        _lib.check(rc, "acez_head_train_fwd_bwd")
+
+    def set_hyper(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, stream=None):
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4] = lr, beta1, beta2, eps, weight_decay
+        self.hyper.copy_(h, non_blocking=True)
+
+    def adamw_step(self, use_scaler=True, stream=None):
+        rc = self.lib.acez_adamw_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg),
+                                      _lib.ptr(self.exp_avg_sq), self.n_params, _lib.ptr(self.hyper),
+                                      _lib.ptr(self.scaler_state), _lib.ptr(self.found_inf), int(use_scaler), self.plan,
+                                      _lib.stream_ptr(stream))
+        _lib.check(rc, "acez_adamw_step")

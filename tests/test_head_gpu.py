@@ -1,0 +1,151 @@
+"""GPU parity of the ACE head kernels (tcgen05 GEMM chain, fused tail, AdamW/GradScaler) against the CPU oracle in
+its autocast-emulating mode. Tolerances are stated per check; they cover fp16 activation rounding flips caused by a
+different fp32 summation order inside the GEMMs (the oracle sums in torch's CPU order, the tensor core in its own)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ace_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(nb, homog, rows, training, mean=(0.0, 0.0, 0.0), seed=200):
+    from acezero_b200.head import HeadEngine
+    sd = ace_ref.make_head_state(seed, nb, homog, mean=mean)
+    eng = HeadEngine(nb, homog, mean, max_rows=rows, training=training)
+    eng.load_state(sd)
+    return eng, sd
+
+
+@pytest.mark.parametrize("nb,homog,rows", [(1, True, 640), (2, False, 384), (1, True, 5120), (1, True, 4800 + 77)])
+def test_head_forward_matches_oracle(nb, homog, rows):
+    eng, sd = _engine(nb, homog, rows, False, mean=(0.3, -0.2, 1.5))
+    feats = ace_ref.synth_batch(11, rows)["features"]
+    sc = eng.forward(feats.cuda()).cpu()
+    with torch.no_grad():
+        ref = ace_ref.head_forward(sd, feats.float(), nb, homog, emulate_half=True)
+    err = (sc - ref).abs()
+    # tolerance: 5e-3 absolute on coordinates of magnitude ~1 (a few fp16 ulps of the last hidden activations)
+    assert err.max() < 5e-3, f"max abs err {err.max():.3e}"
+    assert err.mean() < 5e-4
+
+
+def _run_step(eng, bt, lp_kwargs, rows, want_dP=False):
+    dev = eng.device
+    g = {k: v.to(dev) for k, v in bt.items()}
+    sc_out = torch.empty((rows, 3), device=dev)
+    dP = torch.empty((rows, 3, 4), device=dev) if want_dP else None
+    dK = torch.empty((rows, 2), device=dev) if want_dP else None
+    lp = eng.loss_params(divisor=rows, **lp_kwargs)
+    eng.train_fwd_bwd(rows, lp, g["target_px"], g["intrinsics"], g["intrinsics_inv"], aug_inv=g["aug_poses_inv"],
+                      pose_inv=g["poses_inv"], target_crds=g["target_crds"], features=g["features"], d_P=dP,
+                      d_Kdiag=dK, sc_out=sc_out)
+    torch.cuda.synchronize()
+    return sc_out, dP, dK
+
+
+@pytest.mark.parametrize("loss_type,use_depth", [("dyntanh", False), ("l1+sqrt", True), ("l1", False), ("l1+log", False)])
+def test_train_fwd_bwd_matches_oracle(loss_type, use_depth):
+    """One forward + loss + backward: loss, inlier count and every parameter gradient against autograd through the
+    oracle (emulate_half=True). Scale 1024 keeps fp16 gradients finite so that all of them can be compared."""
+    rows, S, it = 1024, 1024.0, 10
+    eng, sd = _engine(1, True, rows, True)
+    eng.scaler_state[0] = S
+    bt = ace_ref.synth_batch(301, rows, with_depth=use_depth)
+    opts = ace_ref.LossOptions(repro_loss_type=loss_type, use_depth=use_depth, iterations=1000)
+    w = ace_ref.loss_weight(opts, it)
+    _run_step(eng, bt, dict(loss_type=loss_type, loss_weight=w, use_depth=use_depth), rows)
+    stats = eng.stats.cpu().numpy()
+    assert int(eng.found_inf.item()) == 0
+
+    tr = ace_ref.TrainerRef(sd, 1, True, opts, lambda i: 1e-3, emulate_half=True)
+    tr.iteration = it
+    sc = tr.forward(bt["features"].float())
+    loss, inl, n_valid = ace_ref.training_loss(opts, sc, bt["target_px"], bt["aug_poses_inv"], bt["poses_inv"],
+                                               bt["intrinsics"], bt["intrinsics_inv"], bt["target_crds"], it)
+    (loss * S).backward()
+    assert stats[3] == 0
+    # rows whose error sits within fp16 noise of a mask / inlier threshold may flip: allow 3 of 1024
+    assert abs(stats[2] - n_valid) <= 3, (stats, n_valid)
+    assert abs(stats[1] - inl * rows) <= 3
+    assert abs(stats[0] - float(loss)) <= 2e-3 * abs(float(loss)) + 1e-3, (stats[0], float(loss))
+    gv = eng.grad_views()
+    for name in tr.names:
+        for sfx in (".weight", ".bias"):
+            ref = tr.sd[name + sfx].grad.reshape(-1)
+            got = gv[name + sfx].reshape(-1).cpu()
+            rel = (got - ref).norm() / (ref.norm() + 1e-12)
+            # 3e-2 relative L2: fp16 rounding of activations/gradients through up to 9 layers
+            assert rel < 3e-2, f"{name}{sfx}: rel L2 err {rel:.3e} (ref norm {ref.norm():.3e})"
+
+
+def test_pose_and_focal_gradients_match_autograd():
+    """dL/dP (b,3,4) and dL/dK diagonal emitted for the pose / calibration refiners against autograd."""
+    rows, S, it = 512, 256.0, 5
+    eng, sd = _engine(1, True, rows, True)
+    eng.scaler_state[0] = S
+    bt = ace_ref.synth_batch(302, rows)
+    opts = ace_ref.LossOptions(iterations=1000)
+    w = ace_ref.loss_weight(opts, it)
+    sc_out, dP, dK = _run_step(eng, bt, dict(loss_type="dyntanh", loss_weight=w), rows, want_dP=True)
+    # feed the kernel's own scene coordinates to the fp32 oracle so that only the loss math is compared
+    sc = sc_out.cpu()
+    P = torch.bmm(bt["aug_poses_inv"], bt["poses_inv"]).requires_grad_(True)
+    K = bt["intrinsics"].clone().requires_grad_(True)
+    loss, _, _ = ace_ref.training_loss(opts, sc, bt["target_px"], None, None, K, bt["intrinsics_inv"],
+                                       bt["target_crds"], it, P_b34=P)
+    (loss * S).backward()
+    np.testing.assert_allclose(dP.cpu().numpy(), P.grad.numpy(), rtol=2e-3, atol=2e-3 * float(P.grad.abs().max()))
+    kd = torch.stack([K.grad[:, 0, 0], K.grad[:, 1, 1]], 1)
+    np.testing.assert_allclose(dK.cpu().numpy(), kd.numpy(), rtol=2e-3, atol=2e-3 * float(kd.abs().max()))
+
+
+def test_training_trajectory_and_gradscaler():
+    """30 iterations with the real GradScaler dynamics (init 65536): the skip/backoff sequence, the loss trajectory and
+    the final weights follow the oracle."""
+    rows, iters = 1024, 30
+    eng, sd = _engine(1, True, rows, True)
+    opts = ace_ref.LossOptions(iterations=1000)
+    lr_fn = ace_ref.one_cycle_lr(0.005, 1000)
+    tr = ace_ref.TrainerRef(sd, 1, True, opts, lr_fn, emulate_half=True)
+    losses_ref, losses, scales_ref, scales = [], [], [], []
+    for it in range(iters):
+        bt = ace_ref.synth_batch(400 + it, rows)
+        l, _, _, _ = tr.step(bt["features"].float(), bt["target_px"], bt["aug_poses_inv"], bt["poses_inv"],
+                             bt["intrinsics"], bt["intrinsics_inv"], bt["target_crds"])
+        losses_ref.append(l)
+        scales_ref.append(tr.scale)
+        eng.set_hyper(lr_fn(it))
+        _run_step(eng, bt, dict(loss_type="dyntanh", loss_weight=ace_ref.loss_weight(opts, it)), rows)
+        losses.append(float(eng.stats[0]))
+        eng.adamw_step(use_scaler=True)
+        scales.append(float(eng.scaler_state[0]))
+    assert scales == scales_ref, (scales, scales_ref)
+    assert int(eng.scaler_state[2]) == iters - tr.skipped
+    np.testing.assert_allclose(losses, losses_ref, rtol=2e-2)
+    v = eng.views()
+    for k in ("res3_conv1.weight", "0c1.weight", "fc3.weight"):
+        ref = tr.sd[k].detach().reshape(-1)
+        got = v[k].reshape(-1).cpu()
+        # AdamW moves every weight by ~lr per step whatever the gradient scale: compare the *update*
+        upd_ref = ref - sd[k].reshape(-1)
+        upd = got - sd[k].reshape(-1)
+        rel = (upd - upd_ref).norm() / upd_ref.norm()
+        assert rel < 0.15, f"{k}: update rel err {rel:.3f}"
+
+
+def test_gather_rows_bit_exact():
+    from acezero_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    src = torch.randint(-30000, 30000, (5000, 512), generator=g, dtype=torch.int16).cuda()
+    idx = torch.randint(0, 5000, (1280,), generator=g, dtype=torch.int64).cuda()
+    dst = torch.empty((1280, 512), dtype=torch.int16, device="cuda")
+    _lib.check(lib.acez_gather_rows(_lib.ptr(src), _lib.ptr(idx), 1280, 1024, _lib.ptr(dst), _lib.stream_ptr()))
+    assert torch.equal(dst, src[idx])
+    src2 = torch.randn(777, 3, generator=g).cuda()  # 12-byte rows
+    dst2 = torch.empty((1280, 3), device="cuda")
+    idx2 = idx % 777
+    _lib.check(lib.acez_gather_rows(_lib.ptr(src2), _lib.ptr(idx2), 1280, 12, _lib.ptr(dst2), _lib.stream_ptr()))
+    assert torch.equal(dst2, src2[idx2])
