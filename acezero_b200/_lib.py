@@ -55,7 +55,7 @@ class TrainBatch(C.Structure):
         ("features", C.c_void_p), ("target_px_b2", C.c_void_p), ("P_b34", C.c_void_p),
         ("aug_inv_b34", C.c_void_p), ("pose_inv_b44", C.c_void_p), ("K_b33", C.c_void_p), ("Kinv_b33", C.c_void_p),
         ("target_crds_b3", C.c_void_p), ("d_P_b34", C.c_void_p), ("d_Kdiag_b2", C.c_void_p),
-        ("sc_out_b3", C.c_void_p), ("grad_scale_dev", C.c_void_p),
+        ("sc_out_b3", C.c_void_p), ("grad_scale_dev", C.c_void_p), ("loss_weight_dev", C.c_void_p),
     ]
 
 
@@ -81,7 +81,7 @@ EXPORTS = [
     "acez_version", "acez_last_error", "acez_device_check", "acez_gemm_f16", "acez_repro_loss_fwd_bwd",
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
     "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_forward", "acez_head_train_fwd_bwd",
-    "acez_gather_rows", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
+    "acez_gather_rows", "acez_gather_rows_multi", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
     "acez_encoder_forward",
 ]
@@ -114,6 +114,7 @@ def load():
     lib.acez_head_forward.argtypes = [vp, vp, i, vp, vp]
     lib.acez_head_train_fwd_bwd.argtypes = [vp, i, C.POINTER(LossParams), C.POINTER(TrainBatch), vp, vp, vp]
     lib.acez_gather_rows.argtypes = [vp, vp, i, i, vp, vp]
+    lib.acez_gather_rows_multi.argtypes = [vp, vp, vp, i, vp, i, vp]
     lib.acez_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, i, vp, vp]
     lib.acez_dsac_workspace_bytes.argtypes = [i, i, i, i]
     lib.acez_dsac_workspace_bytes.restype = C.c_size_t

@@ -84,6 +84,8 @@ const char* acez_last_error(void) { return acez::g_err; }
 int acez_version(void) { return ACEZ_VERSION; }
 
 int acez_device_check(void) {
+  static bool ok = false;  // cached: the check must not issue device queries inside a CUDA-graph capture
+  if (ok) return ACEZ_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -99,6 +101,7 @@ int acez_device_check(void) {
                     minor);
     return ACEZ_ERR_UNSUPPORTED;
   }
+  ok = true;
   return ACEZ_OK;
 }
 

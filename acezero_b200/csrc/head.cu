@@ -104,6 +104,30 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, const int64_
   }
 }
 
+// All arrays of the patch buffer in one launch: blockIdx.y selects the array (reference ace_trainer.py:485-494
+// issues 8 index kernels + 8 H2D index copies per iteration).
+struct MultiGather {
+  const uint8_t* src[8];
+  uint8_t* dst[8];
+  int row_bytes[8];
+};
+__global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows) {
+  const int a = blockIdx.y;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int rb = g.row_bytes[a];
+  const uint8_t* s = g.src[a] + (size_t)idx[warp] * rb;
+  uint8_t* d = g.dst[a] + (size_t)warp * rb;
+  if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(g.src[a]) | reinterpret_cast<uintptr_t>(g.dst[a])) & 15) == 0) {
+    for (int o = lane * 16; o < rb; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
+  } else if ((rb & 3) == 0) {
+    for (int o = lane * 4; o < rb; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+  } else {
+    for (int o = lane * 2; o < rb; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1] and the fc3 gradient)
 // one warp per row; lane owns columns [16*lane, 16*lane+16)
@@ -118,6 +142,7 @@ struct TailArgs {
   // training
   acez_loss_params lp;
   const float* grad_scale_dev;  // nullable: overrides lp.grad_scale (GradScaler state lives on the device)
+  const float* loss_weight_dev; // nullable: overrides lp.loss_weight (per-iteration dyntanh weight, graph-stable)
   const float* tpx; const float* Pin; const float* A; const float* T; const float* K; const float* Kinv; const float* G;
   float* d_P; float* d_Kdiag;
   __half* dz;           // DZ[L-1] [rows,512]
@@ -147,6 +172,7 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
 
   acez_loss_params lp = a.lp;
   if (a.training && a.grad_scale_dev != nullptr) lp.grad_scale = *a.grad_scale_dev;
+  if (a.training && a.loss_weight_dev != nullptr) lp.loss_weight = *a.loss_weight_dev;
 
   float accW[4][16];
 #pragma unroll
@@ -555,12 +581,13 @@ static int head_run_forward(acez_head_plan* h, const void* features, int rows, i
 
 extern "C" int acez_head_forward(acez_head_plan* h, const void* features, int rows, float* sc_out,
                                  acez_stream_t stream) {
-  ACEZ_REQUIRE(h != nullptr && sc_out != nullptr, "head_forward: null argument");
+  ACEZ_REQUIRE(h != nullptr, "head_forward: null plan");
   int rc = acez_device_check();
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   rc = head_run_forward(h, features, rows, 0, s);
   if (rc) return rc;
+  if (sc_out == nullptr) return ACEZ_OK;  // GEMM chain only (profiling)
   TailArgs t{};
   fill_tail_common(h, rows, t);
   t.training = 0;
@@ -598,6 +625,7 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   t.K = b->K_b33; t.Kinv = b->Kinv_b33; t.G = b->target_crds_b3;
   t.d_P = b->d_P_b34; t.d_Kdiag = b->d_Kdiag_b2;
   t.grad_scale_dev = b->grad_scale_dev;
+  t.loss_weight_dev = b->loss_weight_dev;
   t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
   t.gW3 = gW3;
   t.gb3 = gW3 + (size_t)h->C3 * kC;
@@ -623,6 +651,27 @@ extern "C" int acez_gather_rows(const void* src, const int64_t* idx, int rows, i
   const int grid = (rows * 32 + threads - 1) / threads;
   gather_rows_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint8_t*>(src), idx, rows, row_bytes, reinterpret_cast<uint8_t*>(dst));
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" int acez_gather_rows_multi(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
+                                      const int64_t* idx, int rows, acez_stream_t stream) {
+  ACEZ_REQUIRE(srcs && dsts && row_bytes && idx && n_arrays >= 1 && n_arrays <= 8 && rows >= 0,
+               "gather_rows_multi: bad arguments");
+  MultiGather g{};
+  for (int a = 0; a < n_arrays; ++a) {
+    ACEZ_REQUIRE(srcs[a] && dsts[a] && row_bytes[a] > 0 && (row_bytes[a] & 1) == 0, "gather_rows_multi: bad array %d", a);
+    g.src[a] = reinterpret_cast<const uint8_t*>(srcs[a]);
+    g.dst[a] = reinterpret_cast<uint8_t*>(dsts[a]);
+    g.row_bytes[a] = row_bytes[a];
+  }
+  int rc = acez_device_check();
+  if (rc) return rc;
+  if (rows == 0) return ACEZ_OK;
+  const int threads = 256;
+  dim3 grid((rows * 32 + threads - 1) / threads, n_arrays);
+  gather_rows_multi_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, idx, rows);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;
 }

@@ -51,11 +51,12 @@ class HeadEngine:
         self.plan = None
         self._build_plan()
         # device-resident optimiser / GradScaler state (no host sync in the step)
-        self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01], device=self.device, dtype=torch.float32)
+        # hyper: lr, beta1, beta2, eps, weight_decay (read by acez_adamw_step), [5] = loss weight of the iteration
+        self.hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 50.0, 0.0, 0.0], device=self.device, dtype=torch.float32)
         self.scaler_state = torch.tensor([65536.0, 0.0, 0.0, 0.0], device=self.device, dtype=torch.float32)
         self.found_inf = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.stats = torch.zeros(4, device=self.device, dtype=torch.float32)
-        self._hyper_host = torch.empty(5, dtype=torch.float32).pin_memory()
+        self._hyper_host = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 50.0, 0.0, 0.0]).pin_memory()
 
     # ------------------------------------------------------------------ plan / buffers
     def _config(self):
@@ -169,7 +170,8 @@ class HeadEngine:
                                depth_target, int(use_depth), float(grad_scale), int(divisor))
 
     def train_fwd_bwd(self, rows, lp, target_px, K, Kinv, aug_inv=None, pose_inv=None, P=None, target_crds=None,
-                      features=None, d_P=None, d_Kdiag=None, sc_out=None, use_device_scale=True, stream=None):
+                      features=None, d_P=None, d_Kdiag=None, sc_out=None, use_device_scale=True,
+                      use_device_loss_weight=False, stream=None):
         tb = _lib.TrainBatch()
         tb.features = features.data_ptr() if features is not None else None
         tb.target_px_b2 = target_px.data_ptr()
@@ -183,13 +185,17 @@ class HeadEngine:
         tb.d_Kdiag_b2 = d_Kdiag.data_ptr() if d_Kdiag is not None else None
         tb.sc_out_b3 = sc_out.data_ptr() if sc_out is not None else None
         tb.grad_scale_dev = self.scaler_state.data_ptr() if use_device_scale else None
+        tb.loss_weight_dev = (self.hyper.data_ptr() + 20) if use_device_loss_weight else None
         rc = self.lib.acez_head_train_fwd_bwd(self.plan, rows, C.byref(lp), C.byref(tb), _lib.ptr(self.stats),
                                               _lib.ptr(self.found_inf), _lib.stream_ptr(stream))
         _lib.check(rc, "acez_head_train_fwd_bwd")
 
-    def set_hyper(self, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, stream=None):
+    def set_hyper(self, lr, loss_weight=None, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
+        """Stage this iteration's host-computed scalars (pinned -> device, asynchronous, stream ordered)."""
         h = self._hyper_host
         h[0], h[1], h[2], h[3], h[4] = lr, beta1, beta2, eps, weight_decay
+        if loss_weight is not None:
+            h[5] = loss_weight
         self.hyper.copy_(h, non_blocking=True)
 
     def adamw_step(self, use_scaler=True, stream=None):

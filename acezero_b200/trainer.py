@@ -1,0 +1,302 @@
+"""Training loop core of ACE mapping on the sm_100a kernels: the part of the reference's `TrainerACE` that runs per
+iteration (ace_trainer.py:454-640) — epoch permutation, batch gather, head forward/backward with the fused
+reprojection loss, GradScaler + AdamW — with the patch buffer resident in HBM, one CUDA graph per iteration and no
+host synchronisation (the reference syncs >= 3 times per iteration, ace_trainer.py:578,586,615).
+
+Data parallel (world_size > 1): every rank holds the same buffer and draws the same permutation
+(`training_generator`, ace_trainer.py:79-80,466); rank r processes rows [r*b/G, (r+1)*b/G) of each batch; the loss
+divisor stays the global batch size (ace_trainer.py:613); head gradients are summed with one NCCL all-reduce and the
+GradScaler inf flag / loss statistics with a second, tiny one.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .head import HeadEngine
+
+BUFFER_KEYS = ("features", "target_px", "aug_poses_inv", "poses_inv", "intrinsics", "intrinsics_inv", "target_crds",
+               "pose_idx")
+ROW_BYTES = {"features": 1024, "target_px": 8, "aug_poses_inv": 48, "poses_inv": 64, "intrinsics": 36,
+             "intrinsics_inv": 36, "target_crds": 12, "pose_idx": 2}  # 1230 B / row (ace_trainer.py:330-340)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# learning-rate / loss schedules as functions of the iteration (ace_schedule.py:22-69, ace_loss.py:53-69)
+# ----------------------------------------------------------------------------------------------------------------
+def one_cycle_lr(max_lr, total_steps, pct_start=0.3, div_factor=25.0, final_div_factor=1e4):
+    """torch.optim.lr_scheduler.OneCycleLR(max_lr, total_steps, cycle_momentum=False) with torch defaults
+    (ace_schedule.py:62-69): the lr used by the optimiser step of iteration i."""
+    initial, minimum = max_lr / div_factor, max_lr / div_factor / final_div_factor
+    up_end = float(pct_start * total_steps) - 1
+    down_end = total_steps - 1
+
+    def cos(a, b, pct):
+        return b + (a - b) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+    def fn(i):
+        i = min(i, total_steps - 1)
+        if i <= up_end:
+            return cos(initial, max_lr, i / up_end)
+        return cos(max_lr, minimum, (i - up_end) / (down_end - up_end))
+    return fn
+
+
+class Schedule:
+    """ScheduleACE semantics (ace_schedule.py:8-126) without torch's scheduler objects: lr(i), cooldown trigger and
+    the mutable max_iterations."""
+
+    def __init__(self, o):
+        self.schedule = o.learning_rate_schedule
+        if self.schedule not in ("circle", "constant", "1cyclepoly"):
+            raise ValueError(f"Unknown learning rate schedule: {self.schedule}")
+        self.max_iterations = o.iterations
+        self.lr_min, self.lr_max = o.learning_rate_min, o.learning_rate_max
+        self.in_cooldown_phase = False
+        self.cooldown_start = None
+        self.buffer = []
+        if self.schedule == "circle":
+            self._fn = one_cycle_lr(self.lr_max, self.max_iterations)
+        elif self.schedule == "1cyclepoly":
+            self.warmup_iterations = o.learning_rate_warmup_iterations
+            self.warmup_lr = o.learning_rate_warmup_learning_rate
+            self.cooldown_iterations = o.learning_rate_cooldown_iterations
+            self.trigger = o.learning_rate_cooldown_trigger_percent_threshold
+        self.steps = 0  # scheduler.step() calls so far
+
+    @property
+    def needs_inliers(self):
+        """Only 1cyclepoly consumes the per-iteration inlier fraction (cooldown trigger, ace_schedule.py:91-101)."""
+        return self.schedule == "1cyclepoly" and not self.in_cooldown_phase
+
+    def lr(self):
+        s = self.steps
+        if self.schedule == "constant":
+            return self.lr_min
+        if self.schedule == "circle":
+            return self._fn(s)
+        if not self.in_cooldown_phase:  # LinearLR warm-up (start_factor = warmup_lr / lr_max, end_factor 1)
+            f0 = self.warmup_lr / self.lr_max
+            f = f0 + (1.0 - f0) * min(s, self.warmup_iterations) / self.warmup_iterations
+            return self.lr_max * f
+        # LinearLR cool-down (1 -> lr_min / lr_max over cooldown_iterations). torch's LinearLR is applied
+        # multiplicatively to the lr it finds, and warm-up has finished before a cool-down can start (:81), so the
+        # base is lr_max. The cool-down scheduler object was created at t=0 and its own counter starts at 0.
+        k = min(self.steps - self.cooldown_start, self.cooldown_iterations)
+        f1 = self.lr_min / self.lr_max
+        return self.lr_max * (1.0 + (f1 - 1.0) * k / self.cooldown_iterations)
+
+    def check_and_set_cooldown(self, iteration):
+        """ace_schedule.py:72-101."""
+        if self.schedule != "1cyclepoly" or self.in_cooldown_phase or iteration < self.warmup_iterations:
+            return
+        by_duration = iteration >= (self.max_iterations - self.cooldown_iterations)
+        dynamic = min(self.buffer) > self.trigger
+        if by_duration or dynamic:
+            self.max_iterations = iteration + self.cooldown_iterations
+            self.in_cooldown_phase = True
+            self.cooldown_start = self.steps
+
+    def step(self, batch_inliers):
+        """ace_schedule.py:115-126 (the optimiser part runs on the device)."""
+        if self.schedule == "constant":
+            return
+        self.steps += 1
+        if self.schedule == "1cyclepoly":
+            self.buffer.append(batch_inliers)
+            if len(self.buffer) > 100:
+                self.buffer = self.buffer[1:]
+
+
+def loss_weight(o, iteration):
+    """ace_loss.py:53-69 (tanh weight of iteration); soft_clamp for the l1 family."""
+    if o.repro_loss_type == "dyntanh":
+        w = iteration / o.iterations
+        if o.repro_loss_schedule == "circle":
+            w = 1 - np.sqrt(1 - w ** 2)
+        return float((1 - w) * o.repro_loss_soft_clamp + o.repro_loss_soft_clamp_min)
+    return float(o.repro_loss_soft_clamp)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class TrainLoop:
+    def __init__(self, head: HeadEngine, options, buffer, use_depth=False, rank=0, world_size=1, use_graph=True,
+                 device=None):
+        self.o = options
+        self.head = head
+        self.lib = head.lib
+        self.device = head.device if device is None else torch.device(device)
+        self.use_depth = use_depth
+        self.rank, self.world = rank, world_size
+        self.b_global = options.batch_size
+        if self.b_global % world_size != 0:
+            raise ValueError("batch_size must be divisible by the number of ranks")
+        self.b = self.b_global // world_size
+        self.use_scaler = bool(options.use_half)
+        self.schedule = Schedule(options)
+        self.iteration = 0
+        self.epoch = 0
+        self.training_generator = torch.Generator()
+        self.training_generator.manual_seed(options.base_seed + 8191)  # ace_trainer.py:79-80
+        self.use_graph = use_graph and world_size == 1
+        self._graph = None
+        self._warm = 0
+        self._graph_host = None
+        self._warm_host = 0
+        self.set_buffer(buffer)
+        if head.max_rows < self.b or not head.training:
+            raise ValueError("head engine must be created with training=True and max_rows >= per-rank batch")
+        if not self.use_scaler:
+            head.scaler_state[0] = 1.0
+        # static per-iteration tensors (graph-stable addresses)
+        d = self.device
+        self.idx_dev = torch.zeros(self.b, dtype=torch.int64, device=d)
+        self.idx_host = torch.zeros(self.b, dtype=torch.int64).pin_memory()
+        self.batch = {
+            "target_px": torch.empty((self.b, 2), device=d), "aug_poses_inv": torch.empty((self.b, 3, 4), device=d),
+            "poses_inv": torch.empty((self.b, 4, 4), device=d), "intrinsics": torch.empty((self.b, 3, 3), device=d),
+            "intrinsics_inv": torch.empty((self.b, 3, 3), device=d), "target_crds": torch.empty((self.b, 3), device=d),
+            "pose_idx": torch.empty((self.b, 1), dtype=torch.int16, device=d),
+        }
+        self.loss_w_host = None
+        self.stats_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._last_lw = None
+        self.last_stats = None
+
+    # ------------------------------------------------------------------ buffer
+    def set_buffer(self, buffer):
+        """buffer: dict with the reference's keys/shapes/dtypes (ace_trainer.py:330-340), CUDA-resident."""
+        for k in BUFFER_KEYS:
+            t = buffer[k]
+            if not t.is_cuda:
+                raise ValueError(f"training buffer '{k}' must live on the GPU (180 GB of HBM hold the 9.8 GB maximum)")
+            if t.element_size() * t[0].numel() != ROW_BYTES[k]:
+                raise ValueError(f"training buffer '{k}' has {t.element_size() * t[0].numel()} B rows, expected {ROW_BYTES[k]}")
+        self.buffer = {k: buffer[k].contiguous() for k in BUFFER_KEYS}
+        self.buffer_size = self.buffer["features"].shape[0]
+
+    def _gather(self, stream=None):
+        keys = list(BUFFER_KEYS)
+        n = len(keys)
+        srcs = (C.c_void_p * n)(*[self.buffer[k].data_ptr() for k in keys])
+        dsts = (C.c_void_p * n)(*([self.head.input_buffer(self.b).data_ptr()] + [self.batch[k].data_ptr() for k in keys[1:]]))
+        rbs = (C.c_int * n)(*[ROW_BYTES[k] for k in keys])
+        rc = self.lib.acez_gather_rows_multi(srcs, dsts, rbs, n, _lib.ptr(self.idx_dev), self.b, _lib.stream_ptr(stream))
+        _lib.check(rc, "acez_gather_rows_multi")
+
+    # ------------------------------------------------------------------ one iteration
+    def _enqueue_compute(self, P=None, d_P=None, d_Kdiag=None, gather=True):
+        """gather + forward + loss + backward (+ all-reduce) + GradScaler/AdamW on the current stream."""
+        o, h = self.o, self.head
+        lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
+                           float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
+                           o.depth_target, 1.0)
+        if gather:
+            self._gather()
+        bt = self.batch
+        h.train_fwd_bwd(self.b, lp, bt["target_px"], bt["intrinsics"], bt["intrinsics_inv"],
+                        aug_inv=bt["aug_poses_inv"], pose_inv=bt["poses_inv"], P=P,
+                        target_crds=bt["target_crds"] if self.use_depth else None, features=None, d_P=d_P,
+                        d_Kdiag=d_Kdiag, use_device_scale=True, use_device_loss_weight=True)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(h.grads)
+            small = torch.cat([h.stats, h.found_inf.float()])
+            dist.all_reduce(small)
+            h.stats.copy_(small[:4])
+            h.found_inf.copy_((small[4:] > 0).int())
+        h.adamw_step(use_scaler=self.use_scaler)
+
+    def train_iteration(self, indices, want_stats=False):
+        """indices: int64 CPU tensor of the GLOBAL batch (b_global entries of the epoch permutation)."""
+        sch = self.schedule
+        sch.check_and_set_cooldown(self.iteration)                    # ace_trainer.py:506
+        if self.iteration >= sch.max_iterations:                      # :509
+            return False
+        lo = self.rank * self.b
+        self.idx_host.copy_(indices[lo:lo + self.b])
+        self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
+        if self.use_graph:
+            self._run_graphed()
+        else:
+            self._enqueue_compute()
+        need = want_stats or sch.needs_inliers
+        inl = 0.0
+        if need:
+            self.stats_host.copy_(self.head.stats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.last_stats = self.stats_host.clone()
+            inl = float(self.stats_host[1]) / self.b_global
+        sch.step(inl)                                                  # :632
+        self.iteration += 1
+        return True
+
+    def train_step_from_host(self, host_batch, read_loss=True):
+        """End-to-end step with HOST inputs (the reference's `--training_buffer_cpu` path, ace_trainer.py:485-494):
+        the batch rows arrive in pinned host memory, are copied to the device, trained on, and the loss statistics
+        are read back. Returns (loss, inlier fraction)."""
+        sch = self.schedule
+        self.head.input_buffer(self.b).copy_(host_batch["features"], non_blocking=True)
+        for k in BUFFER_KEYS[1:]:
+            self.batch[k].copy_(host_batch[k], non_blocking=True)
+        self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
+        if self.use_graph:
+            if self._graph_host is None:
+                if self._warm_host < 2:
+                    self._warm_host += 1
+                    self._enqueue_compute(gather=False)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue_compute(gather=False)
+                    self._graph_host = g
+                    g.replay()
+            else:
+                self._graph_host.replay()
+        else:
+            self._enqueue_compute(gather=False)
+        out = None
+        if read_loss:
+            self.stats_host.copy_(self.head.stats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out = (float(self.stats_host[0]), float(self.stats_host[1]) / self.b_global)
+        sch.step(out[1] if out else 0.0)
+        self.iteration += 1
+        return out
+
+    def _run_graphed(self):
+        """The whole iteration (gather, 8+7+1 GEMMs, tail, memsets, check/AdamW/scaler) as one CUDA graph; the
+        per-iteration scalars (indices, lr, loss weight, grad scale) are read from device memory."""
+        if self._graph is None:
+            if self._warm < 2:  # eager iterations first: one-time kernel attribute setup, tensor maps
+                self._warm += 1
+                self._enqueue_compute()
+                return
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_compute()
+            self._graph = g
+        self._graph.replay()
+
+    # ------------------------------------------------------------------ epochs
+    def run_epoch(self, on_iteration=None):
+        """ace_trainer.py:454-497."""
+        if self.iteration >= self.schedule.max_iterations:
+            return False
+        self.epoch += 1
+        perm = torch.randperm(self.buffer_size, generator=self.training_generator)     # :466
+        bg = self.b_global
+        for start in range(0, self.buffer_size, bg):                                   # :469
+            if start + bg > self.buffer_size:                                          # :473 drop ragged tail
+                continue
+            want = on_iteration is not None and (self.iteration % self.o.iterations_output == 0)
+            ran = self.train_iteration(perm[start:start + bg], want_stats=want)
+            if ran and want:
+                on_iteration(self)
+            if not ran:
+                # the reference keeps calling training_step for the rest of the epoch; each call returns at once
+                break
+        return True

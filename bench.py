@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the ACE Zero hot path on B200 (BASELINE.json metric: ACE training iters/s + dsacstar poses/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host cores (oracle port)
+
+One JSON line on stdout (rank 0). A "step" is one ACE training iteration over a 5120-patch batch (head forward, fused
+reprojection loss, backward, GradScaler + AdamW; reference ace_trainer.py:499-640); the DSAC* pose solve
+(dsacstar.forward_rgb, 64 hypotheses, 60x80 scene-coordinate maps) is timed in the same run and reported under "dsac".
+
+Workload = BASELINE.json configs[1] ("7-Scenes 'chess' synthetic: ACE head training + register_mapping on 1 B200"):
+synthetic patch buffer of 1 024 000 rows x 1230 B (1.26 GB, larger than L2; rows are drawn through the epoch
+permutation, so every batch gathers fresh rows from HBM), head with num_head_blocks=1, homogeneous output, dyntanh
+loss, one-cycle lr, fp16 autocast semantics + GradScaler. Multi-GPU: weak scaling — every rank trains on its own
+5120-patch shard of a 5120*N global batch (the loss divisor is the global batch, gradients are all-reduced over NCCL);
+DSAC* images are sharded across ranks with no collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B = 5120
+BUFFER_ROWS = 1_024_000
+FLOP_PER_ITER = 61.80e9          # 12.07 MFLOP / patch x 5120
+FLOP_FWD_GEMM = 2 * 5120 * 512 * 512   # one hidden-layer GEMM launch
+DSAC_HYPS = 64
+DSAC_H, DSAC_W = 60, 80
+DSAC_BATCH = 1024                # images per batched solver call
+
+
+def options(b_global, iterations=5000):
+    return SimpleNamespace(
+        batch_size=b_global, base_seed=2089, use_half=True, iterations=iterations, iterations_output=10 ** 9,
+        learning_rate_schedule="circle", learning_rate_min=0.0005, learning_rate_max=0.005,
+        learning_rate_warmup_iterations=1000, learning_rate_warmup_learning_rate=0.0005,
+        learning_rate_cooldown_iterations=5000, learning_rate_cooldown_trigger_percent_threshold=0.7,
+        learning_rate_cooldown_trigger_px_threshold=10, repro_loss_type="dyntanh", repro_loss_schedule="circle",
+        repro_loss_soft_clamp=50, repro_loss_soft_clamp_min=1, repro_loss_hard_clamp=1000, depth_min=0.1,
+        depth_max=1000.0, depth_target=10.0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic data
+# ----------------------------------------------------------------------------------------------------------------
+def synth_buffer(rows, device, seed):
+    """Patch buffer with the reference's layout (ace_trainer.py:330-340), generated on the device."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n_img = 1000
+    ang = torch.rand((n_img, 3), device=device, generator=g) - 0.5
+    cx, sx = torch.cos(ang[:, 0]), torch.sin(ang[:, 0])
+    cy, sy = torch.cos(ang[:, 1]), torch.sin(ang[:, 1])
+    cz, sz = torch.cos(ang[:, 2]), torch.sin(ang[:, 2])
+    R = torch.stack([cz * cy, cz * sy * sx - sz * cx, cz * sy * cx + sz * sx,
+                     sz * cy, sz * sy * sx + cz * cx, sz * sy * cx - cz * sx,
+                     -sy, cy * sx, cy * cx], 1).view(n_img, 3, 3)
+    T = torch.eye(4, device=device).repeat(n_img, 1, 1)
+    T[:, :3, :3] = R
+    T[:, :3, 3] = torch.rand((n_img, 3), device=device, generator=g) - 0.5
+    T[:, 2, 3] = 2 + 2 * torch.rand(n_img, device=device, generator=g)
+    img = torch.randint(0, n_img, (rows,), device=device, generator=g)
+    a = (torch.rand(rows, device=device, generator=g) - 0.5) * 0.52
+    aug = torch.zeros((rows, 3, 4), device=device)
+    aug[:, 0, 0], aug[:, 0, 1], aug[:, 1, 0], aug[:, 1, 1], aug[:, 2, 2] = torch.cos(a), -torch.sin(a), torch.sin(a), torch.cos(a), 1.0
+    sc = 2 / 3 + torch.rand(rows, device=device, generator=g) * (3 / 2 - 2 / 3)
+    K = torch.zeros((rows, 3, 3), device=device)
+    K[:, 0, 0] = K[:, 1, 1] = 525.0 * sc
+    K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = 320.0 * sc, 240.0 * sc, 1.0
+    Kinv = torch.zeros_like(K)
+    Kinv[:, 0, 0] = Kinv[:, 1, 1] = 1.0 / K[:, 0, 0]
+    Kinv[:, 0, 2], Kinv[:, 1, 2], Kinv[:, 2, 2] = -K[:, 0, 2] / K[:, 0, 0], -K[:, 1, 2] / K[:, 0, 0], 1.0
+    px = torch.stack([8 * (torch.randint(0, 80, (rows,), device=device, generator=g) + 0.5),
+                      8 * (torch.randint(0, 60, (rows,), device=device, generator=g) + 0.5)], 1).float()
+    return {
+        "features": (torch.randn((rows, 512), device=device, generator=g) * 0.5).half(),
+        "target_px": px, "aug_poses_inv": aug, "poses_inv": T[img].contiguous(), "intrinsics": K,
+        "intrinsics_inv": Kinv, "target_crds": torch.zeros((rows, 3), device=device),
+        "pose_idx": img.to(torch.int16).view(-1, 1),
+    }
+
+
+def synth_scene_maps(n, seed):
+    """n scene-coordinate maps [n,3,60,80] with known poses (SURVEY §8d config 5 generator, via the oracle module's
+    numpy code path; a data generator, not a checker)."""
+    from oracle import dsacstar_ref as D
+    base = [D.synth_scene(seed + i)[0] for i in range(16)]
+    sc = np.concatenate(base, 0)
+    reps = (n + 15) // 16
+    return np.tile(sc, (reps, 1, 1, 1))[:n]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle port on the host cores)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_train_iters_per_s(steps, warmup):
+    from oracle import ace_ref
+    torch.set_num_threads(os.cpu_count())
+    sd = ace_ref.make_head_state(200, 1, True)
+    o = ace_ref.LossOptions(iterations=5000)
+    tr = ace_ref.TrainerRef(sd, 1, True, o, ace_ref.one_cycle_lr(0.005, 5000), emulate_half=False)
+    bts = [ace_ref.synth_batch(600 + i, B) for i in range(2)]
+    def one(i):
+        bt = bts[i % 2]
+        tr.step(bt["features"].float(), bt["target_px"], bt["aug_poses_inv"], bt["poses_inv"], bt["intrinsics"],
+                bt["intrinsics_inv"], bt["target_crds"])
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt
+
+
+def cpu_dsac_poses_per_s(n_poses):
+    from oracle import dsacstar_ref as D
+    import cv2
+    cv2.setNumThreads(os.cpu_count())
+    scenes = [D.synth_scene(100 + i) for i in range(min(n_poses, 8))]
+    D.forward_rgb(scenes[0][0], DSAC_HYPS, 10.0, 525.0, 320.0, 240.0, 100.0, 100.0, 8, 1, 16)
+    t0 = time.perf_counter()
+    for i in range(n_poses):
+        sc, _, f, px, py = scenes[i % len(scenes)]
+        D.forward_rgb(sc, DSAC_HYPS, 10.0, f, px, py, 100.0, 100.0, 8, 1 + i, 16)
+    dt = time.perf_counter() - t0
+    return n_poses / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    ips, dt = cpu_train_iters_per_s(args.steps, args.warmup)
+    pps, dt2 = cpu_dsac_poses_per_s(max(4, min(40, args.steps)))
+    line = {
+        "impl": "reference", "metric": "ace_train_iters_per_s", "value": ips, "unit": "iters/s (5120-patch iterations)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / ips,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: ACE head training step b=5120 (CPU, fp32) + dsacstar 64 hyps 60x80"},
+        "cpu_baseline": {"value": ips, "unit": "iters/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} training iterations of b=5120 (oracle/ace_ref.py TrainerRef, torch CPU fp32, "
+                                   f"{cores} threads), {dt:.1f} s"},
+        "e2e": {"value": ips, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dsac": {"poses_per_s": pps, "unit": "poses/s", "hyps": DSAC_HYPS,
+                 "cpu_baseline": {"value": pps, "unit": "poses/s", "cores": cores, "kind": "port",
+                                  "sample": f"cv2 restatement (oracle/dsacstar_ref.py), {dt2:.1f} s"},
+                 "e2e": {"value": pps, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from acezero_b200 import build
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        build.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from acezero_b200.head import HeadEngine
+    from acezero_b200.trainer import TrainLoop, BUFFER_KEYS
+    from acezero_b200 import dsac
+    from oracle import ace_ref  # only for the deterministic head-state generator (numpy) and the cpu_baseline leg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---------------- training ----------------
+    o = options(B * world, max(5000, 2 * (args.steps + args.warmup + 400)))
+    head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B, training=True, device=dev)
+    head.load_state(ace_ref.make_head_state(200, 1, True))
+    buf = synth_buffer(BUFFER_ROWS, dev, 2089)   # identical on every rank (same seed), as the replicated buffer is
+    loop = TrainLoop(head, o, buf, rank=rank, world_size=world, use_graph=(world == 1))
+    perm = torch.randperm(BUFFER_ROWS, generator=loop.training_generator)
+    bg = B * world
+    n_batches = BUFFER_ROWS // bg
+    it = [0]
+
+    def step():
+        s = (it[0] % n_batches) * bg
+        loop.train_iteration(perm[s:s + bg])
+        it[0] += 1
+
+    for _ in range(max(args.warmup, 3) + 2):   # +2: the CUDA graph is captured on the third call
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    iters_per_s = world * 1000.0 / ms_per_step      # 5120-patch iterations per second, whole job
+    loss_final = float(head.stats[0])
+
+    # ---------------- end-to-end (host buffers in, loss out) ----------------
+    host_batches = []
+    for i in range(4):
+        idx = perm[i * B:(i + 1) * B].to(dev)
+        host_batches.append({k: buf[k][idx].cpu().pin_memory() for k in BUFFER_KEYS})
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    for i in range(4):
+        loop.train_step_from_host(host_batches[i % 4])
+    barrier()
+    n_e2e = max(10, min(args.steps, 200))
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        loop.train_step_from_host(host_batches[i % 4])     # H2D copy, step, D2H of the loss statistics + sync
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0 / n_e2e)
+    e2e_ips = world * 1000.0 / e2e_ms
+
+    # ---------------- roofline of the dominant kernel: the hidden-layer forward GEMM (tcgen05) ----------------
+    g = torch.cuda.CUDAGraph()
+    reps = 10
+    feats = host_batches[0]["features"].to(dev)
+    head.input_buffer(B).copy_(feats)
+    lib = head.lib
+    from acezero_b200 import _lib
+    for _ in range(2):
+        _lib.check(lib.acez_head_forward(head.plan, None, B, None, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            _lib.check(lib.acez_head_forward(head.plan, None, B, None, _lib.stream_ptr()))
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_us = e0.elapsed_time(e1) * 1000.0 / (5 * reps * head.L)
+    pk = peaks()
+    achieved_tf = FLOP_FWD_GEMM / (gemm_us * 1e-6) / 1e12
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------- DSAC* ----------------
+    n_img = DSAC_BATCH
+    maps_host = torch.from_numpy(synth_scene_maps(n_img, 1000 + rank * n_img)).pin_memory()
+    maps = maps_host.to(dev)
+    kw = dict(hyps=DSAC_HYPS, inlier_threshold=10.0, inlier_alpha=100.0, max_reproj=100.0, subsample=8, seed=2089,
+              max_tries=16, image_index_base=rank * n_img)
+    for _ in range(3):
+        dsac.forward_rgb_batch(maps, 525.0, 320.0, 240.0, **kw)
+    barrier()
+    e0.record()
+    d_steps = max(3, min(args.steps, 20))
+    for _ in range(d_steps):
+        dsac.forward_rgb_batch(maps, 525.0, 320.0, 240.0, **kw)
+    e1.record()
+    barrier()
+    dsac_ms = max_over_ranks(e0.elapsed_time(e1) / d_steps)
+    poses_per_s = world * n_img * 1000.0 / dsac_ms
+    # end to end: host scene coordinates in, host poses out
+    t0 = time.perf_counter()
+    for _ in range(d_steps):
+        p, n = dsac.forward_rgb_batch(maps_host.to(dev, non_blocking=True), 525.0, 320.0, 240.0, **kw)
+        p_h, n_h = p.cpu(), n.cpu()
+    dsac_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0 / d_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- cpu baseline (bounded sample, rank 0, N = 1 only) ----------------
+    cpu = cpu_d = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips_c, dt_c = cpu_train_iters_per_s(12, 2)
+        pps_c, dt_d = cpu_dsac_poses_per_s(24)
+        cores = os.cpu_count()
+        cpu = {"value": ips_c, "unit": "iters/s", "cores": cores, "kind": "port",
+               "sample": f"12 iterations of b=5120, oracle/ace_ref.py (restated reference trainer, torch CPU fp32), {dt_c:.1f} s"}
+        cpu_d = {"value": pps_c, "unit": "poses/s", "cores": cores, "kind": "port",
+                 "sample": f"24 poses, 64 hyps, cv2 restatement oracle/dsacstar_ref.py, {dt_d:.1f} s"}
+    line = {
+        "metric": "ace_train_iters_per_s", "value": iters_per_s, "unit": "iters/s (5120-patch iterations)",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "configs[1] 'chess'-shaped: ACE head training (b=5120/GPU, 1 head block, homogeneous, dyntanh, "
+                               "one-cycle lr, GradScaler) + register_mapping's DSAC* (64 hyps, 60x80 maps)",
+                   "global_batch": B * world, "buffer_rows": BUFFER_ROWS, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (1.26 GB patch buffer, fresh random rows gathered every step)"},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,K,K,FWD> 5120x512x512",
+                     "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / pk["bf16_tflops"], "traffic": None, "us_per_launch": gemm_us,
+                     "peak_source": pk["source"] + " burst bf16 (kernel timed alone)",
+                     "step_frac_of_sustained": FLOP_PER_ITER / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": args.steps * 21,
+        "launches_per_step": {"gather": 1, "fwd_gemm": 8, "tail": 1, "dgrad_gemm": 7, "wgrad_gemm": 1, "grad_check": 1,
+                              "adamw": 1, "scaler_update": 1},
+        "loss_final": loss_final,
+        "dsac": {"poses_per_s": poses_per_s, "unit": "poses/s", "hyps": DSAC_HYPS, "images_per_call": n_img,
+                 "ms_per_call": dsac_ms, "gpu_launches_per_call": 2,
+                 "e2e": {"value": world * n_img * 1000.0 / dsac_e2e_ms, "unit": "poses/s",
+                         "h2d_bytes_per_step": n_img * 3 * DSAC_H * DSAC_W * 4, "d2h_bytes_per_step": n_img * 68},
+                 "cpu_baseline": cpu_d,
+                 "work": "13.8 MFLOP + 307 k exp per pose (scoring) + refinement; FP64/FP32 issue bound, 57.6 KB in / 68 B out"},
+        "clocks": clk,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,7 +149,8 @@ int acez_head_sync_weights(acez_head_plan* plan, acez_stream_t stream);
 void* acez_head_input_ptr(acez_head_plan* plan);
 
 /* Forward only (registration; ace_network.py:120-149 under autocast): features -> scene coordinates.
- * features: fp16 [rows,512] (nullable = already in the plan's input buffer); sc_out: fp32 [rows,3]. */
+ * features: fp16 [rows,512] (nullable = already in the plan's input buffer); sc_out: fp32 [rows,3]
+ * (nullable: run only the hidden-layer GEMM chain, used by bench.py to time that kernel alone). */
 int acez_head_forward(acez_head_plan* plan, const void* features, int rows, float* sc_out, acez_stream_t stream);
 
 typedef struct acez_train_batch {
@@ -165,6 +166,7 @@ typedef struct acez_train_batch {
   float* d_Kdiag_b2;           /* nullable out */
   float* sc_out_b3;            /* nullable out: predicted scene coordinates (fp32) */
   const float* grad_scale_dev; /* nullable: device scalar overriding loss_params.grad_scale (= scaler_state[0]) */
+  const float* loss_weight_dev; /* nullable: device scalar overriding loss_params.loss_weight (dyntanh schedule) */
 } acez_train_batch;
 
 /* One head forward + reprojection loss + full backward into `grads` (overwritten, scaled by grad_scale).
@@ -176,6 +178,9 @@ int acez_head_train_fwd_bwd(acez_head_plan* plan, int rows, const acez_loss_para
 /* Gather rows of the patch buffer into a batch (reference ace_trainer.py:485-494, 8 index kernels):
  * dst[i, :] = src[idx[i], :], row_bytes multiple of 2. */
 int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_bytes, void* dst, acez_stream_t stream);
+/* The same for up to 8 arrays sharing one index vector, in ONE launch (all arrays of the patch buffer). */
+int acez_gather_rows_multi(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
+                           const int64_t* idx, int rows, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * GradScaler unscale + inf check + AdamW + GradScaler.update, entirely on the device (CUDA-graph capturable, no
