@@ -36,6 +36,7 @@ struct acez_head_plan {
   __half* XTRA;
   __half* DZ;
   __half* GRES;
+  float* G3;
   size_t act_stride;  // max_rows * 512
   int prepared_rows;
   int prepared_training;
@@ -47,7 +48,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, total;
+  size_t w16, w3h, act, xtra, dz, gres, g3, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -63,6 +64,7 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.xtra = off; off = align_up(off + (size_t)nres * rows * kC * 2, 1024);
     o.dz = off; off = align_up(off + (size_t)L * rows * kC * 2, 1024);
     o.gres = off; off = align_up(off + rows * kC * 2, 1024);
+    o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
   }
   o.total = off;
   return o;
@@ -129,8 +131,9 @@ __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __r
 }
 
 // ----------------------------------------------------------------------------------------------
-// tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1] and the fc3 gradient)
-// one warp per row; lane owns columns [16*lane, 16*lane+16)
+// tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1]); one warp per row, lane owns columns
+// [16*lane, 16*lane+16) with its slice of the fc3 weights held in registers. The gradient w.r.t. the 4 fc3 outputs is
+// written to G3 [rows,4]; fc3_wgrad_kernel turns it into dW3 / db3.
 // ----------------------------------------------------------------------------------------------
 struct TailArgs {
   int rows, C3, use_homogeneous, training;
@@ -146,8 +149,7 @@ struct TailArgs {
   const float* tpx; const float* Pin; const float* A; const float* T; const float* K; const float* Kinv; const float* G;
   float* d_P; float* d_Kdiag;
   __half* dz;           // DZ[L-1] [rows,512]
-  float* gW3;           // grads of fc3 weight [C3,512] (atomically accumulated; caller zeroes)
-  float* gb3;           // [C3]
+  float* g3;            // [rows,4] gradient w.r.t. the fc3 outputs (fp16-rounded values)
   float* stats;         // [4]
   int* nonfinite;
 };
@@ -155,17 +157,19 @@ struct TailArgs {
 static constexpr int kTailThreads = 256;
 
 __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
-  __shared__ float sW[4][kC];       // fc3 weights as float (from the fp16 shadow)
-  __shared__ float sG[4][kC];       // block-level accumulation of dW3
-  __shared__ float sRed[4][kTailThreads / 32];
-  __shared__ float sGb[4];
+  __shared__ float sRed[3][kTailThreads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 4 * kC; i += kTailThreads) {
-    (&sW[0][0])[i] = __half2float(a.W3h[i]);
-    (&sG[0][0])[i] = 0.f;
+  // this lane's slice of the fc3 weights: 4 rows x 16 columns, packed fp16
+  __half2 w[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4* wp = reinterpret_cast<const uint4*>(a.W3h + j * kC + lane * 16);
+    uint4 t0 = wp[0], t1 = wp[1];
+    const __half2* h0 = reinterpret_cast<const __half2*>(&t0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&t1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w[j][k] = h0[k]; w[j][4 + k] = h1[k]; }
   }
-  if (tid < 4) sGb[tid] = 0.f;
-  __syncthreads();
   float b3[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) b3[j] = (j < a.C3) ? __half2float(__float2half_rn(a.b3[j])) : 0.f;
@@ -174,34 +178,28 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
   if (a.training && a.grad_scale_dev != nullptr) lp.grad_scale = *a.grad_scale_dev;
   if (a.training && a.loss_weight_dev != nullptr) lp.loss_weight = *a.loss_weight_dev;
 
-  float accW[4][16];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) accW[j][k] = 0.f;
-  float accB[4] = {0.f, 0.f, 0.f, 0.f};
   float loss_sum = 0.f, inl_sum = 0.f, valid_sum = 0.f;
   bool bad = false, bad_g = false;
 
   const int warps_total = gridDim.x * (kTailThreads / 32);
   for (int row = blockIdx.x * (kTailThreads / 32) + warp; row < a.rows; row += warps_total) {
-    // ---- load this lane's 16 activations ----
     const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * kC + lane * 16);
     uint4 xr[2] = {xp[0], xp[1]};
     const __half2* xh = reinterpret_cast<const __half2*>(xr);
-    float xf[16];
+    float2 xf[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float2 f = __half22float2(xh[k]);
-      xf[2 * k] = f.x; xf[2 * k + 1] = f.y;
-    }
+    for (int k = 0; k < 8; ++k) xf[k] = __half22float2(xh[k]);
     // ---- fc3: 4 dot products (fp32 accumulate, fp16 output as the autocast conv produces) ----
     float s[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float d = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) d = fmaf(xf[k], sW[j][lane * 16 + k], d);
+      for (int k = 0; k < 8; ++k) {
+        const float2 wf = __half22float2(w[j][k]);
+        d = fmaf(xf[k].x, wf.x, d);
+        d = fmaf(xf[k].y, wf.y, d);
+      }
       d = warp_sum(d);
       s[j] = __half2float(__float2half_rn(d + b3[j]));
     }
@@ -267,7 +265,8 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
       g[j] = __half2float(__float2half_rn(g[j]));
       bad_g |= !isfinite(g[j]);
     }
-    // ---- dX8 = g W3 (fp16 result), masked by ReLU of x8 -> DZ[L-1]; accumulate dW3, db3 ----
+    if (lane == 0) *reinterpret_cast<float4*>(a.g3 + 4 * (size_t)row) = make_float4(g[0], g[1], g[2], g[3]);
+    // ---- dX8 = g W3 (fp16 result), masked by the ReLU of x8 -> DZ[L-1] ----
     uint4 outv[2];
     __half2* oh = reinterpret_cast<__half2*>(outv);
 #pragma unroll
@@ -275,42 +274,26 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        d0 = fmaf(g[j], sW[j][lane * 16 + 2 * k], d0);
-        d1 = fmaf(g[j], sW[j][lane * 16 + 2 * k + 1], d1);
+        const float2 wf = __half22float2(w[j][k]);
+        d0 = fmaf(g[j], wf.x, d0);
+        d1 = fmaf(g[j], wf.y, d1);
       }
       __half2 hv = __floats2half2_rn(d0, d1);
       const float2 hf = __half22float2(hv);
       bad_g |= !(isfinite(hf.x) && isfinite(hf.y));
-      if (!(xf[2 * k] > 0.f)) hv.x = __float2half_rn(0.f);
-      if (!(xf[2 * k + 1] > 0.f)) hv.y = __float2half_rn(0.f);
+      if (!(xf[k].x > 0.f)) hv.x = __float2half_rn(0.f);
+      if (!(xf[k].y > 0.f)) hv.y = __float2half_rn(0.f);
       oh[k] = hv;
     }
     uint4* dzp = reinterpret_cast<uint4*>(a.dz + (size_t)row * kC + lane * 16);
     dzp[0] = outv[0];
     dzp[1] = outv[1];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) accW[j][k] = fmaf(g[j], xf[k], accW[j][k]);
-      accB[j] += g[j];
-    }
   }
   if (!a.training) return;
 
-  // ---- block reduction of dW3 / db3 / stats, then one round of global atomics per block ----
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) atomicAdd(&sG[j][lane * 16 + k], accW[j][k]);
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(&sGb[j], accB[j]);
-    sRed[0][warp] = loss_sum; sRed[1][warp] = inl_sum; sRed[2][warp] = valid_sum;
-  }
+  if (lane == 0) { sRed[0][warp] = loss_sum; sRed[1][warp] = inl_sum; sRed[2][warp] = valid_sum; }
   const int any_bad = __syncthreads_or(bad ? 1 : 0);
   const int any_bad_g = __syncthreads_or(bad_g ? 1 : 0);
-  for (int i = tid; i < a.C3 * kC; i += kTailThreads) atomicAdd(&a.gW3[i], (&sG[0][0])[i]);
-  if (tid < a.C3) atomicAdd(&a.gb3[tid], sGb[tid]);
   if (tid == 0) {
     float l = 0.f, n = 0.f, v = 0.f;
     for (int k = 0; k < kTailThreads / 32; ++k) { l += sRed[0][k]; n += sRed[1][k]; v += sRed[2][k]; }
@@ -320,6 +303,35 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     if (any_bad) a.stats[3] = 1.f;
     if (any_bad_g && a.nonfinite != nullptr) atomicOr(a.nonfinite, 1);
   }
+}
+
+// dW3[j][c] = sum_rows G3[row][j] * x8[row][c], db3[j] = sum_rows G3[row][j]. Thread t owns columns 2t, 2t+1; a
+// block walks a contiguous slab of rows (coalesced 1 KB row reads), then adds its partial sums to the gradient.
+static constexpr int kFc3Threads = 256;
+__global__ void __launch_bounds__(kFc3Threads) fc3_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ g3,
+                                                               int rows, int C3, float* __restrict__ gW3,
+                                                               float* __restrict__ gb3) {
+  const int t = threadIdx.x;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  float accb = 0.f;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)r * kC + 2 * t));
+    const float4 g = *reinterpret_cast<const float4*>(g3 + 4 * (size_t)r);
+    acc[0][0] = fmaf(g.x, xv.x, acc[0][0]); acc[0][1] = fmaf(g.x, xv.y, acc[0][1]);
+    acc[1][0] = fmaf(g.y, xv.x, acc[1][0]); acc[1][1] = fmaf(g.y, xv.y, acc[1][1]);
+    acc[2][0] = fmaf(g.z, xv.x, acc[2][0]); acc[2][1] = fmaf(g.z, xv.y, acc[2][1]);
+    acc[3][0] = fmaf(g.w, xv.x, acc[3][0]); acc[3][1] = fmaf(g.w, xv.y, acc[3][1]);
+    if (t < 4) accb += (t == 0) ? g.x : (t == 1) ? g.y : (t == 2) ? g.z : g.w;
+  }
+  if (r1 <= r0) return;
+  for (int j = 0; j < C3; ++j) {
+    atomicAdd(&gW3[j * kC + 2 * t], acc[j][0]);
+    atomicAdd(&gW3[j * kC + 2 * t + 1], acc[j][1]);
+  }
+  if (t < C3) atomicAdd(&gb3[t], accb);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -498,7 +510,7 @@ static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
 static int tail_grid(int rows) {
   const int per_block = kTailThreads / 32;
   int g = (rows + per_block - 1) / per_block;
-  const int cap = 2 * sm_count();
+  const int cap = 4 * sm_count();  // ~100 registers/thread: two 256-thread CTAs per SM, a few rows per warp
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 
@@ -545,6 +557,7 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->XTRA = cfg->training ? reinterpret_cast<__half*>(base + lo.xtra) : nullptr;
   h->DZ = cfg->training ? reinterpret_cast<__half*>(base + lo.dz) : nullptr;
   h->GRES = cfg->training ? reinterpret_cast<__half*>(base + lo.gres) : nullptr;
+  h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;
   h->prepared_training = 0;
@@ -627,12 +640,17 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   t.grad_scale_dev = b->grad_scale_dev;
   t.loss_weight_dev = b->loss_weight_dev;
   t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
-  t.gW3 = gW3;
-  t.gb3 = gW3 + (size_t)h->C3 * kC;
+  t.g3 = h->G3;
   t.stats = stats;
   t.nonfinite = nonfinite;
   head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
   ACEZ_CUDA(cudaGetLastError());
+  {
+    int g = (rows + 31) / 32;
+    if (g > sm_count()) g = sm_count();
+    fc3_wgrad_kernel<<<g, kFc3Threads, 0, s>>>(t.x, h->G3, rows, h->C3, gW3, gW3 + (size_t)h->C3 * kC);
+    ACEZ_CUDA(cudaGetLastError());
+  }
   for (int l = L - 1; l >= 1; --l) {
     h->dgrad[l].args.nonfinite = nonfinite;
     rc = gemm_launch(h->dgrad[l], s);
