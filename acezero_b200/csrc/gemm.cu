@@ -93,6 +93,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (A_MN) {
 #pragma unroll
           for (int i = 0; i < BM / 64; ++i) tma_load_3d(a_dst + i * 8192, &tmA, &full_bar[stage], m0 + 64 * i, kb * BK, z);
+        } else if (args.conv.enabled) {
+          // implicit GEMM: k-block = (filter tap, 64-channel chunk); one 4-D box = 16 x 8 pixels x 64 channels
+          const ConvGeom& cg = args.conv;
+          const int tile = blockIdx.y;
+          const int tx = tile % cg.tiles_x, ty = (tile / cg.tiles_x) % cg.tiles_y, img = tile / (cg.tiles_x * cg.tiles_y);
+          const int tap = kb / cg.cin_blocks, cb = kb - tap * cg.cin_blocks;
+          const int ky = tap / cg.ksize, kx = tap - ky * cg.ksize;
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], cb * 64, tx * kConvTileW * cg.stride + kx - cg.pad,
+                      ty * kConvTileH * cg.stride + ky - cg.pad, img);
         } else {
           tma_load_3d(a_dst, &tmA, &full_bar[stage], kb * BK, m0, z);
         }
@@ -139,8 +148,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------ epilogue (4 warps <-> 4 TMEM lane quarters) ------------------------------
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < args.M;
+    int row = m0 + quarter * 32 + lane;
+    bool row_ok = row < args.M;
+    if (args.conv.enabled) {
+      const ConvGeom& cg = args.conv;
+      const int tile = blockIdx.y;
+      const int tx = tile % cg.tiles_x, ty = (tile / cg.tiles_x) % cg.tiles_y, img = tile / (cg.tiles_x * cg.tiles_y);
+      const int r = quarter * 32 + lane;
+      const int py = ty * kConvTileH + r / kConvTileW, px = tx * kConvTileW + r % kConvTileW;
+      row_ok = (py < cg.Ho) && (px < cg.Wo);
+      row = (img * cg.Ho + py) * cg.Wo + px;  // NHWC pixel index
+    }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -303,6 +321,7 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((L.args.N + BN - 1) / BN, (L.args.M + BM - 1) / BM, L.batch);
+  if (L.args.conv.enabled) grid.y = L.args.conv.tiles_x * L.args.conv.tiles_y * L.batch, grid.z = 1;
   kern<<<grid, kThreads, GemmCfg<BN>::kSmem, stream>>>(L.tmA, L.tmB, L.args);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;

@@ -21,7 +21,21 @@ enum GemmEpi : int {
   EPI_WGRAD = 2,  // out32[z] = acc (fp32); optional bias-gradient column (sum over the contraction of A)
 };
 
+// Implicit-GEMM convolution front end (encoder, ace_network.py:26-39): the A tile of a k-block is one 4-D TMA box of an
+// NHWC activation tensor: 16 x 8 output pixels x 64 input channels at filter tap (ky, kx); zero padding comes from
+// TMA out-of-bounds fill, stride 2 from the tensor map's element strides. Output rows are NHWC pixels.
+struct ConvGeom {
+  int enabled;
+  int cin_blocks;  // Cin / 64
+  int ksize;       // 3 (1x1 convolutions run as plain GEMMs)
+  int stride, pad;
+  int Ho, Wo;      // output extent
+  int tiles_x, tiles_y;
+};
+static constexpr int kConvTileW = 16, kConvTileH = 8;  // 128 output pixels per CTA tile
+
 struct GemmArgs {
+  ConvGeom conv;
   int M, N;       // logical output extent; rows >= M / cols >= N are not stored
   int k_blocks;   // contraction length / 64
   // UMMA descriptor constants (bytes); set by gemm_prepare, exposed so the GPU test can probe alternatives

@@ -320,3 +320,51 @@ def synth_batch(seed, b, n_images=5, f=525.0, W=640, H=480, frac_far=0.1, with_d
         "intrinsics": t(K), "intrinsics_inv": t(Kinv), "target_crds": t(crds),
         "pose_idx": t(img.astype(np.int16).reshape(-1, 1)),
     }
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# encoder (ace_network.py:14-59)
+# --------------------------------------------------------------------------------------------------------------------
+ENCODER_LAYERS = [  # name, cin, cout, k, stride, pad — state-dict order of ace_encoder_pretrained.pt
+    ("conv1", 1, 32, 3, 1, 1), ("conv2", 32, 64, 3, 2, 1), ("conv3", 64, 128, 3, 2, 1), ("conv4", 128, 256, 3, 2, 1),
+    ("res1_conv1", 256, 256, 3, 1, 1), ("res1_conv2", 256, 256, 1, 1, 0), ("res1_conv3", 256, 256, 3, 1, 1),
+    ("res2_conv1", 256, 512, 3, 1, 1), ("res2_conv2", 512, 512, 1, 1, 0), ("res2_conv3", 512, 512, 3, 1, 1),
+    ("res2_skip", 256, 512, 1, 1, 0),
+]
+
+
+def make_encoder_state(seed):
+    """Deterministic (numpy RandomState) encoder state dict with the reference's names / shapes (ace_network.py:26-39);
+    He-style scale so that activations keep O(1) magnitude through the 11 layers like the pretrained weights do."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for name, cin, cout, k, _, _ in ENCODER_LAYERS:
+        std = math.sqrt(2.0 / (cin * k * k))
+        sd[name + ".weight"] = torch.from_numpy((rs.standard_normal((cout, cin, k, k)) * std).astype(np.float32))
+        sd[name + ".bias"] = torch.from_numpy(rs.uniform(-0.1, 0.1, (cout,)).astype(np.float32))
+    return sd
+
+
+def encoder_forward(sd, image_b1hw, emulate_half=False):
+    """ace_network.py:41-59. Returns [B,512,h,w]."""
+    spec = {n: (s, p) for n, _, _, _, s, p in ENCODER_LAYERS}
+
+    def conv(x, name, relu=True):
+        s, p = spec[name]
+        y = F.conv2d(x, _rh(sd[name + ".weight"], emulate_half), _rh(sd[name + ".bias"], emulate_half), stride=s, padding=p)
+        y = _rh(y, emulate_half)
+        return F.relu(y) if relu else y
+
+    x = _rh(image_b1hw.float(), emulate_half)
+    x = conv(x, "conv1"); x = conv(x, "conv2"); x = conv(x, "conv3")
+    res = conv(x, "conv4")
+    x = conv(res, "res1_conv1"); x = conv(x, "res1_conv2"); x = conv(x, "res1_conv3")
+    res = _rh(res + x, emulate_half)
+    x = conv(res, "res2_conv1"); x = conv(x, "res2_conv2"); x = conv(x, "res2_conv3")
+    return _rh(conv(res, "res2_skip", relu=False) + x, emulate_half)
+
+
+def synth_image(seed, h=480, w=640):
+    """Normalised grayscale image (dataset.py:150-153: (g - 0.4) / 0.25), numpy-seeded."""
+    rs = np.random.RandomState(seed)
+    return torch.from_numpy(((rs.uniform(0, 1, (1, 1, h, w)) - 0.4) / 0.25).astype(np.float32))

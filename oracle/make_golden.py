@@ -79,6 +79,17 @@ def main():
                 sc = reg.get_scene_coordinates(x).permute(0, 2, 3, 1).flatten(0, 2)   # ace_trainer.py:521
             out[f"head_sc_h{int(homog)}_b{nb}"] = sc.numpy()
 
+    # ---------------------------------------------------------------- 1b. Encoder forward (fp32, CPU)
+    for tag, (h, w) in {"96x128": (96, 128), "75x101": (75, 101)}.items():
+        esd = ace_ref.make_encoder_state(77)
+        enc = ace_network.Encoder(out_channels=512)
+        enc.load_state_dict(esd)
+        enc.eval()
+        with torch.no_grad():
+            f = enc(ace_ref.synth_image(5, h, w))
+        out[f"encoder_{tag}_shape"] = np.array(f.shape)
+        out[f"encoder_{tag}_sample"] = f.reshape(-1)[::53].numpy().copy()
+
     # ---------------------------------------------------------------- 2. training_step x N (fp32, CPU)
     for tag, loss_type, use_depth, sched in (("dyntanh", "dyntanh", False, "circle"), ("l1sqrt_depth", "l1+sqrt", True, "constant"),
                                               ("tanh", "tanh", False, "circle"), ("l1", "l1", False, "circle"),

@@ -69,3 +69,14 @@ def test_synth_batch_has_valid_and_invalid_rows():
                                                 bt["poses_inv"], bt["intrinsics"], bt["intrinsics_inv"],
                                                 bt["target_crds"], 10)
     assert 50 < n_valid < 500
+
+
+@pytest.mark.parametrize("tag,h,w", [("96x128", 96, 128), ("75x101", 75, 101)])
+def test_encoder_forward_matches_reference(golden, tag, h, w):
+    esd = ace_ref.make_encoder_state(77)
+    with torch.no_grad():
+        f = ace_ref.encoder_forward(esd, ace_ref.synth_image(5, h, w), emulate_half=False)
+    assert list(f.shape) == list(golden[f"encoder_{tag}_shape"])
+    ref = golden[f"encoder_{tag}_sample"]
+    got = f.reshape(-1)[::53].numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
