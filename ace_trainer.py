@@ -1,0 +1,237 @@
+"""Drop-in for the reference's `ace_trainer.TrainerACE` (reference ace_trainer.py:45-728) on the sm_100a kernels.
+
+Same options object (train_ace.py flags), same seeds / generators / call order for everything that is part of the
+integer contract (image order, patch indices, epoch permutations), same output files (fp16 head state dict, log file,
+`poses_<map>_preliminary.txt`). What changes is how the work is executed:
+
+  create_training_buffer : encoder = tcgen05 implicit-GEMM plan, NHWC rows; `torch.multinomial` with the reference's CUDA
+                           generator (bit-exact indices); one fused fill kernel per image instead of ~12 small kernels;
+                           the mask test runs on the CPU copy of the mask (no GPU sync per image)
+  run_epoch/training_step: `acezero_b200.trainer.TrainLoop` — one CUDA graph per iteration, no host sync
+"""
+import logging
+import os
+import random
+import time
+
+import numpy as np
+import torch
+import torchvision.transforms.functional as TF
+from torch.utils.data import DataLoader, sampler
+
+from ace_network import Regressor
+from acezero_b200 import _lib
+from acezero_b200 import posefile
+from acezero_b200.trainer import TrainLoop, BUFFER_KEYS
+
+_logger = logging.getLogger(__name__)
+
+
+def set_seed(seed):
+    """reference ace_trainer.py:36-42"""
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+class TrainerACE:
+    def __init__(self, options, dataset=None):
+        self.log_file = None
+        self.options = options
+        self.device = torch.device('cuda')
+        if getattr(options, "training_buffer_cpu", False):
+            _logger.warning("--training_buffer_cpu is ignored: the patch buffer stays in HBM (<= 9.8 GB of 180 GB)")
+        if getattr(options, "pose_refinement", "none") != "none" or getattr(options, "refine_calibration", False):
+            raise NotImplementedError("pose / calibration refinement is the next row of the hot-path scope table "
+                                      "(SURVEY §8f); the kernels already emit dL/dP and dL/dK for it")
+        if getattr(options, "render_visualization", False):
+            raise NotImplementedError("the visualiser is out of scope (SURVEY §2.1 row 13)")
+
+        # Seeds and generators exactly as the reference (ace_trainer.py:61-80).
+        self.base_seed = options.base_seed
+        set_seed(self.base_seed)
+        self.batch_generator = torch.Generator()
+        self.batch_generator.manual_seed(self.base_seed + 1023)
+        self.loader_generator = torch.Generator()
+        self.loader_generator.manual_seed(self.base_seed + 511)
+        self.sampling_generator = torch.Generator(device=self.device)
+        self.sampling_generator.manual_seed(self.base_seed + 4095)
+
+        self.iteration = 0
+        self.epoch = 0
+        self.training_start = None
+        self.num_data_loader_workers = options.num_data_workers
+        self.use_depth = (options.use_pose_seed >= 0) or (options.depth_files is not None)
+        if self.use_depth and options.depth_files is None:
+            self.num_data_loader_workers = 0
+
+        if dataset is None:
+            # the reference's CamLocDataset (dataset.py) when this runs inside an ACE0 checkout
+            try:
+                from dataset import CamLocDataset
+            except ImportError as e:
+                raise RuntimeError("no dataset object was passed and the reference's dataset.CamLocDataset cannot be "
+                                   f"imported ({e}); dataset I/O is outside the hot path (SURVEY §2.1 row 9)") from e
+            dataset = CamLocDataset(
+                rgb_files=options.rgb_files, pose_files=options.pose_files, ace_pose_file=options.use_ace_pose_file,
+                ace_pose_file_conf_threshold=options.ace_pose_file_conf_threshold, pose_seed=options.use_pose_seed,
+                depth_files=options.depth_files, use_depth=self.use_depth, augment=options.use_aug,
+                aug_rotation=options.aug_rotation, aug_scale_max=options.aug_scale, aug_scale_min=1 / options.aug_scale,
+                image_short_size=options.image_resolution, use_half=options.use_half,
+                use_heuristic_focal_length=options.use_heuristic_focal_length)
+        self.dataset = dataset
+        if options.use_external_focal_length is not None:
+            self.dataset.set_external_focal_length(options.use_external_focal_length)
+        _logger.info("Loaded training scan from: {} -- {} images, mean: {:.2f} {:.2f} {:.2f}".format(
+            options.rgb_files, len(self.dataset), *[float(v) for v in self.dataset.mean_cam_center]))
+
+        # Network (reference :127-148). Head weights are initialised by nn.Conv2d under the global seed, in the
+        # reference's construction order.
+        encoder_state_dict = options.encoder_state_dict if getattr(options, "encoder_state_dict", None) is not None \
+            else torch.load(options.encoder_path, map_location="cpu")
+        if options.load_weights is None:
+            self.regressor = Regressor.create_from_encoder(encoder_state_dict, mean=self.dataset.mean_cam_center,
+                                                           num_head_blocks=options.num_head_blocks,
+                                                           use_homogeneous=options.use_homogeneous)
+        else:
+            head_state_dict = torch.load(options.load_weights, map_location="cpu")
+            self.regressor = Regressor.create_from_split_state_dict(encoder_state_dict, head_state_dict)
+        self.regressor = self.regressor.to(self.device)
+        self.regressor.train()
+
+        self.iterations_output = options.iterations_output
+        self.training_buffer = None
+        self.training_buffer_size = options.max_training_buffer_size
+        self.loop = None
+
+    # ------------------------------------------------------------------------------------------------------------
+    def train(self):
+        creating_buffer_time = 0.
+        self.training_start = time.time()
+        t0 = time.time()
+        self.create_training_buffer()
+        creating_buffer_time += time.time() - t0
+        _logger.info(f"Filled training buffer in {creating_buffer_time:.1f}s.")
+
+        base_file_name, _ = os.path.splitext(self.options.output_map_file)
+        self.log_file = open(base_file_name + '.txt', 'w')
+
+        head = self.regressor.heads.engine(training=True, max_rows=self.options.batch_size)
+        self.loop = TrainLoop(head, self.options, self.training_buffer, use_depth=self.use_depth)
+        t0 = time.time()
+        while self.loop.run_epoch(on_iteration=self._log_iteration):
+            pass
+        torch.cuda.synchronize()
+        training_time = time.time() - t0
+        self.iteration, self.epoch = self.loop.iteration, self.loop.epoch
+        self.regressor.heads.export_engine_weights()
+
+        self.save_model()
+        self.save_poses()
+        self.log_file.close()
+        _logger.info(f'Done without errors. Creating buffer time: {creating_buffer_time:.1f} seconds. '
+                     f'Training time: {training_time:.1f} seconds. '
+                     f'Total time: {time.time() - self.training_start:.1f} seconds.')
+
+    def _log_iteration(self, loop):
+        """reference ace_trainer.py:642-673 (pose statistics are zero without pose refinement)."""
+        st = loop.last_stats
+        loss, inl = float(st[0]), float(st[1]) / loop.b_global
+        if float(st[3]) != 0 or not np.isfinite(loss):
+            _logger.error("Aborting because of NaN loss")  # reference :615-617
+            raise SystemExit(1)
+        t = time.time() - self.training_start
+        _logger.info(f'Iteration: {loop.iteration:6d}|{loop.schedule.max_iterations:6d} / Epoch {loop.epoch:03d}, '
+                     f'Loss: {loss:.1f}, Batch inliers ({self.options.learning_rate_cooldown_trigger_px_threshold}px): '
+                     f'{inl * 100:.1f}%, Time: {t:.0f}s')
+        self.log_file.write(f"{loop.iteration} {t} {loss} {inl} 0.0 0.0 0.0\n")
+
+    # ------------------------------------------------------------------------------------------------------------
+    def create_training_buffer(self):
+        """reference ace_trainer.py:293-452."""
+        o = self.options
+        batch_sampler = sampler.BatchSampler(sampler.RandomSampler(self.dataset, generator=self.batch_generator),
+                                             batch_size=1, drop_last=False)
+
+        def seed_worker(worker_id):
+            worker_seed = torch.initial_seed() % 2 ** 32
+            np.random.seed(worker_seed)
+            random.seed(worker_seed)
+
+        loader = DataLoader(dataset=self.dataset, sampler=batch_sampler, batch_size=None, worker_init_fn=seed_worker,
+                            generator=self.loader_generator, pin_memory=True, num_workers=self.num_data_loader_workers,
+                            persistent_workers=self.num_data_loader_workers > 0,
+                            timeout=60 if self.num_data_loader_workers > 0 else 0)
+        _logger.info("Starting creation of the training buffer.")
+        size = min(o.max_dataset_passes * len(self.dataset) * o.samples_per_image, o.max_training_buffer_size)
+        d = self.device
+        buf = {
+            'features': torch.empty((size, self.regressor.feature_dim), dtype=torch.float16, device=d),
+            'target_px': torch.empty((size, 2), dtype=torch.float32, device=d),
+            'aug_poses_inv': torch.empty((size, 3, 4), dtype=torch.float32, device=d),
+            'poses_inv': torch.empty((size, 4, 4), dtype=torch.float32, device=d),
+            'intrinsics': torch.empty((size, 3, 3), dtype=torch.float32, device=d),
+            'intrinsics_inv': torch.empty((size, 3, 3), dtype=torch.float32, device=d),
+            'target_crds': torch.empty((size, 3), dtype=torch.float32, device=d),
+            'pose_idx': torch.empty((size, 1), dtype=torch.int16, device=d),
+        }
+        lib = _lib.load()
+        enc = self.regressor.encoder
+        self.sample_log = []  # (image index, sampled cells) — kept for the bit-exactness tests
+        keep_log = bool(getattr(o, "keep_sample_log", False))
+        buffer_idx, passes = 0, 0
+        with torch.no_grad():
+            while buffer_idx < o.max_training_buffer_size and passes < o.max_dataset_passes:
+                passes += 1
+                for image, mask, pose_inv, aug_pose_inv, K, Kinv, crds, _, idx in loader:
+                    B = image.shape[0]
+                    assert B == 1, "the buffer is filled image by image (batch_size=1 sampler, reference :298-300)"
+                    feats = enc.forward_nhwc(image.to(d, non_blocking=True))      # [1,h,w,512] fp16
+                    _, H, W, C = feats.shape
+                    # mask at output resolution (reference :373-378); decided on the CPU copy: no GPU sync
+                    m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
+                    if m.sum() == 0:
+                        continue
+                    weights = m.float().view(-1).to(d, non_blocking=True)
+                    n_sel = min(o.samples_per_image * B, o.max_training_buffer_size - buffer_idx)
+                    sample_idxs = torch.multinomial(weights, n_sel, replacement=True,
+                                                    generator=self.sampling_generator)     # reference :423-426
+                    if keep_log:
+                        self.sample_log.append((int(idx), sample_idxs.cpu()))
+                    mats = torch.cat([aug_pose_inv[0, :3].reshape(-1), pose_inv[0].reshape(-1), K[0].reshape(-1),
+                                      Kinv[0].reshape(-1)]).float().pin_memory().to(d, non_blocking=True)
+                    crds_d = crds[0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
+                    rc = lib.acez_buffer_fill(_lib.ptr(feats), _lib.ptr(sample_idxs), n_sel, W, H * W,
+                                              Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats), _lib.ptr(crds_d), int(idx),
+                                              buffer_idx, _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
+                                              _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
+                                              _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
+                                              _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
+                    _lib.check(rc, "acez_buffer_fill")
+                    buffer_idx += n_sel
+                    if buffer_idx >= o.max_training_buffer_size:
+                        break
+        self.training_buffer_size = min(buffer_idx, o.max_training_buffer_size)
+        self.training_buffer = {k: v[:self.training_buffer_size] for k, v in buf.items()}
+        gb = sum(v.element_size() * v.nelement() for v in self.training_buffer.values()) / 1024 ** 3
+        _logger.info(f"Created buffer of {gb:.2f}GB with {passes} passes over the training data.")
+
+    # ------------------------------------------------------------------------------------------------------------
+    def save_model(self):
+        """fp16 head state dict, reference ace_trainer.py:681-694."""
+        head_state_dict = self.regressor.heads.state_dict()
+        for k in head_state_dict:
+            head_state_dict[k] = head_state_dict[k].half()
+        torch.save(head_state_dict, self.options.output_map_file)
+        _logger.info(f"Saved trained head weights to: {self.options.output_map_file}")
+
+    def save_poses(self):
+        """reference ace_trainer.py:696-728: world-to-cam lines, confidence inf."""
+        pose_file = self.options.output_map_file.parent / f"poses_{self.options.output_map_file.stem}_preliminary.txt"
+        with open(pose_file, 'w') as f:
+            for i in range(len(self.dataset)):
+                pose_34 = torch.as_tensor(self.dataset.poses[i]).float().inverse()[:3].cpu().numpy()
+                posefile.write_pose_to_pose_file(f, rgb_file=self.dataset.rgb_files[i], pose=pose_34,
+                                                 confidence=float('inf'),
+                                                 focal_length=self.dataset.get_focal_length(i))
+        _logger.info(f"Saved refined poses to: {pose_file}")

@@ -80,8 +80,9 @@ _lib = None
 EXPORTS = [
     "acez_version", "acez_last_error", "acez_device_check", "acez_gemm_f16", "acez_repro_loss_fwd_bwd",
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
-    "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_forward", "acez_head_train_fwd_bwd",
-    "acez_gather_rows", "acez_gather_rows_multi", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
+    "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_forward", "acez_head_forward_train",
+    "acez_head_backward", "acez_head_train_fwd_bwd",
+    "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
     "acez_encoder_forward",
 ]
@@ -112,9 +113,12 @@ def load():
     lib.acez_head_input_ptr.argtypes = [vp]
     lib.acez_head_input_ptr.restype = vp
     lib.acez_head_forward.argtypes = [vp, vp, i, vp, vp]
+    lib.acez_head_forward_train.argtypes = [vp, vp, i, vp, vp]
+    lib.acez_head_backward.argtypes = [vp, i, vp, vp, vp]
     lib.acez_head_train_fwd_bwd.argtypes = [vp, i, C.POINTER(LossParams), C.POINTER(TrainBatch), vp, vp, vp]
     lib.acez_gather_rows.argtypes = [vp, vp, i, i, vp, vp]
     lib.acez_gather_rows_multi.argtypes = [vp, vp, vp, i, vp, i, vp]
+    lib.acez_buffer_fill.argtypes = [vp, vp, i, i, i, i, vp, vp, i, C.c_longlong] + [vp] * 8 + [vp]
     lib.acez_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, i, vp, vp]
     lib.acez_dsac_workspace_bytes.argtypes = [i, i, i, i]
     lib.acez_dsac_workspace_bytes.restype = C.c_size_t

@@ -148,6 +148,7 @@ struct TailArgs {
   const float* loss_weight_dev; // nullable: overrides lp.loss_weight (per-iteration dyntanh weight, graph-stable)
   const float* tpx; const float* Pin; const float* A; const float* T; const float* K; const float* Kinv; const float* G;
   float* d_P; float* d_Kdiag;
+  const float* d_sc_in; // training == 2: gradient w.r.t. the scene coordinates supplied by the caller (autograd)
   __half* dz;           // DZ[L-1] [rows,512]
   float* g3;            // [rows,4] gradient w.r.t. the fc3 outputs (fp16-rounded values)
   float* stats;         // [4]
@@ -223,6 +224,14 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     if (a.sc_out != nullptr && lane < 3) a.sc_out[(size_t)row * 3 + lane] = X[lane];
     if (!a.training) continue;
 
+    RowLoss o;
+    if (a.training == 2) {
+      // external gradient (torch.autograd through the Regressor module): skip the loss, take dL/dX from the caller
+#pragma unroll
+      for (int i = 0; i < 3; ++i) o.gX[i] = a.d_sc_in[3 * (size_t)row + i];
+      o.loss = 0.f; o.valid = true; o.inlier = false; o.gK00 = o.gK11 = 0.f;
+      o.gc[0] = o.gc[1] = o.gc[2] = 0.f;
+    } else {
     // ---- reprojection loss + backward (all lanes redundantly; inputs are warp-broadcast loads) ----
     float P[12];
     if (a.Pin != nullptr) {
@@ -234,17 +243,17 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     float Kr[9], Ki[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) { Kr[k] = a.K[9 * (size_t)row + k]; Ki[k] = a.Kinv[9 * (size_t)row + k]; }
-    RowLoss o;
     repro_row(lp, X, P, Kr, Ki, a.tpx[2 * (size_t)row], a.tpx[2 * (size_t)row + 1],
               (lp.use_depth && a.G) ? a.G + 3 * (size_t)row : nullptr, o);
-    if (lane == 0) {
+    }
+    if (lane == 0 && a.training == 1) {
       loss_sum += o.loss / (float)lp.divisor;
       inl_sum += o.inlier ? 1.f : 0.f;
       valid_sum += o.valid ? 1.f : 0.f;
       bad |= !isfinite(o.loss);
       if (a.d_Kdiag != nullptr) { a.d_Kdiag[2 * (size_t)row] = o.gK00; a.d_Kdiag[2 * (size_t)row + 1] = o.gK11; }
     }
-    if (a.d_P != nullptr && lane < 12) {
+    if (a.training == 1 && a.d_P != nullptr && lane < 12) {
       const int r = lane >> 2, c = lane & 3;
       a.d_P[12 * (size_t)row + lane] = o.gc[r] * (c < 3 ? X[c] : 1.f);
     }
@@ -297,10 +306,12 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
   if (tid == 0) {
     float l = 0.f, n = 0.f, v = 0.f;
     for (int k = 0; k < kTailThreads / 32; ++k) { l += sRed[0][k]; n += sRed[1][k]; v += sRed[2][k]; }
-    atomicAdd(&a.stats[0], l);
-    atomicAdd(&a.stats[1], n);
-    atomicAdd(&a.stats[2], v);
-    if (any_bad) a.stats[3] = 1.f;
+    if (a.stats != nullptr) {
+      atomicAdd(&a.stats[0], l);
+      atomicAdd(&a.stats[1], n);
+      atomicAdd(&a.stats[2], v);
+      if (any_bad) a.stats[3] = 1.f;
+    }
     if (any_bad_g && a.nonfinite != nullptr) atomicOr(a.nonfinite, 1);
   }
 }
@@ -657,6 +668,62 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
     if (rc) return rc;
   }
   return gemm_launch(h->wgrad, s);
+}
+
+extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc_b3, int* nonfinite,
+                                  acez_stream_t stream) {
+  ACEZ_REQUIRE(h && d_sc_b3 && nonfinite, "head_backward: null argument");
+  ACEZ_REQUIRE(h->cfg.training && h->grads, "head_backward: plan was not created for training");
+  ACEZ_REQUIRE(h->prepared_rows == rows && h->prepared_training >= 1,
+               "head_backward: call acez_head_forward_train with the same row count first");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int L = h->L;
+  float* gW3 = h->grads + (size_t)L * kLayerStride;
+  ACEZ_CUDA(cudaMemsetAsync(gW3, 0, ((size_t)h->C3 * kC + h->C3) * sizeof(float), s));
+  ACEZ_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), s));
+  TailArgs t{};
+  fill_tail_common(h, rows, t);
+  t.training = 2;
+  t.lp.grad_scale = 1.f; t.lp.divisor = 1;
+  t.d_sc_in = d_sc_b3;
+  t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
+  t.g3 = h->G3;
+  t.stats = nullptr;
+  t.nonfinite = nonfinite;
+  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
+  ACEZ_CUDA(cudaGetLastError());
+  {
+    int g = (rows + 31) / 32;
+    if (g > sm_count()) g = sm_count();
+    fc3_wgrad_kernel<<<g, kFc3Threads, 0, s>>>(t.x, h->G3, rows, h->C3, gW3, gW3 + (size_t)h->C3 * kC);
+    ACEZ_CUDA(cudaGetLastError());
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    h->dgrad[l].args.nonfinite = nonfinite;
+    rc = gemm_launch(h->dgrad[l], s);
+    if (rc) return rc;
+  }
+  return gemm_launch(h->wgrad, s);
+}
+
+extern "C" int acez_head_forward_train(acez_head_plan* h, const void* features, int rows, float* sc_out,
+                                       acez_stream_t stream) {
+  ACEZ_REQUIRE(h != nullptr && sc_out != nullptr, "head_forward_train: null argument");
+  ACEZ_REQUIRE(h->cfg.training && h->grads, "head_forward_train: plan was not created for training");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  rc = head_run_forward(h, features, rows, 1, s);
+  if (rc) return rc;
+  TailArgs t{};
+  fill_tail_common(h, rows, t);
+  t.training = 0;
+  t.sc_out = sc_out;
+  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
 }
 
 extern "C" int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_bytes, void* dst,

@@ -1,0 +1,72 @@
+"""Registration loop on the GPU (reference register_mapping.py:201-258): encoder + head + DSAC* per image, with the
+scene coordinates staying on the device (the reference copies them to the CPU and runs RANSAC there, GPU idle).
+Images are grouped into micro-batches of equal size; poses are solved by one batched DSAC* launch per micro-batch and
+read back once at the end. With world_size > 1, image i is processed by rank i % world_size; the RNG of each image is
+keyed by its dataset index, so the result does not depend on the number of ranks.
+"""
+import time
+
+import torch
+
+from . import dsac
+
+
+def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0, max_pixel_error=100.0,
+             base_seed=1305, max_tries=1000000, max_estimates=-1, micro_batch=16, rank=0, world_size=1,
+             device="cuda"):
+    """Returns a list of dicts {file, index, pose (4x4 cam->world numpy), inliers, focal} in processing order."""
+    pending, results = [], []
+    stats = {"images": 0, "seconds": 0.0}
+    t0 = time.time()
+
+    def flush():
+        if not pending:
+            return
+        imgs = torch.cat([p[0] for p in pending], 0).to(device, non_blocking=True)
+        K = torch.stack([p[1] for p in pending], 0)
+        f = K[:, 0, 0].contiguous()
+        with torch.no_grad():
+            sc = network(imgs).float().contiguous()                   # [n,3,h,w] stays on the device
+        # one launch for the whole micro-batch when indices are consecutive-keyed: key image j by its dataset index
+        idx = [int(p[3]) for p in pending]
+        if all(idx[j] == idx[0] + j for j in range(len(idx))):
+            poses, inl = dsac.forward_rgb_batch(sc, f, K[:, 0, 2].contiguous(), K[:, 1, 2].contiguous(), hypotheses,
+                                                threshold, inlier_alpha, max_pixel_error, network.OUTPUT_SUBSAMPLE,
+                                                base_seed, max_tries, image_index_base=idx[0])
+        else:
+            ps, ns = [], []
+            for j in range(len(idx)):
+                pj, nj = dsac.forward_rgb_batch(sc[j:j + 1], f[j:j + 1], K[j:j + 1, 0, 2].contiguous(),
+                                                K[j:j + 1, 1, 2].contiguous(), hypotheses, threshold, inlier_alpha,
+                                                max_pixel_error, network.OUTPUT_SUBSAMPLE, base_seed, max_tries,
+                                                image_index_base=idx[j])
+                ps.append(pj); ns.append(nj)
+            poses, inl = torch.cat(ps), torch.cat(ns)
+        for j, p in enumerate(pending):
+            results.append({"file": p[2], "index": int(p[3]), "pose": poses[j], "inliers": inl[j], "focal": float(f[j])})
+        pending.clear()
+
+    count = 0
+    for image, _, _, _, K, _, _, filenames, indices in loader:
+        B = image.shape[0]
+        for b in range(B):
+            i = int(indices[b]) if torch.is_tensor(indices) else int(indices)
+            if i % world_size != rank:
+                continue
+            Kb = K[b]
+            assert torch.allclose(Kb[0, 0], Kb[1, 1]), "a single focal length is supported (register_mapping.py:219)"
+            item = (image[b:b + 1], Kb.to(device), filenames[b] if not isinstance(filenames, str) else filenames, i)
+            if pending and (pending[0][0].shape != item[0].shape or len(pending) >= micro_batch):
+                flush()
+            pending.append(item)
+            count += 1
+        if 0 < max_estimates <= count:
+            break
+    flush()
+    torch.cuda.synchronize()
+    for r in results:   # one device->host transfer at the end
+        r["pose"] = r["pose"].cpu().numpy()
+        r["inliers"] = int(r["inliers"])
+    stats["images"] = len(results)
+    stats["seconds"] = time.time() - t0
+    return results, stats

@@ -153,6 +153,13 @@ void* acez_head_input_ptr(acez_head_plan* plan);
  * (nullable: run only the hidden-layer GEMM chain, used by bench.py to time that kernel alone). */
 int acez_head_forward(acez_head_plan* plan, const void* features, int rows, float* sc_out, acez_stream_t stream);
 
+/* The same forward on a training plan, keeping what the backward needs (activations, ReLU masks), followed by the
+ * backward from an externally supplied dL/d(scene coordinates) [rows,3] (unscaled or pre-scaled by the caller) into
+ * `grads` — the pair torch.autograd needs when the reference's own training loop drives `Regressor`
+ * (ace_trainer.py:516-518 forward, :627 backward). */
+int acez_head_forward_train(acez_head_plan* plan, const void* features, int rows, float* sc_out, acez_stream_t stream);
+int acez_head_backward(acez_head_plan* plan, int rows, const float* d_sc_b3, int* nonfinite, acez_stream_t stream);
+
 typedef struct acez_train_batch {
   const void* features;        /* fp16 [rows,512]; nullable = already in the plan's input buffer */
   const float* target_px_b2;
@@ -181,6 +188,16 @@ int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_byte
 /* The same for up to 8 arrays sharing one index vector, in ONE launch (all arrays of the patch buffer). */
 int acez_gather_rows_multi(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
                            const int64_t* idx, int rows, acez_stream_t stream);
+
+/* Patch-buffer fill for one image (reference ace_trainer.py:381-436, ~12 small kernels): writes the rows
+ * [row0, row0 + n_samples) of all 8 buffer arrays for the cells `sample_idx` (the int64 output of torch.multinomial,
+ * ace_trainer.py:423-426 — the caller keeps torch's generator and call order, so indices stay bit-exact).
+ * feat_rows: fp16 NHWC rows [cells,512] of the image; mats46: device floats aug_inv(12) | pose_inv(16) | K(9) | Kinv(9);
+ * target_crds_3hw: planar [3,cells] or NULL (zeros, dataset.py returns zeros without depth). */
+int acez_buffer_fill(const void* feat_rows, const int64_t* sample_idx, int n_samples, int map_w, int cells, int subsample,
+                     const float* mats46, const float* target_crds_3hw, int pose_idx, long long row0, void* d_features,
+                     float* d_target_px, float* d_aug_inv, float* d_pose_inv, float* d_K, float* d_Kinv,
+                     float* d_target_crds, int16_t* d_pose_idx, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * GradScaler unscale + inf check + AdamW + GradScaler.update, entirely on the device (CUDA-graph capturable, no

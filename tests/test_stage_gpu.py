@@ -1,0 +1,155 @@
+"""Stage-level GPU tests: buffer creation (bit-exact patch indices, fused fill kernel), the drop-in `Regressor` module
+(state-dict compatibility, autograd bridge), and mapping + registration end to end on a procedural scene with known
+poses (the reference's own acceptance criterion is pose accuracy, eval_poses.py:138-191)."""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ace_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _options(tmp_path, **kw):
+    import train_ace
+    o = train_ace.build_parser().parse_args(["synthetic", str(tmp_path / "map.pt")])
+    o.encoder_state_dict = None
+    o.num_data_workers = 0
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def test_training_buffer_indices_are_bit_exact_and_rows_match(tmp_path):
+    """A3/A2: same generators, same call order => the sampled cells equal an independent replay of
+    torch.multinomial(seed base+4095) in RandomSampler(seed base+1023) image order; every buffer row equals the
+    reference's formulae (ace_trainer.py:381-436) evaluated with torch."""
+    from ace_trainer import TrainerACE
+    from acezero_b200.synthetic import SyntheticDataset
+    from acezero_b200.weights import random_encoder_state
+    from torch.utils.data import sampler
+    ds = SyntheticDataset(6, H=96, W=128, device="cuda", with_coords=False)
+    o = _options(tmp_path, samples_per_image=256, max_dataset_passes=2, keep_sample_log=True, batch_size=512)
+    o.encoder_state_dict = random_encoder_state(77)
+    tr = TrainerACE(o, dataset=ds)
+    tr.create_training_buffer()
+    buf = tr.training_buffer
+    assert buf["features"].shape == (2 * 6 * 256, 512)
+    # independent replay of the integer contract
+    bg = torch.Generator(); bg.manual_seed(o.base_seed + 1023)
+    sg = torch.Generator(device="cuda"); sg.manual_seed(o.base_seed + 4095)
+    order = []
+    for _ in range(2):
+        order += [i[0] for i in sampler.BatchSampler(sampler.RandomSampler(ds, generator=bg), 1, False)]
+    assert [i for i, _ in tr.sample_log] == order
+    row = 0
+    enc = tr.regressor.encoder
+    for img_idx, cells in tr.sample_log:
+        w = torch.ones(12 * 16, device="cuda")
+        expect = torch.multinomial(w, 256, replacement=True, generator=sg).cpu()
+        assert torch.equal(cells, expect)
+        item = ds[[img_idx]]
+        feats = enc.forward_nhwc(item[0].cuda()).view(-1, 512)
+        sl = slice(row, row + 256)
+        assert torch.equal(buf["features"][sl], feats[cells.cuda()])
+        px = torch.stack([8 * ((cells % 16).float() + 0.5), 8 * ((cells // 16).float() + 0.5)], 1)
+        assert torch.equal(buf["target_px"][sl].cpu(), px)
+        assert torch.equal(buf["poses_inv"][sl].cpu(), item[2].expand(256, 4, 4))
+        assert torch.equal(buf["aug_poses_inv"][sl].cpu(), item[3][:, :3].expand(256, 3, 4))
+        assert torch.equal(buf["intrinsics"][sl].cpu(), item[4].expand(256, 3, 3))
+        assert torch.equal(buf["intrinsics_inv"][sl].cpu(), item[5].expand(256, 3, 3))
+        assert (buf["pose_idx"][sl].cpu() == img_idx).all()
+        row += 256
+
+
+def test_regressor_state_dict_and_forward_match_oracle():
+    """A10: reference key names / shapes; forward == oracle (autocast-emulating) on encoder + head."""
+    from ace_network import Regressor
+    esd = ace_ref.make_encoder_state(77)
+    hsd = ace_ref.make_head_state(200, 1, True, mean=(0.3, -0.2, 1.5))
+    reg = Regressor.create_from_split_state_dict(esd, {k: v.half() for k, v in hsd.items()}).cuda().eval()
+    keys = list(reg.state_dict().keys())
+    assert keys[:2] == ["encoder.conv1.weight", "encoder.conv1.bias"]
+    assert [k for k in keys if k.startswith("heads.")] == ["heads." + k for k in hsd.keys()]
+    assert reg.heads.num_head_blocks == 1 and reg.heads.use_homogeneous
+    img = ace_ref.synth_image(5, 96, 128)
+    with torch.no_grad():
+        sc = reg(img.cuda()).float().cpu()
+        assert tuple(sc.shape) == (1, 3, 12, 16)
+        hsd16 = {k: v.half().float() for k, v in hsd.items()}
+        f = ace_ref.encoder_forward(esd, img, emulate_half=True)
+        ref = ace_ref.head_forward(hsd16, f.permute(0, 2, 3, 1).reshape(-1, 512), 1, True, emulate_half=True)
+        ref = ref.view(1, 12, 16, 3).permute(0, 3, 1, 2)
+        feats = reg.get_features(img.cuda())
+        assert tuple(feats.shape) == (1, 512, 12, 16)
+        sc2 = reg.get_scene_coordinates(feats).float().cpu()
+    assert (sc - ref).abs().max() < 2e-2
+    assert torch.equal(sc, sc2)
+
+
+def test_head_autograd_bridge_matches_oracle():
+    """The reference's own loop differentiates through Regressor.get_scene_coordinates (ace_trainer.py:516-518,627)."""
+    from ace_network import Regressor
+    hsd = ace_ref.make_head_state(201, 1, True)
+    reg = Regressor(torch.zeros(3), 1, True).cuda().train()
+    reg.heads.load_state_dict(hsd)
+    feats = ace_ref.synth_batch(12, 512)["features"]
+    x = feats.cuda()[None, None, ...].view(-1, 16, 32, 512).permute(0, 3, 1, 2)   # ace_trainer.py:516
+    sc = reg.get_scene_coordinates(x)
+    g = torch.randn(sc.shape, generator=torch.Generator().manual_seed(0)).cuda() * 8.0
+    (sc * g).sum().backward()
+    tr = ace_ref.TrainerRef(hsd, 1, True, ace_ref.LossOptions(), lambda i: 0.0, emulate_half=True)
+    ref = tr.forward(feats.float())
+    gr = g.cpu().permute(0, 2, 3, 1).reshape(-1, 3)
+    (ref * gr).sum().backward()
+    for n in ("res3_conv1", "0c2", "fc2", "fc3"):
+        got = dict(reg.heads.named_modules())[n].weight.grad.reshape(-1).cpu()
+        want = tr.sd[n + ".weight"].grad.reshape(-1)
+        rel = (got - want).norm() / want.norm()
+        assert rel < 3e-2, (n, float(rel))
+
+
+def _pose_err(T_est, T_gt):
+    dR = T_est[:3, :3].T @ T_gt[:3, :3]
+    return float(np.rad2deg(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))), float(np.linalg.norm(T_est[:3, 3] - T_gt[:3, 3]))
+
+
+def test_mapping_then_registration_recovers_held_out_poses(tmp_path):
+    """configs[1] in miniature: train the head on 48 rendered frames of a textured room, register 12 held-out views
+    through the CLIs' code path (TrainerACE.train -> .pt -> Regressor -> register); median error < 5 cm / 5 deg,
+    the reference's acceptance thresholds (eval_poses.py)."""
+    from ace_trainer import TrainerACE
+    from ace_network import Regressor
+    from acezero_b200.synthetic import SyntheticDataset
+    from acezero_b200.weights import random_encoder_state
+    from acezero_b200.registration import register
+    from torch.utils.data import DataLoader
+    esd = random_encoder_state(77)
+    ds = SyntheticDataset(48, H=240, W=320, focal=262.5, device="cuda")
+    o = _options(tmp_path, iterations=2500, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
+                 use_external_focal_length=262.5)
+    o.encoder_state_dict = esd
+    tr = TrainerACE(o, dataset=ds)
+    tr.train()
+    assert (tmp_path / "map.pt").exists() and (tmp_path / "poses_map_preliminary.txt").exists()
+    lines = (tmp_path / "map.txt").read_text().strip().splitlines()
+    first, last = [float(x) for x in lines[0].split()], [float(x) for x in lines[-1].split()]
+    assert last[2] < 0.5 * first[2], "the loss must fall"          # columns: iter time loss inliers ...
+    assert last[3] > 0.5, f"batch inliers {last[3]}"
+    head_sd = torch.load(tmp_path / "map.pt", map_location="cpu")
+    assert all(v.dtype == torch.float16 for v in head_sd.values())
+    net = Regressor.create_from_split_state_dict(esd, head_sd).cuda().eval()
+    test = SyntheticDataset(12, H=240, W=320, focal=262.5, device="cuda", s_offset=0.5)
+    # same path, sampled between the training frames (12 of the 48 half-way points)
+    from acezero_b200.synthetic import trajectory
+    test.gt_poses = trajectory(48, s_offset=0.5)[::4]
+    test.poses = [p.clone() for p in test.gt_poses]
+    res, stats = register(net, DataLoader(test, shuffle=False, num_workers=0), hypotheses=64, max_tries=16)
+    errs = [_pose_err(r["pose"].astype(np.float64), test.gt_poses[r["index"]].numpy().astype(np.float64)) for r in res]
+    rot = np.median([e[0] for e in errs]); tra = np.median([e[1] for e in errs])
+    assert len(res) == 12
+    assert rot < 5.0 and tra < 0.05, (rot, tra, errs)
+    assert np.median([r["inliers"] for r in res]) > 300
