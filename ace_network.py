@@ -35,13 +35,13 @@ class Encoder(nn.Module):
         self._engine = None
         self._engine_version = None
 
-    def _version(self):
+    def _weights_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self):
         """The CUDA plan over the current (frozen) weights; rebuilt if they were replaced or modified."""
         from acezero_b200.encoder import EncoderEngine
-        v = self._version()
+        v = self._weights_version()
         if self._engine is None or v != self._engine_version:
             self._engine = EncoderEngine(self.state_dict(), device=next(self.parameters()).device)
             self._engine_version = v
@@ -142,7 +142,7 @@ class Head(nn.Module):
         mods = dict(self.named_modules())
         return [getattr(mods[n], s) for n in self._layer_names() for s in ("weight", "bias")]
 
-    def _version(self):
+    def _weights_version(self):
         return tuple((p.data_ptr(), p._version) for p in self._params()) + (self.mean.data_ptr(), self.mean._version)
 
     def engine(self, training=False, max_rows=5120):
@@ -158,7 +158,7 @@ class Head(nn.Module):
                                       max_rows=max_rows, training=training, homogeneous_min_scale=min_scale,
                                       homogeneous_max_scale=max_scale, device=dev)
             self._engine_version = None
-        v = self._version()
+        v = self._weights_version()
         if v != self._engine_version:
             sd = {k: t for k, t in self.state_dict().items()}
             self._engine.load_state(sd)
@@ -178,7 +178,7 @@ class Head(nn.Module):
             for n in self._layer_names():
                 mods[n].weight.copy_(v[n + ".weight"])
                 mods[n].bias.copy_(v[n + ".bias"])
-        self._engine_version = self._version()
+        self._engine_version = self._weights_version()
 
     # ---- forward ---------------------------------------------------------------------------------------------
     def forward_rows(self, rows_f16):
