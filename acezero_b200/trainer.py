@@ -201,12 +201,8 @@ class TrainLoop:
                         target_crds=bt["target_crds"] if self.use_depth else None, features=None, d_P=d_P,
                         d_Kdiag=d_Kdiag, use_device_scale=True, use_device_loss_weight=True)
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(h.grads)
-            small = torch.cat([h.stats, h.found_inf.float()])
-            dist.all_reduce(small)
-            h.stats.copy_(small[:4])
-            h.found_inf.copy_((small[4:] > 0).int())
+            from .parallel import allreduce_training_state
+            allreduce_training_state(h.grads, h.stats, h.found_inf)
         h.adamw_step(use_scaler=self.use_scaler)
 
     def train_iteration(self, indices, want_stats=False):
@@ -215,8 +211,9 @@ class TrainLoop:
         sch.check_and_set_cooldown(self.iteration)                    # ace_trainer.py:506
         if self.iteration >= sch.max_iterations:                      # :509
             return False
-        lo = self.rank * self.b
-        self.idx_host.copy_(indices[lo:lo + self.b])
+        from .parallel import shard_bounds
+        lo, hi = shard_bounds(self.rank, self.world, self.b_global)
+        self.idx_host.copy_(indices[lo:hi])
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
         self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
         if self.use_graph:
