@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("bias_grad", C.c_void_p), ("bias_grad_zstride", C.c_longlong),
         ("a_lbo", C.c_uint), ("a_sbo", C.c_uint), ("a_kstep", C.c_uint),
         ("b_lbo", C.c_uint), ("b_sbo", C.c_uint), ("b_kstep", C.c_uint),
+        ("dbg_clock", C.c_void_p),
     ]
 
 

@@ -46,6 +46,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* dbg = args.dbg_clock
+                       ? args.dbg_clock + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
+                       : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
   const int z = blockIdx.z;
@@ -68,17 +72,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int i = threadIdx.x - 64; i < Cfg::kOnesBytes / 4; i += 128) o[i] = __floats2half2_rn(1.f, 1.f);
     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
   }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of the previous kernel in the stream; global memory is only touched after the dependency has resolved.
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (dbg && threadIdx.x == 0) dbg[2] = clock64();
   if (EPI == EPI_FWD && warp >= 2) {
     for (int i = threadIdx.x - 64; i < BN; i += 128) {
       const int n = n0 + i;
       // autocast casts the fp32 bias to fp16 before the conv adds it
       sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(args.bias[n])) : 0.f;
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -123,6 +134,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int kb = 0; kb < k_blocks; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
+      if (dbg && kb == 0 && lane == 0) dbg[3] = clock64();
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(sA + stage * Cfg::kAStage);
         const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBStage);
@@ -161,6 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     bool bad = false;
 #pragma unroll 1
@@ -253,12 +266,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (dbg && threadIdx.x == 64) dbg[6] = clock64();
+  if (dbg && threadIdx.x == 32) dbg[4] = clock64();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -322,8 +338,17 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   }
   dim3 grid((L.args.N + BN - 1) / BN, (L.args.M + BM - 1) / BM, L.batch);
   if (L.args.conv.enabled) grid.y = L.args.conv.tiles_x * L.args.conv.tiles_y * L.batch, grid.z = 1;
-  kern<<<grid, kThreads, GemmCfg<BN>::kSmem, stream>>>(L.tmA, L.tmB, L.args);
-  ACEZ_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = GemmCfg<BN>::kSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.args));
   return ACEZ_OK;
 }
 
@@ -385,6 +410,7 @@ extern "C" int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream) {
   a.ldo32 = d->ldo32;
   a.bias_grad = d->bias_grad;
   a.bias_grad_zstride = d->bias_grad_zstride;
+  a.dbg_clock = reinterpret_cast<long long*>(d->dbg_clock);
   if (d->a_lbo) a.a_lbo = d->a_lbo;
   if (d->a_sbo) a.a_sbo = d->a_sbo;
   if (d->a_kstep) a.a_kstep = d->a_kstep;

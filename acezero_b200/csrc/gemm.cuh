@@ -56,6 +56,7 @@ struct GemmArgs {
   int ldo32;
   float* bias_grad;      // [z][M] nullable: column sum over the contraction dimension of A (dZ^T 1)
   long long bias_grad_zstride;
+  long long* dbg_clock;  // nullable: 8 clock64 stamps per CTA (profiling probe)
 };
 
 struct GemmLaunch {

@@ -140,7 +140,7 @@ class TrainLoop:
         self.epoch = 0
         self.training_generator = torch.Generator()
         self.training_generator.manual_seed(options.base_seed + 8191)  # ace_trainer.py:79-80
-        self.use_graph = use_graph and world_size == 1
+        self.use_graph = use_graph
         self._graph = None
         self._warm = 0
         self._graph_host = None
@@ -187,19 +187,24 @@ class TrainLoop:
         _lib.check(rc, "acez_gather_rows_multi")
 
     # ------------------------------------------------------------------ one iteration
-    def _enqueue_compute(self, P=None, d_P=None, d_Kdiag=None, gather=True):
+    def _enqueue_compute(self, P=None, d_P=None, d_Kdiag=None, gather=True, part="all"):
         """gather + forward + loss + backward (+ all-reduce) + GradScaler/AdamW on the current stream."""
         o, h = self.o, self.head
         lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
                            o.depth_target, 1.0)
-        if gather:
+        if part in ("all", "fwd_bwd") and gather:
             self._gather()
         bt = self.batch
+        if part == "optimizer":
+            h.adamw_step(use_scaler=self.use_scaler)
+            return
         h.train_fwd_bwd(self.b, lp, bt["target_px"], bt["intrinsics"], bt["intrinsics_inv"],
                         aug_inv=bt["aug_poses_inv"], pose_inv=bt["poses_inv"], P=P,
                         target_crds=bt["target_crds"] if self.use_depth else None, features=None, d_P=d_P,
                         d_Kdiag=d_Kdiag, use_device_scale=True, use_device_loss_weight=True)
+        if part == "fwd_bwd":
+            return
         if self.world > 1:
             from .parallel import allreduce_training_state
             allreduce_training_state(h.grads, h.stats, h.found_inf)
@@ -272,11 +277,26 @@ class TrainLoop:
                 self._warm += 1
                 self._enqueue_compute()
                 return
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue_compute()
-            self._graph = g
-        self._graph.replay()
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_compute()
+                self._graph = (g,)
+            else:
+                # data parallel: the NCCL all-reduces stay outside the graphs (two graphs around them)
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._enqueue_compute(part="fwd_bwd")
+                with torch.cuda.graph(gb):
+                    self._enqueue_compute(part="optimizer")
+                self._graph = (ga, gb)
+        if self.world == 1:
+            self._graph[0].replay()
+        else:
+            from .parallel import allreduce_training_state
+            self._graph[0].replay()
+            allreduce_training_state(self.head.grads, self.head.stats, self.head.found_inf)
+            self._graph[1].replay()
 
     # ------------------------------------------------------------------ epochs
     def run_epoch(self, on_iteration=None):

@@ -241,7 +241,7 @@ def run_ours(args):
     head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B, training=True, device=dev)
     head.load_state(ace_ref.make_head_state(200, 1, True))
     buf = synth_buffer(BUFFER_ROWS, dev, 2089)   # identical on every rank (same seed), as the replicated buffer is
-    loop = TrainLoop(head, o, buf, rank=rank, world_size=world, use_graph=(world == 1))
+    loop = TrainLoop(head, o, buf, rank=rank, world_size=world, use_graph=True)
     perm = torch.randperm(BUFFER_ROWS, generator=loop.training_generator)
     bg = B * world
     n_batches = BUFFER_ROWS // bg

@@ -75,6 +75,8 @@ typedef struct acez_gemm_desc {
   long long bias_grad_zstride;
   /* 0 = library defaults; non-zero values override the UMMA shared-memory descriptor constants (test probing) */
   unsigned a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+  void* dbg_clock; /* nullable: int64 [CTAs][8] clock64() stamps (entry, prologue, dependency, first tile, MMA issued,
+                      accumulator ready, epilogue done, exit) */
 } acez_gemm_desc;
 
 int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream);
