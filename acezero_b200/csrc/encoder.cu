@@ -214,6 +214,8 @@ static int encoder_prepare(acez_encoder_plan* e, int n, int H, int W, void* out)
   if ((rc = conv_launch_prepare(L(9), e->act[6], n, h8, w8, 256, e->wp[10], 512, 1, 1, h8, w8))) return rc;
   L(9)->args.bias = e->b[10]; L(9)->args.relu = 0; L(9)->args.out = nullptr; L(9)->args.resid = e->act[9];
   L(9)->args.out2 = reinterpret_cast<__half*>(out);
+  for (int i = 0; i < 10; ++i)
+    if ((rc = gemm_finalize(L(i)))) return rc;
   e->prepared_n = n; e->prepared_h = H; e->prepared_w = W; e->prepared_out = out;
   return ACEZ_OK;
 }

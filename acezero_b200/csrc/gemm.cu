@@ -13,21 +13,27 @@ static constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle row
 static constexpr int kThreads = 192;
 static constexpr uint32_t kSw128 = 2;
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int kAStage = BM * BK * 2;
   static constexpr int kBStage = BN * BK * 2;
   static constexpr int kStage = kAStage + kBStage;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // fp16 epilogues reserve one 128 x BN operand tile (residual / ReLU mask, prefetched by TMA during the main loop) and
+  // reuse the pipeline stages as staging for the TMA stores of up to two output tiles
+  static constexpr int kOpBytes = (EPI == EPI_WGRAD) ? 0 : BM * BN * 2;
+  static constexpr int kStages = (EPI == EPI_WGRAD) ? 6 : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
   static constexpr int kOnesBytes = 16 * BK * 2;  // 16 x 64 tile of 1.0 for the bias-gradient column
-  static constexpr int kSmem = kStages * kStage + kOnesBytes + BN * 4 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kSmem =
+      kStages * kStage + kOpBytes + kOnesBytes + BN * 4 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+  static_assert(EPI == EPI_WGRAD || kStages * kStage >= 2 * BM * BN * 2, "stage memory must hold two output tiles");
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                    const __grid_constant__ CUtensorMap tmOp, const GemmArgs args) {
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kBiasCol = (EPI == EPI_WGRAD);
   constexpr uint32_t kTmemCols = kBiasCol ? (BN >= 256 ? 512 : 2 * BN) : (BN < 32 ? 32 : BN);
@@ -37,12 +43,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kAStage;
-  uint8_t* sOnes = smem + kStages * Cfg::kStage;
+  uint8_t* sOp = smem + kStages * Cfg::kStage;
+  uint8_t* sOnes = sOp + Cfg::kOpBytes;
   float* sBias = reinterpret_cast<float*>(sOnes + Cfg::kOnesBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sBias + BN);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* op_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(op_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -54,15 +62,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m0 = blockIdx.y * BM;
   const int z = blockIdx.z;
   const int k_blocks = args.k_blocks;
+  // implicit-GEMM tile coordinates (conv front end)
+  int c_tx = 0, c_ty = 0, c_img = 0;
+  if (args.conv.enabled) {
+    const ConvGeom& cg = args.conv;
+    const int tile = blockIdx.y;
+    c_tx = tile % cg.tiles_x; c_ty = (tile / cg.tiles_x) % cg.tiles_y; c_img = tile / (cg.tiles_x * cg.tiles_y);
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (EPI != EPI_WGRAD) {
+      if (args.st_out) tma_prefetch_desc(&tmOut);
+      if (args.st_out2) tma_prefetch_desc(&tmOut2);
+      if (args.ld_op) tma_prefetch_desc(&tmOp);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(op_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -76,24 +97,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
   // tail of the previous kernel in the stream; global memory is only touched after the dependency has resolved.
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   pdl_wait();
   pdl_launch_dependents();
   if (dbg && threadIdx.x == 0) dbg[2] = clock64();
-  if (EPI == EPI_FWD && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      const int n = n0 + i;
-      // autocast casts the fp32 bias to fp16 before the conv adds it
-      sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(args.bias[n])) : 0.f;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-  }
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
+      if (EPI != EPI_WGRAD && args.ld_op) {
+        // epilogue operand tile (residual / ReLU mask): lands while the main loop runs
+        mbar_arrive_expect_tx(op_bar, BM * BN * 2);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) {
+          if (args.conv.enabled)
+            tma_load_4d(sOp + b * 16384, &tmOp, op_bar, n0 + 64 * b, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
+          else
+            tma_load_3d(sOp + b * 16384, &tmOp, op_bar, n0 + 64 * b, m0, 0);
+        }
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
@@ -107,12 +131,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (args.conv.enabled) {
           // implicit GEMM: k-block = (filter tap, 64-channel chunk); one 4-D box = 16 x 8 pixels x 64 channels
           const ConvGeom& cg = args.conv;
-          const int tile = blockIdx.y;
-          const int tx = tile % cg.tiles_x, ty = (tile / cg.tiles_x) % cg.tiles_y, img = tile / (cg.tiles_x * cg.tiles_y);
           const int tap = kb / cg.cin_blocks, cb = kb - tap * cg.cin_blocks;
           const int ky = tap / cg.ksize, kx = tap - ky * cg.ksize;
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], cb * 64, tx * kConvTileW * cg.stride + kx - cg.pad,
-                      ty * kConvTileH * cg.stride + ky - cg.pad, img);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], cb * 64, c_tx * kConvTileW * cg.stride + kx - cg.pad,
+                      c_ty * kConvTileH * cg.stride + ky - cg.pad, c_img);
         } else {
           tma_load_3d(a_dst, &tmA, &full_bar[stage], kb * BK, m0, z);
         }
@@ -157,24 +179,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (dbg && lane == 0) dbg[4] = clock64();
   } else {
     // ------------------------------ epilogue (4 warps <-> 4 TMEM lane quarters) ------------------------------
     const int quarter = warp & 3;
-    int row = m0 + quarter * 32 + lane;
+    const int r = quarter * 32 + lane;  // row inside the tile
+    int row = m0 + r;
     bool row_ok = row < args.M;
     if (args.conv.enabled) {
       const ConvGeom& cg = args.conv;
-      const int tile = blockIdx.y;
-      const int tx = tile % cg.tiles_x, ty = (tile / cg.tiles_x) % cg.tiles_y, img = tile / (cg.tiles_x * cg.tiles_y);
-      const int r = quarter * 32 + lane;
-      const int py = ty * kConvTileH + r / kConvTileW, px = tx * kConvTileW + r % kConvTileW;
+      const int py = c_ty * kConvTileH + r / kConvTileW, px = c_tx * kConvTileW + r % kConvTileW;
       row_ok = (py < cg.Ho) && (px < cg.Wo);
-      row = (img * cg.Ho + py) * cg.Wo + px;  // NHWC pixel index
+      row = (c_img * cg.Ho + py) * cg.Wo + px;  // NHWC pixel index
     }
+    if (EPI == EPI_FWD) {
+      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        const int n = n0 + i;
+        // autocast casts the fp32 bias to fp16 before the conv adds it
+        sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(args.bias[n])) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    }
+    if (EPI != EPI_WGRAD && args.ld_op) mbar_wait(op_bar, 0);
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // all pipeline stages are drained by now: their memory stages the output tiles for the TMA stores
+    uint8_t* sOut = smem;
+    uint8_t* sOut2 = smem + BM * BN * 2;
+    const uint32_t swz = (uint32_t)(r & 7);
     bool bad = false;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -182,8 +216,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tmem_ld_32x32(t_row + c * 32, v);
       tmem_ld_wait();
       const int ncol = n0 + c * 32;
-      if (!row_ok || ncol >= args.N) continue;
       if (EPI == EPI_WGRAD) {
+        if (!row_ok || ncol >= args.N) continue;
         float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride +
                                                 (long long)row * args.ldo32 + ncol);
 #pragma unroll
@@ -191,18 +225,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       } else {
-        const long long off = (long long)row * args.ldo + ncol;
-        uint4 o[4], o2[4];
-        if (EPI == EPI_FWD) {
-          uint4 r[4];
-          if (args.resid != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(args.resid + off);
+        // shared-memory position of this thread's 32 columns: 64-column box, 128-byte rows, SWIZZLE_128B chunks
+        const int box = c >> 1, jbase = (c & 1) * 4;
+        const uint32_t row_off = (uint32_t)box * 16384u + (uint32_t)r * 128u;
+        uint4 opv[4];
+        if (args.ld_op) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) r[j] = rp[j];
-          }
-          __half2* oh = reinterpret_cast<__half2*>(o);
-          __half2* o2h = reinterpret_cast<__half2*>(o2);
-          const __half2* rh = reinterpret_cast<const __half2*>(r);
+          for (int q = 0; q < 4; ++q)
+            opv[q] = *reinterpret_cast<const uint4*>(sOp + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4));
+        }
+        uint4 o[4], o2[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+        __half2* o2h = reinterpret_cast<__half2*>(o2);
+        const __half2* ph = reinterpret_cast<const __half2*>(opv);
+        if (EPI == EPI_FWD) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a = __uint_as_float(v[2 * j]) + sBias[c * 32 + 2 * j];
@@ -210,51 +246,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (args.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
             const __half2 h = __floats2half2_rn(a, b);
             oh[j] = h;
-            if (args.resid != nullptr) o2h[j] = __hadd2(rh[j], h);
+            if (args.ld_op) o2h[j] = __hadd2(ph[j], h);  // residual sum in fp16, as the reference's `res + x`
           }
         } else {  // EPI_DGRAD
-          uint4 mk[4], ad[4];
-          const uint4* mp = reinterpret_cast<const uint4*>(args.mask + off);
+          uint4 ad[4];
+          const bool has_add = args.addend != nullptr;
+          if (has_add) {
+            if (row_ok && ncol < args.N) {
+              const uint4* ap = reinterpret_cast<const uint4*>(args.addend + (long long)row * args.ldo + ncol);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mk[j] = mp[j];
-          if (args.addend != nullptr) {
-            const uint4* ap = reinterpret_cast<const uint4*>(args.addend + off);
+              for (int j = 0; j < 4; ++j) ad[j] = ap[j];
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ad[j] = ap[j];
+              for (int j = 0; j < 4; ++j) ad[j] = make_uint4(0, 0, 0, 0);
+            }
           }
-          __half2* oh = reinterpret_cast<__half2*>(o);
-          __half2* o2h = reinterpret_cast<__half2*>(o2);
-          const __half2* mh = reinterpret_cast<const __half2*>(mk);
           const __half2* ah = reinterpret_cast<const __half2*>(ad);
           const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
             __half2 h = __floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            if (args.addend != nullptr) h = __hadd2(h, ah[j]);
+            if (has_add) h = __hadd2(h, ah[j]);
             o2h[j] = h;
             const float2 hf = __half22float2(h);
             bad |= !(isfinite(hf.x) && isfinite(hf.y));
-            const __half2 gt = __hgt2(mh[j], zero2);  // 1.0 where mask > 0
-            oh[j] = __hmul2(h, gt);
-            // inf * 0 would give nan: force exact zero where masked
-            const float2 g = __half22float2(gt);
-            if (g.x == 0.f) oh[j].x = __float2half_rn(0.f);
-            if (g.y == 0.f) oh[j].y = __float2half_rn(0.f);
+            const float2 mf = __half22float2(ph[j]);  // ReLU mask source (prefetched tile)
+            __half2 m = h;
+            if (!(mf.x > 0.f)) m.x = __float2half_rn(0.f);
+            if (!(mf.y > 0.f)) m.y = __float2half_rn(0.f);
+            oh[j] = m;
           }
         }
-        if (args.out != nullptr) {
-          uint4* op = reinterpret_cast<uint4*>(args.out + off);
+        if (args.st_out) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = o[j];
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(sOut + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4)) = o[q];
         }
-        if (args.out2 != nullptr && (EPI == EPI_DGRAD || args.resid != nullptr)) {
-          uint4* o2p = reinterpret_cast<uint4*>(args.out2 + off);
+        if (args.st_out2) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o2p[j] = o2[j];
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(sOut2 + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4)) = o2[q];
+        }
+        if (c & 1) {
+          // a 64-column box is complete in shared memory: hand it to the TMA store engine
+          fence_proxy_async();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (threadIdx.x == 64) {
+            if (args.conv.enabled) {
+              if (args.st_out) tma_store_4d(&tmOut, sOut + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
+              if (args.st_out2) tma_store_4d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
+            } else {
+              if (args.st_out) tma_store_3d(&tmOut, sOut + box * 16384, n0 + 64 * box, m0, 0);
+              if (args.st_out2) tma_store_3d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, m0, 0);
+            }
+            tma_store_commit();
+          }
         }
       }
     }
+    if (EPI != EPI_WGRAD && threadIdx.x == 64) tma_store_wait_all();
     if (kBiasCol && n0 == 0 && args.bias_grad != nullptr) {
       uint32_t v[32];
       tmem_ld_32x32(t_row + BN, v);
@@ -264,10 +315,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (EPI == EPI_DGRAD && args.nonfinite != nullptr) {
       if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
   }
 
-  if (dbg && threadIdx.x == 64) dbg[6] = clock64();
-  if (dbg && threadIdx.x == 32) dbg[4] = clock64();
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -328,12 +378,58 @@ int gemm_prepare(GemmLaunch* L, const GemmProblem& p) {
   return encode_operand(&L->tmB, p.B, p.b_mn, p.N, p.K, p.ldb, p.batch, p.b_zstride, bn);
 }
 
+// Tensor maps of the fp16 epilogue: out / out2 (TMA stores from the staged tile) and the prefetched operand tile
+// (residual for EPI_FWD, ReLU mask for EPI_DGRAD). All are [rows, ldo] row-major fp16 with the output's geometry.
+static int encode_tile_map(CUtensorMap* tm, const void* base, const GemmArgs& a, int batch_images) {
+  if (a.conv.enabled) {
+    uint64_t dims[4] = {(uint64_t)a.N, (uint64_t)a.conv.Wo, (uint64_t)a.conv.Ho, (uint64_t)batch_images};
+    uint64_t strides[3] = {(uint64_t)a.ldo * 2, (uint64_t)a.conv.Wo * a.ldo * 2, (uint64_t)a.conv.Ho * a.conv.Wo * a.ldo * 2};
+    uint32_t box[4] = {64, (uint32_t)kConvTileW, (uint32_t)kConvTileH, 1};
+    return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  uint64_t dims[3] = {(uint64_t)a.N, (uint64_t)a.M, 1};
+  uint64_t strides[2] = {(uint64_t)a.ldo * 2, (uint64_t)a.M * a.ldo * 2};
+  uint32_t box[3] = {64, (uint32_t)BM, 1};
+  return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int gemm_finalize(GemmLaunch* L) {
+  GemmArgs& a = L->args;
+  a.st_out = a.st_out2 = a.ld_op = 0;
+  if (L->epi == EPI_WGRAD) return ACEZ_OK;
+  ACEZ_REQUIRE(a.N % 64 == 0 && a.ldo % 8 == 0, "gemm: fp16 epilogue needs N %% 64 == 0 and ldo %% 8 == 0 (N=%d ldo=%d)", a.N, a.ldo);
+  const int imgs = a.conv.enabled ? L->batch : 1;
+  int rc;
+  const __half* op = (L->epi == EPI_FWD) ? a.resid : a.mask;
+  if (a.out != nullptr) {
+    if ((rc = encode_tile_map(&L->tmOut, a.out, a, imgs))) return rc;
+    a.st_out = 1;
+  }
+  const bool want2 = a.out2 != nullptr && (L->epi == EPI_DGRAD || a.resid != nullptr);
+  if (want2) {
+    if ((rc = encode_tile_map(&L->tmOut2, a.out2, a, imgs))) return rc;
+    a.st_out2 = 1;
+  }
+  if (op != nullptr) {
+    if ((rc = encode_tile_map(&L->tmOp, op, a, imgs))) return rc;
+    a.ld_op = 1;
+  }
+  ACEZ_REQUIRE(L->epi != EPI_DGRAD || a.ld_op, "gemm: dgrad epilogue needs a mask");
+  // unused maps must still be valid kernel parameters
+  if (!a.st_out) L->tmOut = a.st_out2 ? L->tmOut2 : L->tmA;
+  if (!a.st_out2) L->tmOut2 = L->tmOut;
+  if (!a.ld_op) L->tmOp = L->tmOut;
+  return ACEZ_OK;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
-    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmem));
+    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, EPI>::kSmem));
     configured = true;
   }
   dim3 grid((L.args.N + BN - 1) / BN, (L.args.M + BM - 1) / BM, L.batch);
@@ -341,14 +437,14 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = GemmCfg<BN>::kSmem;
+  cfg.dynamicSmemBytes = GemmCfg<BN, EPI>::kSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.args));
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmOut, L.tmOut2, L.tmOp, L.args));
   return ACEZ_OK;
 }
 
@@ -423,5 +519,7 @@ extern "C" int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream) {
     ACEZ_REQUIRE((d->out != nullptr || d->out2 != nullptr) && d->ldo % 8 == 0, "gemm: fp16 epilogue needs out with ldo %% 8 == 0");
     ACEZ_REQUIRE(d->epilogue != ACEZ_EPI_DGRAD || d->mask != nullptr, "gemm: dgrad epilogue needs a mask");
   }
+  rc = gemm_finalize(&L);
+  if (rc) return rc;
   return gemm_launch(L, reinterpret_cast<cudaStream_t>(stream));
 }

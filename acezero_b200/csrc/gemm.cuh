@@ -57,10 +57,12 @@ struct GemmArgs {
   float* bias_grad;      // [z][M] nullable: column sum over the contraction dimension of A (dZ^T 1)
   long long bias_grad_zstride;
   long long* dbg_clock;  // nullable: 8 clock64 stamps per CTA (profiling probe)
+  int st_out, st_out2, ld_op;  // set by gemm_finalize: which of tmOut / tmOut2 / tmOp are live
 };
 
 struct GemmLaunch {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmOut, tmOut2, tmOp;  // fp16 epilogues: staged TMA stores / prefetched operand tile (gemm_finalize)
   GemmArgs args;
   int bn;        // 64, 128 or 256
   int a_mn, b_mn;
@@ -82,6 +84,8 @@ struct GemmProblem {
 
 // Fills L->tmA/tmB and the descriptor constants; the caller then fills the epilogue pointers in L->args.
 int gemm_prepare(GemmLaunch* L, const GemmProblem& p);
+// After the epilogue pointers are set: encode the output / operand tensor maps (fp16 epilogues).
+int gemm_finalize(GemmLaunch* L);
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream);
 
 }  // namespace acez

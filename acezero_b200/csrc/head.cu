@@ -441,6 +441,8 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     } else {
       a.out = h->ACT + (size_t)(l + 1) * h->act_stride;
     }
+    rc = gemm_finalize(&h->fwd[l]);
+    if (rc) return rc;
   }
   if (training) {
     h->dgrad.assign(L, GemmLaunch{});
@@ -469,6 +471,8 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       } else {
         a.mask = h->ACT + (size_t)l * h->act_stride;
       }
+      rc = gemm_finalize(&h->dgrad[l]);
+      if (rc) return rc;
     }
     // all weight gradients in one launch: grid.z = layer, no split-K, plain fp32 stores
     GemmProblem p{};
@@ -499,6 +503,8 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     a.ldo32 = kC;
     a.bias_grad = h->grads + (size_t)kC * kC;
     a.bias_grad_zstride = (long long)kLayerStride;
+    rc = gemm_finalize(&h->wgrad);
+    if (rc) return rc;
   }
   h->prepared_rows = rows;
   h->prepared_training = training;
