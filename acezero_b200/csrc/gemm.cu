@@ -224,6 +224,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int j = 0; j < 8; ++j)
           dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if (args.nonfinite != nullptr) {
+          // GradScaler check folded in: autocast materialises weight gradients in fp16, so |g| > 65504 is an overflow
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float g = __uint_as_float(v[j]);
+            bad |= !isfinite(g) || fabsf(g) > 65504.f;
+          }
+        }
       } else {
         // shared-memory position of this thread's 32 columns: 64-column box, 128-byte rows, SWIZZLE_128B chunks
         const int box = c >> 1, jbase = (c & 1) * 4;
@@ -310,9 +318,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t v[32];
       tmem_ld_32x32(t_row + BN, v);
       tmem_ld_wait();
-      if (row_ok) args.bias_grad[(long long)z * args.bias_grad_zstride + row] = __uint_as_float(v[0]);
+      if (row_ok) {
+        const float g = __uint_as_float(v[0]);
+        args.bias_grad[(long long)z * args.bias_grad_zstride + row] = g;
+        bad |= !isfinite(g) || fabsf(g) > 65504.f;
+      }
     }
-    if (EPI == EPI_DGRAD && args.nonfinite != nullptr) {
+    if (EPI != EPI_FWD && args.nonfinite != nullptr) {
       if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
@@ -425,7 +437,7 @@ int gemm_finalize(GemmLaunch* L) {
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
+static int launch_variant(const GemmLaunch& L, cudaStream_t stream, bool pdl) {
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -443,14 +455,14 @@ static int launch_variant(const GemmLaunch& L, cudaStream_t stream) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmOut, L.tmOut2, L.tmOp, L.args));
   return ACEZ_OK;
 }
 
-int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+int gemm_launch(const GemmLaunch& L, cudaStream_t stream, bool pdl) {
 #define ACEZ_GEMM_CASE(BN_, AMN_, BMN_, EPI_) \
-  if (L.bn == BN_ && L.a_mn == AMN_ && L.b_mn == BMN_ && L.epi == EPI_) return launch_variant<BN_, AMN_, BMN_, EPI_>(L, stream);
+  if (L.bn == BN_ && L.a_mn == AMN_ && L.b_mn == BMN_ && L.epi == EPI_) return launch_variant<BN_, AMN_, BMN_, EPI_>(L, stream, pdl);
   ACEZ_GEMM_CASE(256, false, false, EPI_FWD)
   ACEZ_GEMM_CASE(128, false, false, EPI_FWD)
   ACEZ_GEMM_CASE(64, false, false, EPI_FWD)
@@ -521,5 +533,5 @@ extern "C" int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream) {
   }
   rc = gemm_finalize(&L);
   if (rc) return rc;
-  return gemm_launch(L, reinterpret_cast<cudaStream_t>(stream));
+  return gemm_launch(L, reinterpret_cast<cudaStream_t>(stream), /*pdl=*/false);
 }

@@ -86,6 +86,7 @@ struct GemmProblem {
 int gemm_prepare(GemmLaunch* L, const GemmProblem& p);
 // After the epilogue pointers are set: encode the output / operand tensor maps (fp16 epilogues).
 int gemm_finalize(GemmLaunch* L);
-int gemm_launch(const GemmLaunch& L, cudaStream_t stream);
+// pdl: launch with the programmatic-dependent-launch attribute (only valid when the stream predecessor is a kernel)
+int gemm_launch(const GemmLaunch& L, cudaStream_t stream, bool pdl = true);
 
 }  // namespace acez

@@ -37,6 +37,10 @@ struct acez_head_plan {
   __half* DZ;
   __half* GRES;
   float* G3;
+  float* FC3PART;
+  float* BLKPART;
+  unsigned int* BLKCOUNT;
+  bool counters_zeroed;
   size_t act_stride;  // max_rows * 512
   int prepared_rows;
   int prepared_training;
@@ -48,7 +52,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, g3, total;
+  size_t w16, w3h, act, xtra, dz, gres, g3, fc3part, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -65,9 +69,31 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.dz = off; off = align_up(off + (size_t)L * rows * kC * 2, 1024);
     o.gres = off; off = align_up(off + rows * kC * 2, 1024);
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
+    o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
   }
   o.total = off;
   return o;
+}
+
+// Launch with the programmatic-dependent-launch attribute: the kernel may be scheduled while its predecessor in the
+// stream still runs; every kernel launched this way starts with pdl_wait() (griddepcontrol.wait) before it touches
+// global memory and calls pdl_launch_dependents() so that ITS successor can be scheduled early in turn.
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // The attribute is only safe when the stream predecessor is a kernel: griddepcontrol.wait does not order against a
+  // preceding memcpy / memset / cross-stream event, so the FIRST kernel of every C-ABI call is launched plainly.
+  cfg.numAttrs = pdl ? 1 : 0;
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+  return ACEZ_OK;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -114,6 +140,8 @@ struct MultiGather {
   int row_bytes[8];
 };
 __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int a = blockIdx.y;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,15 +179,21 @@ struct TailArgs {
   const float* d_sc_in; // training == 2: gradient w.r.t. the scene coordinates supplied by the caller (autograd)
   __half* dz;           // DZ[L-1] [rows,512]
   float* g3;            // [rows,4] gradient w.r.t. the fc3 outputs (fp16-rounded values)
-  float* stats;         // [4]
-  int* nonfinite;
+  float* stats;         // [4]: written (not accumulated) by the last block to finish
+  int* nonfinite;       // written (not OR-ed) by the last block: later kernels of the iteration OR into it
+  float* blk_part;      // [gridDim.x][8] per-block partial sums
+  unsigned int* blk_count;  // self-resetting completion counter
 };
 
 static constexpr int kTailThreads = 256;
 
 __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
   __shared__ float sRed[3][kTailThreads / 32];
+  __shared__ float sGeo[kTailThreads / 32][48];  // per-warp staging of one row's geometry (one load per lane)
+  __shared__ int sLast;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   // this lane's slice of the fc3 weights: 4 rows x 16 columns, packed fp16
   __half2 w[4][8];
 #pragma unroll
@@ -232,18 +266,40 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
       o.loss = 0.f; o.valid = true; o.inlier = false; o.gK00 = o.gK11 = 0.f;
       o.gc[0] = o.gc[1] = o.gc[2] = 0.f;
     } else {
-    // ---- reprojection loss + backward (all lanes redundantly; inputs are warp-broadcast loads) ----
+    // ---- reprojection loss + backward (all lanes redundantly). The row's geometry (46 + 2 floats from 5 arrays) is
+    // fetched with ONE load per lane, issued before the fc3 dot products above complete, and broadcast through smem.
     float P[12];
-    if (a.Pin != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) P[k] = a.Pin[12 * (size_t)row + k];
-    } else {
-      compose_pose(a.A + 12 * (size_t)row, a.T + 16 * (size_t)row, P);
-    }
     float Kr[9], Ki[9];
+    {
+      float gv = 0.f;
+      if (a.Pin != nullptr) {
+        if (lane < 12) gv = a.Pin[12 * (size_t)row + lane];
+      } else if (lane < 12) gv = a.A[12 * (size_t)row + lane];
+      else if (lane < 28) gv = a.T[16 * (size_t)row + (lane - 12)];
+      float gv2 = 0.f;  // second wave: K (9), Kinv (9), target px (2) -> 20 values on lanes 0..19
+      if (lane < 9) gv2 = a.K[9 * (size_t)row + lane];
+      else if (lane < 18) gv2 = a.Kinv[9 * (size_t)row + (lane - 9)];
+      else if (lane < 20) gv2 = a.tpx[2 * (size_t)row + (lane - 18)];
+      __syncwarp();
+      if (lane < 28) sGeo[warp][lane] = gv;
+      if (lane < 20) sGeo[warp][28 + lane] = gv2;
+      __syncwarp();
+      if (a.Pin != nullptr) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { Kr[k] = a.K[9 * (size_t)row + k]; Ki[k] = a.Kinv[9 * (size_t)row + k]; }
-    repro_row(lp, X, P, Kr, Ki, a.tpx[2 * (size_t)row], a.tpx[2 * (size_t)row + 1],
+        for (int k = 0; k < 12; ++k) P[k] = sGeo[warp][k];
+      } else {
+        float A[12], T[16];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] = sGeo[warp][k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) T[k] = sGeo[warp][12 + k];
+        compose_pose(A, T, P);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { Kr[k] = sGeo[warp][28 + k]; Ki[k] = sGeo[warp][37 + k]; }
+    }
+    const float tpx0 = sGeo[warp][46], tpx1 = sGeo[warp][47];
+    repro_row(lp, X, P, Kr, Ki, tpx0, tpx1,
               (lp.use_depth && a.G) ? a.G + 3 * (size_t)row : nullptr, o);
     }
     if (lane == 0 && a.training == 1) {
@@ -303,46 +359,118 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
   if (lane == 0) { sRed[0][warp] = loss_sum; sRed[1][warp] = inl_sum; sRed[2][warp] = valid_sum; }
   const int any_bad = __syncthreads_or(bad ? 1 : 0);
   const int any_bad_g = __syncthreads_or(bad_g ? 1 : 0);
+  // per-block partials, then the last block to finish writes the totals (no pre-zeroing, deterministic order)
   if (tid == 0) {
     float l = 0.f, n = 0.f, v = 0.f;
     for (int k = 0; k < kTailThreads / 32; ++k) { l += sRed[0][k]; n += sRed[1][k]; v += sRed[2][k]; }
-    if (a.stats != nullptr) {
-      atomicAdd(&a.stats[0], l);
-      atomicAdd(&a.stats[1], n);
-      atomicAdd(&a.stats[2], v);
-      if (any_bad) a.stats[3] = 1.f;
+    float* p = a.blk_part + 8 * (size_t)blockIdx.x;
+    p[0] = l; p[1] = n; p[2] = v; p[3] = any_bad ? 1.f : 0.f; p[4] = any_bad_g ? 1.f : 0.f;
+    __threadfence();
+    const unsigned int done = atomicAdd(a.blk_count, 1u);
+    sLast = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sLast) {
+    __threadfence();
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = tid; b < (int)gridDim.x; b += kTailThreads) {
+      const volatile float* p = a.blk_part + 8 * (size_t)b;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] += p[k];
     }
-    if (any_bad_g && a.nonfinite != nullptr) atomicOr(a.nonfinite, 1);
+    __shared__ float sTot[5][kTailThreads / 32];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float w = warp_sum(acc[k]);
+      if (lane == 0) sTot[k][warp] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 5; ++k)
+        for (int w = 0; w < kTailThreads / 32; ++w) t[k] += sTot[k][w];
+      if (a.stats != nullptr) { a.stats[0] = t[0]; a.stats[1] = t[1]; a.stats[2] = t[2]; a.stats[3] = t[3] > 0.f ? 1.f : 0.f; }
+      if (a.nonfinite != nullptr) *a.nonfinite = t[4] > 0.f ? 1 : 0;
+      *a.blk_count = 0u;  // ready for the next launch
+    }
   }
 }
 
-// dW3[j][c] = sum_rows G3[row][j] * x8[row][c], db3[j] = sum_rows G3[row][j]. Thread t owns columns 2t, 2t+1; a
-// block walks a contiguous slab of rows (coalesced 1 KB row reads), then adds its partial sums to the gradient.
+// dW3[j][c] = sum_rows G3[row][j] * x8[row][c], db3[j] = sum_rows G3[row][j].
+// Stage 1: one block per 32-row slab; thread (cg, rs) owns 8 columns (one 16-byte load per row) of every 4th row, all
+// loads of a thread are independent; slab partials go to global. Stage 2: sum the slab partials (coalesced), write the
+// gradient, and fold the GradScaler overflow check for these values into the same pass.
 static constexpr int kFc3Threads = 256;
-__global__ void __launch_bounds__(kFc3Threads) fc3_wgrad_kernel(const __half* __restrict__ x, const float* __restrict__ g3,
-                                                               int rows, int C3, float* __restrict__ gW3,
-                                                               float* __restrict__ gb3) {
-  const int t = threadIdx.x;
-  const int per = (rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-  float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-  float accb = 0.f;
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    const float2 xv = __half22float2(*reinterpret_cast<const __half2*>(x + (size_t)r * kC + 2 * t));
-    const float4 g = *reinterpret_cast<const float4*>(g3 + 4 * (size_t)r);
-    acc[0][0] = fmaf(g.x, xv.x, acc[0][0]); acc[0][1] = fmaf(g.x, xv.y, acc[0][1]);
-    acc[1][0] = fmaf(g.y, xv.x, acc[1][0]); acc[1][1] = fmaf(g.y, xv.y, acc[1][1]);
-    acc[2][0] = fmaf(g.z, xv.x, acc[2][0]); acc[2][1] = fmaf(g.z, xv.y, acc[2][1]);
-    acc[3][0] = fmaf(g.w, xv.x, acc[3][0]); acc[3][1] = fmaf(g.w, xv.y, acc[3][1]);
-    if (t < 4) accb += (t == 0) ? g.x : (t == 1) ? g.y : (t == 2) ? g.z : g.w;
+static constexpr int kFc3Rows = 32;
+__global__ void __launch_bounds__(kFc3Threads) fc3_wgrad_partial_kernel(const __half* __restrict__ x,
+                                                                       const float* __restrict__ g3, int rows,
+                                                                       float* __restrict__ part /*[nblk][2052]*/) {
+  __shared__ float sAcc[4][64][33];
+  __shared__ float sB[4][4];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int t = threadIdx.x, cg = t & 63, rs = t >> 6;
+  const int r0 = blockIdx.x * kFc3Rows, r1 = min(rows, r0 + kFc3Rows);
+  float acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < kFc3Rows / 4; ++i) {
+    const int r = r0 + rs + 4 * i;
+    if (r < r1) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)r * kC + 8 * cg);
+      const float4 g = *reinterpret_cast<const float4*>(g3 + 4 * (size_t)r);
+      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
+      const float gj[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 f = __half22float2(xh[c]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][2 * c] = fmaf(gj[j], f.x, acc[j][2 * c]);
+          acc[j][2 * c + 1] = fmaf(gj[j], f.y, acc[j][2 * c + 1]);
+        }
+      }
+      if (cg == 0) { accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w; }
+    }
   }
-  if (r1 <= r0) return;
-  for (int j = 0; j < C3; ++j) {
-    atomicAdd(&gW3[j * kC + 2 * t], acc[j][0]);
-    atomicAdd(&gW3[j * kC + 2 * t + 1], acc[j][1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sAcc[rs][cg][j * 8 + c] = acc[j][c];
+  if (cg == 0)
+    for (int j = 0; j < 4; ++j) sB[rs][j] = accb[j];
+  __syncthreads();
+  float* out = part + (size_t)blockIdx.x * (4 * kC + 4);
+  for (int idx = t; idx < 4 * kC; idx += kFc3Threads) {
+    const int j = idx / kC, col = idx % kC;
+    const int g = col >> 3, c = col & 7;
+    out[idx] = sAcc[0][g][j * 8 + c] + sAcc[1][g][j * 8 + c] + sAcc[2][g][j * 8 + c] + sAcc[3][g][j * 8 + c];
   }
-  if (t < C3) atomicAdd(&gb3[t], accb);
+  if (t < 4) out[4 * kC + t] = sB[0][t] + sB[1][t] + sB[2][t] + sB[3][t];
+}
+
+__global__ void fc3_reduce_kernel(const float* __restrict__ part, int nblk, int C3, float* __restrict__ gW3,
+                                  float* __restrict__ gb3, int* __restrict__ nonfinite) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 4 * kC + 4;
+  bool bad = false;
+  if (idx < total) {
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * total + idx];
+    if (idx < 4 * kC) {
+      if (idx < C3 * kC) { gW3[idx] = s; bad = !isfinite(s) || fabsf(s) > 65504.f; }
+    } else if (idx - 4 * kC < C3) {
+      gb3[idx - 4 * kC] = s;
+      bad = !isfinite(s) || fabsf(s) > 65504.f;
+    }
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0 && nonfinite != nullptr) atomicOr(nonfinite, 1);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -350,6 +478,8 @@ __global__ void __launch_bounds__(kFc3Threads) fc3_wgrad_kernel(const __half* __
 //   scaler_state: [0] scale S, [1] growth tracker, [2] optimizer step count t
 // ----------------------------------------------------------------------------------------------
 __global__ void grad_check_kernel(const float* __restrict__ g, size_t n, int* __restrict__ found_inf) {
+  pdl_wait();
+  pdl_launch_dependents();
   bool bad = false;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = g[i];
@@ -359,45 +489,9 @@ __global__ void grad_check_kernel(const float* __restrict__ g, size_t n, int* __
   if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(found_inf, 1);
 }
 
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, size_t n, const float* __restrict__ hyper,
-                             const float* __restrict__ scaler_state, const int* __restrict__ found_inf,
-                             int use_scaler, __half* __restrict__ W16, __half* __restrict__ W3h, int L, int C3) {
-  if (use_scaler && *found_inf != 0) return;  // GradScaler.step skips optimizer.step() on inf/nan
-  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
-  const float inv_scale = use_scaler ? 1.f / scaler_state[0] : 1.f;
-  const float t = scaler_state[2] + 1.f;  // this step's index (torch: state['step'] += 1 before use)
-  const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
-  const float step_size = lr / bc1;
-  const float bc2_sqrt = sqrtf(bc2);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float gi = g[i];
-    if (use_scaler) gi = __half2float(__float2half_rn(gi));  // fp16 weight gradient of the autocast conv
-    gi *= inv_scale;                                          // GradScaler.unscale_
-    float pi = p[i];
-    pi *= (1.f - lr * wd);                             // decoupled weight decay (torch adamw)
-    const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= step_size * (mi / denom);
-    p[i] = pi;
-    m[i] = mi;
-    v[i] = vi;
-    if (W16 != nullptr) {  // refresh the fp16 shadow the next forward reads
-      const size_t l = i / kLayerStride, r = i % kLayerStride;
-      if (l < (size_t)L) {
-        if (r < (size_t)kC * kC) W16[l * (size_t)kC * kC + r] = __float2half_rn(pi);
-      } else if (r < (size_t)C3 * kC) {
-        W3h[r] = __float2half_rn(pi);
-      }
-    }
-  }
-}
-
-// torch.cuda.amp.GradScaler.update(): backoff 0.5 on inf, growth x2 every 2000 clean steps
-__global__ void scaler_update_kernel(float* __restrict__ st, const int* __restrict__ found_inf, int use_scaler) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (use_scaler && *found_inf != 0) {
+__device__ __forceinline__ void scaler_update(float* st, int found, int use_scaler) {
+  // torch.cuda.amp.GradScaler.update(): backoff 0.5 on inf, growth x2 every 2000 clean steps
+  if (use_scaler && found) {
     st[0] *= 0.5f;
     st[1] = 0.f;
   } else {
@@ -405,6 +499,56 @@ __global__ void scaler_update_kernel(float* __restrict__ st, const int* __restri
     if (use_scaler) {
       st[1] += 1.f;
       if (st[1] >= 2000.f) { st[0] *= 2.f; st[1] = 0.f; }
+    }
+  }
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, size_t n, const float* __restrict__ hyper,
+                             float* __restrict__ scaler_state, const int* __restrict__ found_inf,
+                             int use_scaler, __half* __restrict__ W16, __half* __restrict__ W3h, int L, int C3) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int found = use_scaler ? *found_inf : 0;
+  if (!found) {  // GradScaler.step skips optimizer.step() on inf/nan
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+    const float inv_scale = use_scaler ? 1.f / scaler_state[0] : 1.f;
+    const float t = scaler_state[2] + 1.f;  // this step's index (torch: state['step'] += 1 before use)
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1;
+    const float bc2_sqrt = sqrtf(bc2);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      float gi = g[i];
+      if (use_scaler) gi = __half2float(__float2half_rn(gi));  // fp16 weight gradient of the autocast conv
+      gi *= inv_scale;                                          // GradScaler.unscale_
+      float pi = p[i];
+      pi *= (1.f - lr * wd);                             // decoupled weight decay (torch adamw)
+      const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      pi -= step_size * (mi / denom);
+      p[i] = pi;
+      m[i] = mi;
+      v[i] = vi;
+      if (W16 != nullptr) {  // refresh the fp16 shadow the next forward reads
+        const size_t l = i / kLayerStride, r = i % kLayerStride;
+        if (l < (size_t)L) {
+          if (r < (size_t)kC * kC) W16[l * (size_t)kC * kC + r] = __float2half_rn(pi);
+        } else if (r < (size_t)C3 * kC) {
+          W3h[r] = __float2half_rn(pi);
+        }
+      }
+    }
+  }
+  // the last block to finish applies GradScaler.update() (scale / growth tracker / step count); the completion
+  // counter lives in scaler_state[3] (bit pattern, starts at 0) and resets itself
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(scaler_state + 3);
+    if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+      scaler_update(scaler_state, found, use_scaler);
+      *cnt = 0u;
     }
   }
 }
@@ -527,8 +671,33 @@ static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
 static int tail_grid(int rows) {
   const int per_block = kTailThreads / 32;
   int g = (rows + per_block - 1) / per_block;
-  const int cap = 4 * sm_count();  // ~100 registers/thread: two 256-thread CTAs per SM, a few rows per warp
+  const int cap = 4 * sm_count() < 4096 ? 4 * sm_count() : 4096;  // per-block partial slots: 4096
   return g < cap ? (g < 1 ? 1 : g) : cap;
+}
+
+// tail (+ fc3 gradient) launch sequence shared by the training entries
+static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s, int* nonfinite, bool with_fc3_grad,
+                       bool pdl) {
+  if (!h->counters_zeroed) {  // once per plan: the completion counter is self-resetting afterwards
+    ACEZ_CUDA(cudaMemsetAsync(h->BLKCOUNT, 0, 256, s));
+    h->counters_zeroed = true;
+    pdl = false;  // predecessor is a memset
+  }
+  t.blk_part = h->BLKPART;
+  t.blk_count = h->BLKCOUNT;
+  int rc = launch_pdl(head_tail_kernel, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t);
+  if (rc) return rc;
+  if (with_fc3_grad) {
+    const int nblk = (rows + kFc3Rows - 1) / kFc3Rows;
+    float* gW3 = h->grads + (size_t)h->L * kLayerStride;
+    rc = launch_pdl(fc3_wgrad_partial_kernel, dim3(nblk), dim3(kFc3Threads), 0, s, true, t.x, (const float*)h->G3, rows, h->FC3PART);
+    if (rc) return rc;
+    const int total = 4 * kC + 4;
+    rc = launch_pdl(fc3_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
+                    gW3 + (size_t)h->C3 * kC, nonfinite);
+    if (rc) return rc;
+  }
+  return ACEZ_OK;
 }
 
 }  // namespace acez
@@ -575,6 +744,10 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->DZ = cfg->training ? reinterpret_cast<__half*>(base + lo.dz) : nullptr;
   h->GRES = cfg->training ? reinterpret_cast<__half*>(base + lo.gres) : nullptr;
   h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
+  h->FC3PART = cfg->training ? reinterpret_cast<float*>(base + lo.fc3part) : nullptr;
+  h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);
+  h->BLKCOUNT = reinterpret_cast<unsigned int*>(base + lo.blkpart + 4096 * 8 * sizeof(float));
+  h->counters_zeroed = false;
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;
   h->prepared_training = 0;
@@ -603,7 +776,7 @@ static int head_run_forward(acez_head_plan* h, const void* features, int rows, i
   if (features != nullptr && features != h->ACT)
     ACEZ_CUDA(cudaMemcpyAsync(h->ACT, features, (size_t)rows * kC * 2, cudaMemcpyDeviceToDevice, s));
   for (int l = 0; l < h->L; ++l) {
-    rc = gemm_launch(h->fwd[l], s);
+    rc = gemm_launch(h->fwd[l], s, /*pdl=*/l > 0);  // the first kernel of the call follows a copy / foreign work
     if (rc) return rc;
   }
   return ACEZ_OK;
@@ -622,9 +795,7 @@ extern "C" int acez_head_forward(acez_head_plan* h, const void* features, int ro
   fill_tail_common(h, rows, t);
   t.training = 0;
   t.sc_out = sc_out;
-  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
-  ACEZ_CUDA(cudaGetLastError());
-  return ACEZ_OK;
+  return launch_tail(h, t, rows, s, nullptr, false, true);
 }
 
 extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_loss_params* lp,
@@ -642,10 +813,6 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   rc = head_run_forward(h, b->features, rows, 1, s);
   if (rc) return rc;
   const int L = h->L;
-  float* gW3 = h->grads + (size_t)L * kLayerStride;
-  ACEZ_CUDA(cudaMemsetAsync(gW3, 0, ((size_t)h->C3 * kC + h->C3) * sizeof(float), s));
-  ACEZ_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), s));
-  ACEZ_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), s));
   TailArgs t{};
   fill_tail_common(h, rows, t);
   t.training = 1;
@@ -660,19 +827,14 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   t.g3 = h->G3;
   t.stats = stats;
   t.nonfinite = nonfinite;
-  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
-  ACEZ_CUDA(cudaGetLastError());
-  {
-    int g = (rows + 31) / 32;
-    if (g > sm_count()) g = sm_count();
-    fc3_wgrad_kernel<<<g, kFc3Threads, 0, s>>>(t.x, h->G3, rows, h->C3, gW3, gW3 + (size_t)h->C3 * kC);
-    ACEZ_CUDA(cudaGetLastError());
-  }
+  rc = launch_tail(h, t, rows, s, nonfinite, true, true);
+  if (rc) return rc;
   for (int l = L - 1; l >= 1; --l) {
     h->dgrad[l].args.nonfinite = nonfinite;
     rc = gemm_launch(h->dgrad[l], s);
     if (rc) return rc;
   }
+  h->wgrad.args.nonfinite = nonfinite;  // fp16-overflow / inf check of the weight gradients in the epilogue
   return gemm_launch(h->wgrad, s);
 }
 
@@ -686,9 +848,6 @@ extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int L = h->L;
-  float* gW3 = h->grads + (size_t)L * kLayerStride;
-  ACEZ_CUDA(cudaMemsetAsync(gW3, 0, ((size_t)h->C3 * kC + h->C3) * sizeof(float), s));
-  ACEZ_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), s));
   TailArgs t{};
   fill_tail_common(h, rows, t);
   t.training = 2;
@@ -698,19 +857,14 @@ extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc
   t.g3 = h->G3;
   t.stats = nullptr;
   t.nonfinite = nonfinite;
-  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
-  ACEZ_CUDA(cudaGetLastError());
-  {
-    int g = (rows + 31) / 32;
-    if (g > sm_count()) g = sm_count();
-    fc3_wgrad_kernel<<<g, kFc3Threads, 0, s>>>(t.x, h->G3, rows, h->C3, gW3, gW3 + (size_t)h->C3 * kC);
-    ACEZ_CUDA(cudaGetLastError());
-  }
+  rc = launch_tail(h, t, rows, s, nonfinite, true, false);  // first kernel of this call
+  if (rc) return rc;
   for (int l = L - 1; l >= 1; --l) {
     h->dgrad[l].args.nonfinite = nonfinite;
     rc = gemm_launch(h->dgrad[l], s);
     if (rc) return rc;
   }
+  h->wgrad.args.nonfinite = nonfinite;
   return gemm_launch(h->wgrad, s);
 }
 
@@ -727,9 +881,7 @@ extern "C" int acez_head_forward_train(acez_head_plan* h, const void* features, 
   fill_tail_common(h, rows, t);
   t.training = 0;
   t.sc_out = sc_out;
-  head_tail_kernel<<<tail_grid(rows), kTailThreads, 0, s>>>(t);
-  ACEZ_CUDA(cudaGetLastError());
-  return ACEZ_OK;
+  return launch_tail(h, t, rows, s, nullptr, false, true);
 }
 
 extern "C" int acez_gather_rows(const void* src, const int64_t* idx, int rows, int row_bytes, void* dst,
@@ -762,9 +914,7 @@ extern "C" int acez_gather_rows_multi(const void* const* srcs, void* const* dsts
   if (rows == 0) return ACEZ_OK;
   const int threads = 256;
   dim3 grid((rows * 32 + threads - 1) / threads, n_arrays);
-  gather_rows_multi_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, idx, rows);
-  ACEZ_CUDA(cudaGetLastError());
-  return ACEZ_OK;
+  return launch_pdl(gather_rows_multi_kernel, grid, dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), false, g, idx, rows);
 }
 
 extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
@@ -778,15 +928,13 @@ extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = 8 * sm_count();
-  if (use_scaler) {
-    grad_check_kernel<<<grid, 256, 0, s>>>(grads, n, found_inf_dev);
-    ACEZ_CUDA(cudaGetLastError());
+  if (use_scaler == 1) {  // 2 = the caller's flag already covers every gradient (acez_head_train_fwd_bwd does)
+    rc = launch_pdl(grad_check_kernel, dim3(grid), dim3(256), 0, s, false, grads, n, found_inf_dev);
+    if (rc) return rc;
   }
-  adamw_kernel<<<grid, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, hyper_dev, scaler_state_dev, found_inf_dev,
-                                    use_scaler, plan ? plan->W16 : nullptr, plan ? plan->W3h : nullptr,
-                                    plan ? plan->L : 0, plan ? plan->C3 : 0);
-  ACEZ_CUDA(cudaGetLastError());
-  scaler_update_kernel<<<1, 32, 0, s>>>(scaler_state_dev, found_inf_dev, use_scaler);
-  ACEZ_CUDA(cudaGetLastError());
+  rc = launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, use_scaler == 1, params, grads, exp_avg, exp_avg_sq, n, hyper_dev,
+                  scaler_state_dev, (const int*)found_inf_dev, use_scaler ? 1 : 0, plan ? plan->W16 : (__half*)nullptr,
+                  plan ? plan->W3h : (__half*)nullptr, plan ? plan->L : 0, plan ? plan->C3 : 0);
+  if (rc) return rc;
   return ACEZ_OK;
 }

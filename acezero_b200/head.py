@@ -198,9 +198,11 @@ class HeadEngine:
             h[5] = loss_weight
         self.hyper.copy_(h, non_blocking=True)
 
-    def adamw_step(self, use_scaler=True, stream=None):
+    def adamw_step(self, use_scaler=True, flag_complete=True, stream=None):
+        """flag_complete: found_inf already covers all gradients (true after train_fwd_bwd)."""
         rc = self.lib.acez_adamw_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg),
                                       _lib.ptr(self.exp_avg_sq), self.n_params, _lib.ptr(self.hyper),
-                                      _lib.ptr(self.scaler_state), _lib.ptr(self.found_inf), int(use_scaler), self.plan,
+                                      _lib.ptr(self.scaler_state), _lib.ptr(self.found_inf),
+                                      (2 if flag_complete else 1) if use_scaler else 0, self.plan,
                                       _lib.stream_ptr(stream))
         _lib.check(rc, "acez_adamw_step")

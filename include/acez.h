@@ -179,8 +179,9 @@ typedef struct acez_train_batch {
 } acez_train_batch;
 
 /* One head forward + reprojection loss + full backward into `grads` (overwritten, scaled by grad_scale).
- * stats: [4] floats as in acez_repro_loss_fwd_bwd, zeroed by the call. nonfinite (int, device) is zeroed and set
- * to 1 if any activation gradient overflowed fp16. Replaces ace_trainer.py:516-627. */
+ * stats: [4] floats as in acez_repro_loss_fwd_bwd, overwritten by the call. nonfinite (int, device) is overwritten: 1 if
+ * any activation gradient or (fp16-rounded) weight gradient is inf/nan — the complete GradScaler found_inf of this
+ * backward pass. Replaces ace_trainer.py:516-627. */
 int acez_head_train_fwd_bwd(acez_head_plan* plan, int rows, const acez_loss_params* lp, const acez_train_batch* batch,
                             float* stats, int* nonfinite, acez_stream_t stream);
 
@@ -210,7 +211,10 @@ int acez_buffer_fill(const void* feat_rows, const int64_t* sample_idx, int n_sam
  *   scaler_state_dev float[4]: [0] scale S, [1] growth tracker, [2] optimizer step count t (bias correction), [3] -
  *   found_inf_dev    int: OR-ed with the grads' non-finite / fp16-overflow check; must already hold the activation-
  *                    gradient overflow flag of acez_head_train_fwd_bwd (same pointer). Not cleared by this call.
- *   use_scaler       0: plain AdamW (use_half False): no check, no unscale, no skip
+ *   use_scaler       0: plain AdamW (use_half False): no check, no unscale, no skip; 1: check grads here;
+ *                    2: found_inf_dev is already complete (acez_head_train_fwd_bwd folds the check of every gradient
+ *                    into the kernels that produce it), no extra pass over the gradients
+ *   scaler_state_dev[3] is a completion counter used by the kernel (keep it 0).
  * Also refreshes the head's fp16 weight shadow when `plan` is non-null.
  * ---------------------------------------------------------------------------------------------------------- */
 int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
