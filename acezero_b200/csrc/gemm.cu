@@ -196,7 +196,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int i = threadIdx.x - 64; i < BN; i += 128) {
         const int n = n0 + i;
         // autocast casts the fp32 bias to fp16 before the conv adds it
-        sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(args.bias[n])) : 0.f;
+        sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(__ldcg(args.bias + n))) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     }
@@ -263,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (row_ok && ncol < args.N) {
               const uint4* ap = reinterpret_cast<const uint4*>(args.addend + (long long)row * args.ldo + ncol);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) ad[j] = ap[j];
+              for (int j = 0; j < 4; ++j) ad[j] = __ldcg(ap + j);  // L2 load: the kernel may have been launched early (PDL)
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) ad[j] = make_uint4(0, 0, 0, 0);

@@ -71,6 +71,7 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
     o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
   }
+  o.blkpart = off; off = align_up(off + 4096 * 8 * sizeof(float) + 256, 1024);  // tail per-block partials + counter
   o.total = off;
   return o;
 }
@@ -932,7 +933,7 @@ extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg
     rc = launch_pdl(grad_check_kernel, dim3(grid), dim3(256), 0, s, false, grads, n, found_inf_dev);
     if (rc) return rc;
   }
-  rc = launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, use_scaler == 1, params, grads, exp_avg, exp_avg_sq, n, hyper_dev,
+  rc = launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, false, params, grads, exp_avg, exp_avg_sq, n, hyper_dev,
                   scaler_state_dev, (const int*)found_inf_dev, use_scaler ? 1 : 0, plan ? plan->W16 : (__half*)nullptr,
                   plan ? plan->W3h : (__half*)nullptr, plan ? plan->L : 0, plan ? plan->C3 : 0);
   if (rc) return rc;
