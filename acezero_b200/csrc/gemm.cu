@@ -1,7 +1,8 @@
 // tcgen05 + TMA GEMM for sm_100a. See gemm.cuh for the operand conventions.
 //
 // One CTA computes one 128 x BN output tile: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread UMMA
-// issuer, warps 2..5 = epilogue (TMEM -> registers -> global). A ring of kStages shared-memory stages is handed
+// issuer, warps 2..9 = epilogue (TMEM -> registers -> swizzled smem -> TMA store; two groups of four warps, one per
+// TMEM lane quarter each, splitting the 64-column boxes). A ring of kStages shared-memory stages is handed
 // between producer and issuer with full/empty mbarriers; tcgen05.commit releases stages and publishes the
 // accumulator to the epilogue warps.
 #include "gemm.cuh"
@@ -10,7 +11,7 @@ namespace acez {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 fp16 = one 128-byte swizzle row
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (2 warps per SMSP)
 static constexpr uint32_t kSw128 = 2;
 
 template <int BN, int EPI>
@@ -21,7 +22,7 @@ struct GemmCfg {
   // fp16 epilogues reserve one 128 x BN operand tile (residual / ReLU mask, prefetched by TMA during the main loop) and
   // reuse the pipeline stages as staging for the TMA stores of up to two output tiles
   static constexpr int kOpBytes = (EPI == EPI_WGRAD) ? 0 : BM * BN * 2;
-  static constexpr int kStages = (EPI == EPI_WGRAD) ? 6 : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
+  static constexpr int kStages = (EPI == EPI_WGRAD) ? (BN >= 256 ? 4 : 6) : ((BN >= 256) ? 3 : (BN >= 128 ? 4 : 6));
   static constexpr int kOnesBytes = 16 * BK * 2;  // 16 x 64 tile of 1.0 for the bias-gradient column
   static constexpr int kSmem =
       kStages * kStage + kOpBytes + kOnesBytes + BN * 4 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
@@ -90,7 +91,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (kBiasCol && warp >= 2) {
     // ones tile: layout irrelevant (all entries equal)
     __half2* o = reinterpret_cast<__half2*>(sOnes);
-    for (int i = threadIdx.x - 64; i < Cfg::kOnesBytes / 4; i += 128) o[i] = __floats2half2_rn(1.f, 1.f);
+    for (int i = threadIdx.x - 64; i < Cfg::kOnesBytes / 4; i += 256) o[i] = __floats2half2_rn(1.f, 1.f);
     fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
   }
   tcgen05_fence_before();
@@ -183,6 +184,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------ epilogue (4 warps <-> 4 TMEM lane quarters) ------------------------------
     const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;     // epilogue group 0 / 1: boxes (chunks) are interleaved between the groups
     const int r = quarter * 32 + lane;  // row inside the tile
     int row = m0 + r;
     bool row_ok = row < args.M;
@@ -193,30 +195,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       row = (c_img * cg.Ho + py) * cg.Wo + px;  // NHWC pixel index
     }
     if (EPI == EPI_FWD) {
-      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      for (int i = threadIdx.x - 64; i < BN; i += 256) {
         const int n = n0 + i;
         // autocast casts the fp32 bias to fp16 before the conv adds it
         sBias[i] = (args.bias != nullptr && n < args.N) ? __half2float(__float2half_rn(__ldcg(args.bias + n))) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      asm volatile("bar.sync 3, 256;" ::: "memory");  // all epilogue warps
     }
     if (EPI != EPI_WGRAD && args.ld_op) mbar_wait(op_bar, 0);
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
+    const bool issuer = (lane == 0) && (quarter == 2 - 2 * grp);  // first warp of the group: warp 2 / warp 6
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     // all pipeline stages are drained by now: their memory stages the output tiles for the TMA stores
     uint8_t* sOut = smem;
     uint8_t* sOut2 = smem + BM * BN * 2;
     const uint32_t swz = (uint32_t)(r & 7);
     bool bad = false;
+    if (EPI == EPI_WGRAD) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + c * 32, v);
-      tmem_ld_wait();
-      const int ncol = n0 + c * 32;
-      if (EPI == EPI_WGRAD) {
+      for (int c = grp; c < BN / 32; c += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int ncol = n0 + c * 32;
         if (!row_ok || ncol >= args.N) continue;
         float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride +
                                                 (long long)row * args.ldo32 + ncol);
@@ -232,89 +235,79 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bad |= !isfinite(g) || fabsf(g) > 65504.f;
           }
         }
-      } else {
-        // shared-memory position of this thread's 32 columns: 64-column box, 128-byte rows, SWIZZLE_128B chunks
-        const int box = c >> 1, jbase = (c & 1) * 4;
+      }
+    } else {
+      uint32_t badbits = 0;
+      const bool has_add = (EPI == EPI_DGRAD) && args.addend != nullptr;
+#pragma unroll 1
+      for (int box = grp; box < BN / 64; box += 2) {
+        // one 64-column box per iteration: a single TMEM load, 8 swizzled 16-byte chunks per tile row
+        uint32_t v[64];
+        tmem_ld_32x64(t_row + box * 64, v);
+        tmem_ld_wait();
         const uint32_t row_off = (uint32_t)box * 16384u + (uint32_t)r * 128u;
-        uint4 opv[4];
-        if (args.ld_op) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            opv[q] = *reinterpret_cast<const uint4*>(sOp + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4));
-        }
-        uint4 o[4], o2[4];
-        __half2* oh = reinterpret_cast<__half2*>(o);
-        __half2* o2h = reinterpret_cast<__half2*>(o2);
-        const __half2* ph = reinterpret_cast<const __half2*>(opv);
-        if (EPI == EPI_FWD) {
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t off = row_off + ((((uint32_t)q) ^ swz) << 4);
+          uint4 opv = make_uint4(0, 0, 0, 0);
+          if (args.ld_op) opv = *reinterpret_cast<const uint4*>(sOp + off);
+          const __half2* ph = reinterpret_cast<const __half2*>(&opv);
+          uint4 o, o2;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+          __half2* o2h = reinterpret_cast<__half2*>(&o2);
+          if (EPI == EPI_FWD) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(v[2 * j]) + sBias[c * 32 + 2 * j];
-            float b = __uint_as_float(v[2 * j + 1]) + sBias[c * 32 + 2 * j + 1];
-            if (args.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            const __half2 h = __floats2half2_rn(a, b);
-            oh[j] = h;
-            if (args.ld_op) o2h[j] = __hadd2(ph[j], h);  // residual sum in fp16, as the reference's `res + x`
-          }
-        } else {  // EPI_DGRAD
-          uint4 ad[4];
-          const bool has_add = args.addend != nullptr;
-          if (has_add) {
-            if (row_ok && ncol < args.N) {
-              const uint4* ap = reinterpret_cast<const uint4*>(args.addend + (long long)row * args.ldo + ncol);
+            for (int j = 0; j < 4; ++j) {
+              const int col = q * 8 + 2 * j;
+              float a = __uint_as_float(v[col]) + sBias[box * 64 + col];
+              float b = __uint_as_float(v[col + 1]) + sBias[box * 64 + col + 1];
+              if (args.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              const __half2 h = __floats2half2_rn(a, b);
+              oh[j] = h;
+              o2h[j] = __hadd2(ph[j], h);  // residual sum in fp16, as the reference's `res + x`
+            }
+          } else {  // EPI_DGRAD
+            uint4 ad = make_uint4(0, 0, 0, 0);
+            if (has_add && row_ok) {  // L2 load: the kernel may have been launched early (PDL)
+              ad = __ldcg(reinterpret_cast<const uint4*>(args.addend + (long long)row * args.ldo + n0 + box * 64 + q * 8));
+            }
+            const __half2* ah = reinterpret_cast<const __half2*>(&ad);
+            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) ad[j] = __ldcg(ap + j);  // L2 load: the kernel may have been launched early (PDL)
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) ad[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) {
+              const int col = q * 8 + 2 * j;
+              // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+              __half2 h = __floats2half2_rn(__uint_as_float(v[col]), __uint_as_float(v[col + 1]));
+              if (has_add) h = __hadd2(h, ah[j]);
+              o2h[j] = h;
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+              badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+              ob[j] = hb & __hgt2_mask(ph[j], zero2);                       // ReLU mask from the saved activation
             }
           }
-          const __half2* ah = reinterpret_cast<const __half2*>(ad);
-          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
-            __half2 h = __floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-            if (has_add) h = __hadd2(h, ah[j]);
-            o2h[j] = h;
-            const float2 hf = __half22float2(h);
-            bad |= !(isfinite(hf.x) && isfinite(hf.y));
-            const float2 mf = __half22float2(ph[j]);  // ReLU mask source (prefetched tile)
-            __half2 m = h;
-            if (!(mf.x > 0.f)) m.x = __float2half_rn(0.f);
-            if (!(mf.y > 0.f)) m.y = __float2half_rn(0.f);
-            oh[j] = m;
+          if (args.st_out) *reinterpret_cast<uint4*>(sOut + off) = o;
+          if (args.st_out2) *reinterpret_cast<uint4*>(sOut2 + off) = o2;
+        }
+        // the box is complete in shared memory: hand it to the TMA store engine
+        fence_proxy_async();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer) {
+          if (args.conv.enabled) {
+            if (args.st_out) tma_store_4d(&tmOut, sOut + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
+            if (args.st_out2) tma_store_4d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
+          } else {
+            if (args.st_out) tma_store_3d(&tmOut, sOut + box * 16384, n0 + 64 * box, m0, 0);
+            if (args.st_out2) tma_store_3d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, m0, 0);
           }
-        }
-        if (args.st_out) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(sOut + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4)) = o[q];
-        }
-        if (args.st_out2) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(sOut2 + row_off + ((((uint32_t)(jbase + q)) ^ swz) << 4)) = o2[q];
-        }
-        if (c & 1) {
-          // a 64-column box is complete in shared memory: hand it to the TMA store engine
-          fence_proxy_async();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (threadIdx.x == 64) {
-            if (args.conv.enabled) {
-              if (args.st_out) tma_store_4d(&tmOut, sOut + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
-              if (args.st_out2) tma_store_4d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, c_tx * kConvTileW, c_ty * kConvTileH, c_img);
-            } else {
-              if (args.st_out) tma_store_3d(&tmOut, sOut + box * 16384, n0 + 64 * box, m0, 0);
-              if (args.st_out2) tma_store_3d(&tmOut2, sOut2 + box * 16384, n0 + 64 * box, m0, 0);
-            }
-            tma_store_commit();
-          }
+          tma_store_commit();
         }
       }
+      bad = badbits != 0;
     }
-    if (EPI != EPI_WGRAD && threadIdx.x == 64) tma_store_wait_all();
-    if (kBiasCol && n0 == 0 && args.bias_grad != nullptr) {
+    if (EPI != EPI_WGRAD && issuer) tma_store_wait_all();
+    if (kBiasCol && grp == 0 && n0 == 0 && args.bias_grad != nullptr) {
       uint32_t v[32];
       tmem_ld_32x32(t_row + BN, v);
       tmem_ld_wait();
@@ -469,6 +462,7 @@ int gemm_launch(const GemmLaunch& L, cudaStream_t stream, bool pdl) {
   ACEZ_GEMM_CASE(256, false, true, EPI_DGRAD)
   ACEZ_GEMM_CASE(128, false, true, EPI_DGRAD)
   ACEZ_GEMM_CASE(128, true, true, EPI_WGRAD)
+  ACEZ_GEMM_CASE(256, true, true, EPI_WGRAD)
   // generic fp32-output variants (tests / probing of operand layouts)
   ACEZ_GEMM_CASE(128, false, false, EPI_WGRAD)
   ACEZ_GEMM_CASE(128, false, true, EPI_WGRAD)

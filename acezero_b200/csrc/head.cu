@@ -10,6 +10,8 @@
 //   XTRA           : [nres][max_rows][512] fp16 post-ReLU output of the last conv of each residual block (ReLU mask)
 //   DZ             : [L][max_rows][512] fp16 gradient w.r.t. the pre-activation of each hidden layer (x grad_scale)
 //   GRES           : [max_rows][512] fp16 running skip-path gradient
+#include <stdlib.h>
+
 #include <vector>
 
 #include "gemm.cuh"
@@ -46,7 +48,13 @@ struct acez_head_plan {
   int prepared_training;
   std::vector<acez::GemmLaunch> fwd;
   std::vector<acez::GemmLaunch> dgrad;
-  acez::GemmLaunch wgrad;
+  acez::GemmLaunch wgrad;                    // all layers in one launch (grid.z = layer)
+  std::vector<acez::GemmLaunch> wgrad_layer;  // one launch per layer, run on a side stream under the dgrad chain
+  cudaStream_t side_stream;
+  cudaEvent_t ev_dz[32];
+  cudaEvent_t ev_join;
+  bool side_ready;
+  int overlap_wgrad;
 };
 
 namespace acez {
@@ -518,26 +526,49 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1;
     const float bc2_sqrt = sqrtf(bc2);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-      float gi = g[i];
+    auto update = [&](float gi, float& pi, float& mi, float& vi) {
       if (use_scaler) gi = __half2float(__float2half_rn(gi));  // fp16 weight gradient of the autocast conv
       gi *= inv_scale;                                          // GradScaler.unscale_
-      float pi = p[i];
-      pi *= (1.f - lr * wd);                             // decoupled weight decay (torch adamw)
-      const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // exp_avg.lerp_(grad, 1 - beta1)
-      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      pi *= (1.f - lr * wd);                                    // decoupled weight decay (torch adamw)
+      mi = mi + (1.f - b1) * (gi - mi);                         // exp_avg.lerp_(grad, 1 - beta1)
+      vi = b2 * vi + (1.f - b2) * gi * gi;
       const float denom = sqrtf(vi) / bc2_sqrt + eps;
       pi -= step_size * (mi / denom);
-      p[i] = pi;
-      m[i] = mi;
-      v[i] = vi;
-      if (W16 != nullptr) {  // refresh the fp16 shadow the next forward reads
-        const size_t l = i / kLayerStride, r = i % kLayerStride;
+    };
+    const size_t n4 = n / 4;
+    const size_t wsz = (size_t)kC * kC;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+      const float4 g4 = reinterpret_cast<const float4*>(g)[q];
+      float4 p4 = reinterpret_cast<float4*>(p)[q], m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+      update(g4.x, p4.x, m4.x, v4.x);
+      update(g4.y, p4.y, m4.y, v4.y);
+      update(g4.z, p4.z, m4.z, v4.z);
+      update(g4.w, p4.w, m4.w, v4.w);
+      reinterpret_cast<float4*>(p)[q] = p4;
+      reinterpret_cast<float4*>(m)[q] = m4;
+      reinterpret_cast<float4*>(v)[q] = v4;
+      if (W16 != nullptr) {  // refresh the fp16 shadow the next forward reads (layer strides are multiples of 4)
+        const size_t i = 4 * q, l = i / kLayerStride, r = i % kLayerStride;
+        __half2 lo = __floats2half2_rn(p4.x, p4.y), hi = __floats2half2_rn(p4.z, p4.w);
+        uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         if (l < (size_t)L) {
-          if (r < (size_t)kC * kC) W16[l * (size_t)kC * kC + r] = __float2half_rn(pi);
-        } else if (r < (size_t)C3 * kC) {
-          W3h[r] = __float2half_rn(pi);
+          if (r < wsz) *reinterpret_cast<uint2*>(W16 + l * wsz + r) = pk;
+        } else if (r + 3 < (size_t)C3 * kC) {
+          *reinterpret_cast<uint2*>(W3h + r) = pk;
+        } else {
+          const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+          for (int k = 0; k < 4; ++k)
+            if (r + k < (size_t)C3 * kC) W3h[r + k] = __float2half_rn(pv[k]);
         }
+      }
+    }
+    for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      update(g[i], pi, mi, vi);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      if (W16 != nullptr) {
+        const size_t l = i / kLayerStride, r = i % kLayerStride;
+        if (l >= (size_t)L && r < (size_t)C3 * kC) W3h[r] = __float2half_rn(pi);
       }
     }
   }
@@ -626,7 +657,7 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     p.M = kC; p.N = kC; p.K = (rows + 63) / 64 * 64; p.batch = L;
     p.a_zstride = (long long)h->act_stride; p.b_zstride = (long long)h->act_stride;
     p.lda = kC; p.ldb = kC;
-    p.bn = 128;
+    p.bn = 256;  // 128 x 256 tiles: 64 CTAs, 25 % less L2 -> SM operand traffic than 128 x 128 (the kernel is ingest-bound)
     p.epi = EPI_WGRAD;
     int rc = gemm_prepare(&h->wgrad, p);
     if (rc) return rc;
@@ -650,6 +681,35 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     a.bias_grad_zstride = (long long)kLayerStride;
     rc = gemm_finalize(&h->wgrad);
     if (rc) return rc;
+    // per-layer variant (128 x 128 tiles, 16 CTAs per layer): small enough to run on the SMs the 80-CTA dgrad kernels
+    // leave idle, so the weight gradients are computed concurrently with the dgrad chain on a second stream
+    h->wgrad_layer.assign(L, GemmLaunch{});
+    for (int l = 0; l < L; ++l) {
+      GemmProblem q = p;
+      q.A = h->DZ + (size_t)l * h->act_stride;
+      q.B = h->ACT + (size_t)l * h->act_stride;
+      q.batch = 1;
+      q.bn = 128;
+      rc = gemm_prepare(&h->wgrad_layer[l], q);
+      if (rc) return rc;
+      uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, 1};
+      uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)h->act_stride * 2};
+      uint32_t box[3] = {64, 64, 1};
+      rc = make_tensor_map(&h->wgrad_layer[l].tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q.A, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = make_tensor_map(&h->wgrad_layer[l].tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, q.B, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      GemmArgs& b = h->wgrad_layer[l].args;
+      b.out32 = h->grads + (size_t)l * kLayerStride;
+      b.out32_zstride = 0;
+      b.ldo32 = kC;
+      b.bias_grad = h->grads + (size_t)l * kLayerStride + (size_t)kC * kC;
+      b.bias_grad_zstride = 0;
+      rc = gemm_finalize(&h->wgrad_layer[l]);
+      if (rc) return rc;
+    }
   }
   h->prepared_rows = rows;
   h->prepared_training = training;
@@ -701,6 +761,45 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
   return ACEZ_OK;
 }
 
+// dgrad chain + weight gradients. Overlapped mode: layer l's wgrad is enqueued on the plan's side stream as soon as
+// DZ[l] exists (event after the kernel that produced it) and runs on the SMs the dgrad kernels leave idle; the main
+// stream joins at the end. Works eagerly and under stream capture (fork / join through events).
+static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfinite) {
+  const int L = h->L;
+  if (!h->overlap_wgrad) {
+    for (int l = L - 1; l >= 1; --l) {
+      h->dgrad[l].args.nonfinite = nonfinite;
+      int rc = gemm_launch(h->dgrad[l], s);
+      if (rc) return rc;
+    }
+    h->wgrad.args.nonfinite = nonfinite;  // fp16-overflow / inf check of the weight gradients in the epilogue
+    return gemm_launch(h->wgrad, s);
+  }
+  if (!h->side_ready) {
+    ACEZ_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < L; ++i) ACEZ_CUDA(cudaEventCreateWithFlags(&h->ev_dz[i], cudaEventDisableTiming));
+    ACEZ_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->side_ready = true;
+  }
+  cudaStream_t side = h->side_stream;
+  for (int l = L - 1; l >= 0; --l) {
+    // DZ[l] is complete here (tail for l = L-1, dgrad l+1 otherwise)
+    ACEZ_CUDA(cudaEventRecord(h->ev_dz[l], s));
+    ACEZ_CUDA(cudaStreamWaitEvent(side, h->ev_dz[l], 0));
+    h->wgrad_layer[l].args.nonfinite = nonfinite;
+    int rc = gemm_launch(h->wgrad_layer[l], side, /*pdl=*/false);
+    if (rc) return rc;
+    if (l >= 1) {
+      h->dgrad[l].args.nonfinite = nonfinite;
+      rc = gemm_launch(h->dgrad[l], s, /*pdl=*/false);  // an event record sits between consecutive dgrad kernels
+      if (rc) return rc;
+    }
+  }
+  ACEZ_CUDA(cudaEventRecord(h->ev_join, side));
+  ACEZ_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+  return ACEZ_OK;
+}
+
 }  // namespace acez
 
 // ----------------------------------------------------------------------------------------------
@@ -749,6 +848,13 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);
   h->BLKCOUNT = reinterpret_cast<unsigned int*>(base + lo.blkpart + 4096 * 8 * sizeof(float));
   h->counters_zeroed = false;
+  h->side_ready = false;
+  {
+    const char* e = getenv("ACEZ_WGRAD_OVERLAP");
+    // measured on B200 (round 1): the 16-CTA per-layer kernels are bound by the per-SM L2 ingest rate (~20 us each)
+    // and become the critical path (393 us / iteration vs 216 us batched), so the batched launch stays the default
+    h->overlap_wgrad = (e == nullptr) ? 0 : atoi(e);
+  }
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;
   h->prepared_training = 0;
@@ -756,7 +862,15 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   return ACEZ_OK;
 }
 
-extern "C" void acez_head_plan_destroy(acez_head_plan* plan) { delete plan; }
+extern "C" void acez_head_plan_destroy(acez_head_plan* plan) {
+  if (plan == nullptr) return;
+  if (plan->side_ready) {
+    cudaStreamDestroy(plan->side_stream);
+    for (int i = 0; i < plan->L; ++i) cudaEventDestroy(plan->ev_dz[i]);
+    cudaEventDestroy(plan->ev_join);
+  }
+  delete plan;
+}
 
 extern "C" int acez_head_sync_weights(acez_head_plan* h, acez_stream_t stream) {
   ACEZ_REQUIRE(h != nullptr, "head_sync_weights: null plan");
@@ -830,13 +944,7 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   t.nonfinite = nonfinite;
   rc = launch_tail(h, t, rows, s, nonfinite, true, true);
   if (rc) return rc;
-  for (int l = L - 1; l >= 1; --l) {
-    h->dgrad[l].args.nonfinite = nonfinite;
-    rc = gemm_launch(h->dgrad[l], s);
-    if (rc) return rc;
-  }
-  h->wgrad.args.nonfinite = nonfinite;  // fp16-overflow / inf check of the weight gradients in the epilogue
-  return gemm_launch(h->wgrad, s);
+  return launch_backward_gemms(h, s, nonfinite);
 }
 
 extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc_b3, int* nonfinite,
@@ -860,13 +968,7 @@ extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc
   t.nonfinite = nonfinite;
   rc = launch_tail(h, t, rows, s, nonfinite, true, false);  // first kernel of this call
   if (rc) return rc;
-  for (int l = L - 1; l >= 1; --l) {
-    h->dgrad[l].args.nonfinite = nonfinite;
-    rc = gemm_launch(h->dgrad[l], s);
-    if (rc) return rc;
-  }
-  h->wgrad.args.nonfinite = nonfinite;
-  return gemm_launch(h->wgrad, s);
+  return launch_backward_gemms(h, s, nonfinite);
 }
 
 extern "C" int acez_head_forward_train(acez_head_plan* h, const void* features, int rows, float* sc_out,
