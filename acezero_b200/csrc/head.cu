@@ -148,22 +148,25 @@ struct MultiGather {
   uint8_t* dst[8];
   int row_bytes[8];
 };
-__global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows) {
+__global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows, int n_arrays) {
   pdl_wait();
   pdl_launch_dependents();
-  const int a = blockIdx.y;
+  // one warp per batch row, all arrays: the 1 KB feature row moves as 2 x 16 B per lane, the small arrays as words
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const int rb = g.row_bytes[a];
-  const uint8_t* s = g.src[a] + (size_t)idx[warp] * rb;
-  uint8_t* d = g.dst[a] + (size_t)warp * rb;
-  if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(g.src[a]) | reinterpret_cast<uintptr_t>(g.dst[a])) & 15) == 0) {
-    for (int o = lane * 16; o < rb; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
-  } else if ((rb & 3) == 0) {
-    for (int o = lane * 4; o < rb; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
-  } else {
-    for (int o = lane * 2; o < rb; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+  const size_t src_row = (size_t)idx[warp];
+  for (int a = 0; a < n_arrays; ++a) {
+    const int rb = g.row_bytes[a];
+    const uint8_t* s = g.src[a] + src_row * rb;
+    uint8_t* d = g.dst[a] + (size_t)warp * rb;
+    if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(g.src[a]) | reinterpret_cast<uintptr_t>(g.dst[a])) & 15) == 0) {
+      for (int o = lane * 16; o < rb; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
+    } else if ((rb & 3) == 0) {
+      for (int o = lane * 4; o < rb; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+    } else {
+      for (int o = lane * 2; o < rb; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+    }
   }
 }
 
@@ -226,9 +229,30 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
   bool bad = false, bad_g = false;
 
   const int warps_total = gridDim.x * (kTailThreads / 32);
+  // software pipeline: the next row's activations and geometry are in flight while the current row is processed
+  uint4 xn[2];
+  float gvn = 0.f, gv2n = 0.f;
+  auto prefetch = [&](int rr) {
+    if (rr >= a.rows) return;
+    const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)rr * kC + lane * 16);
+    xn[0] = xp[0]; xn[1] = xp[1];
+    if (a.training == 1) {
+      gvn = 0.f; gv2n = 0.f;
+      if (a.Pin != nullptr) {
+        if (lane < 12) gvn = a.Pin[12 * (size_t)rr + lane];
+      } else if (lane < 12) gvn = a.A[12 * (size_t)rr + lane];
+      else if (lane < 28) gvn = a.T[16 * (size_t)rr + (lane - 12)];
+      // second wave: K (9), Kinv (9), target px (2) -> 20 values on lanes 0..19
+      if (lane < 9) gv2n = a.K[9 * (size_t)rr + lane];
+      else if (lane < 18) gv2n = a.Kinv[9 * (size_t)rr + (lane - 9)];
+      else if (lane < 20) gv2n = a.tpx[2 * (size_t)rr + (lane - 18)];
+    }
+  };
+  prefetch(blockIdx.x * (kTailThreads / 32) + warp);
   for (int row = blockIdx.x * (kTailThreads / 32) + warp; row < a.rows; row += warps_total) {
-    const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * kC + lane * 16);
-    uint4 xr[2] = {xp[0], xp[1]};
+    uint4 xr[2] = {xn[0], xn[1]};
+    const float gv = gvn, gv2 = gv2n;
+    prefetch(row + warps_total);
     const __half2* xh = reinterpret_cast<const __half2*>(xr);
     float2 xf[8];
 #pragma unroll
@@ -280,15 +304,6 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     float P[12];
     float Kr[9], Ki[9];
     {
-      float gv = 0.f;
-      if (a.Pin != nullptr) {
-        if (lane < 12) gv = a.Pin[12 * (size_t)row + lane];
-      } else if (lane < 12) gv = a.A[12 * (size_t)row + lane];
-      else if (lane < 28) gv = a.T[16 * (size_t)row + (lane - 12)];
-      float gv2 = 0.f;  // second wave: K (9), Kinv (9), target px (2) -> 20 values on lanes 0..19
-      if (lane < 9) gv2 = a.K[9 * (size_t)row + lane];
-      else if (lane < 18) gv2 = a.Kinv[9 * (size_t)row + (lane - 9)];
-      else if (lane < 20) gv2 = a.tpx[2 * (size_t)row + (lane - 18)];
       __syncwarp();
       if (lane < 28) sGeo[warp][lane] = gv;
       if (lane < 20) sGeo[warp][28 + lane] = gv2;
@@ -466,12 +481,18 @@ __global__ void fc3_reduce_kernel(const float* __restrict__ part, int nblk, int 
                                   float* __restrict__ gb3, int* __restrict__ nonfinite) {
   pdl_wait();
   pdl_launch_dependents();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 threads per output element (strided over the slab partials), 3 shuffles to combine
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gt >> 3, sub = gt & 7;
   const int total = 4 * kC + 4;
+  float s = 0.f;
+  if (idx < total)
+    for (int b = sub; b < nblk; b += 8) s += part[(size_t)b * total + idx];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
   bool bad = false;
-  if (idx < total) {
-    float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * total + idx];
+  if (idx < total && sub == 0) {
     if (idx < 4 * kC) {
       if (idx < C3 * kC) { gW3[idx] = s; bad = !isfinite(s) || fabsf(s) > 65504.f; }
     } else if (idx - 4 * kC < C3) {
@@ -537,9 +558,24 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     };
     const size_t n4 = n / 4;
     const size_t wsz = (size_t)kC * kC;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
-      const float4 g4 = reinterpret_cast<const float4*>(g)[q];
-      float4 p4 = reinterpret_cast<float4*>(p)[q], m4 = reinterpret_cast<float4*>(m)[q], v4 = reinterpret_cast<float4*>(v)[q];
+    const size_t tstride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += 2 * tstride) {
+     // two independent groups per trip: 8 loads in flight per thread
+     float4 G[2], P[2], M[2], V[2];
+#pragma unroll
+     for (int u = 0; u < 2; ++u) {
+       const size_t q = q0 + u * tstride;
+       if (q < n4) {
+         G[u] = reinterpret_cast<const float4*>(g)[q]; P[u] = reinterpret_cast<float4*>(p)[q];
+         M[u] = reinterpret_cast<float4*>(m)[q]; V[u] = reinterpret_cast<float4*>(v)[q];
+       }
+     }
+#pragma unroll
+     for (int u = 0; u < 2; ++u) {
+      const size_t q = q0 + u * tstride;
+      if (q >= n4) continue;
+      const float4 g4 = G[u];
+      float4 p4 = P[u], m4 = M[u], v4 = V[u];
       update(g4.x, p4.x, m4.x, v4.x);
       update(g4.y, p4.y, m4.y, v4.y);
       update(g4.z, p4.z, m4.z, v4.z);
@@ -561,6 +597,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
             if (r + k < (size_t)C3 * kC) W3h[r + k] = __float2half_rn(pv[k]);
         }
       }
+     }
     }
     for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
       float pi = p[i], mi = m[i], vi = v[i];
@@ -657,7 +694,11 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     p.M = kC; p.N = kC; p.K = (rows + 63) / 64 * 64; p.batch = L;
     p.a_zstride = (long long)h->act_stride; p.b_zstride = (long long)h->act_stride;
     p.lda = kC; p.ldb = kC;
-    p.bn = 256;  // 128 x 256 tiles: 64 CTAs, 25 % less L2 -> SM operand traffic than 128 x 128 (the kernel is ingest-bound)
+    {
+      const char* e = getenv("ACEZ_WGRAD_BN");
+      // measured (round 1, warm graph replays): 128 x 128 tiles / 128 CTAs: 220 us per iteration, 128 x 256 / 64 CTAs: 231 us
+      p.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;
+    }
     p.epi = EPI_WGRAD;
     int rc = gemm_prepare(&h->wgrad, p);
     if (rc) return rc;
@@ -732,7 +773,7 @@ static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
 static int tail_grid(int rows) {
   const int per_block = kTailThreads / 32;
   int g = (rows + per_block - 1) / per_block;
-  const int cap = 4 * sm_count() < 4096 ? 4 * sm_count() : 4096;  // per-block partial slots: 4096
+  const int cap = 2 * sm_count() < 4096 ? 2 * sm_count() : 4096;  // two CTAs per SM; per-block partial slots: 4096
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 
@@ -754,7 +795,7 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
     rc = launch_pdl(fc3_wgrad_partial_kernel, dim3(nblk), dim3(kFc3Threads), 0, s, true, t.x, (const float*)h->G3, rows, h->FC3PART);
     if (rc) return rc;
     const int total = 4 * kC + 4;
-    rc = launch_pdl(fc3_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, s, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
+    rc = launch_pdl(fc3_reduce_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, s, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
                     gW3 + (size_t)h->C3 * kC, nonfinite);
     if (rc) return rc;
   }
@@ -1016,8 +1057,9 @@ extern "C" int acez_gather_rows_multi(const void* const* srcs, void* const* dsts
   if (rc) return rc;
   if (rows == 0) return ACEZ_OK;
   const int threads = 256;
-  dim3 grid((rows * 32 + threads - 1) / threads, n_arrays);
-  return launch_pdl(gather_rows_multi_kernel, grid, dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), false, g, idx, rows);
+  dim3 grid((rows * 32 + threads - 1) / threads);
+  return launch_pdl(gather_rows_multi_kernel, grid, dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), false, g, idx, rows,
+                    n_arrays);
 }
 
 extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,

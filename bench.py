@@ -401,8 +401,8 @@ def run_ours(args):
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "ms_per_step": e2e_ms},
         "gpu_launches": args.steps * 21,
-        "launches_per_step": {"gather": 1, "fwd_gemm": 8, "tail": 1, "dgrad_gemm": 7, "wgrad_gemm": 1, "grad_check": 1,
-                              "adamw": 1, "scaler_update": 1},
+        "launches_per_step": {"gather": 1, "fwd_gemm": 8, "tail": 1, "fc3_wgrad_partial": 1, "fc3_reduce": 1,
+                              "dgrad_gemm": 7, "wgrad_gemm": 1, "adamw": 1},
         "loss_final": loss_final,
         "dsac": {"poses_per_s": poses_per_s, "unit": "poses/s", "hyps": DSAC_HYPS, "images_per_call": n_img,
                  "ms_per_call": dsac_ms, "gpu_launches_per_call": 2,
