@@ -7,7 +7,9 @@ integer contract (image order, patch indices, epoch permutations), same output f
   create_training_buffer : encoder = tcgen05 implicit-GEMM plan, NHWC rows; `torch.multinomial` with the reference's CUDA
                            generator (bit-exact indices); one fused fill kernel per image instead of ~12 small kernels;
                            the mask test runs on the CPU copy of the mask (no GPU sync per image)
-  run_epoch/training_step: `acezero_b200.trainer.TrainLoop` — one CUDA graph per iteration, no host sync
+  run_epoch/training_step: `acezero_b200.trainer.TrainLoop` — one CUDA graph per iteration, no host sync; with
+                           `--pose_refinement naive|mlp` / `--refine_calibration` the refiners stay PyTorch-autograd
+                           models fed by the kernel's dL/dP, dL/dK (eager launches)
 """
 import logging
 import os
@@ -41,9 +43,6 @@ class TrainerACE:
         self.device = torch.device('cuda')
         if getattr(options, "training_buffer_cpu", False):
             _logger.warning("--training_buffer_cpu is ignored: the patch buffer stays in HBM (<= 9.8 GB of 180 GB)")
-        if getattr(options, "pose_refinement", "none") != "none" or getattr(options, "refine_calibration", False):
-            raise NotImplementedError("pose / calibration refinement is the next row of the hot-path scope table "
-                                      "(SURVEY §8f); the kernels already emit dL/dP and dL/dK for it")
         if getattr(options, "render_visualization", False):
             raise NotImplementedError("the visualiser is out of scope (SURVEY §2.1 row 13)")
 
@@ -99,6 +98,12 @@ class TrainerACE:
         self.regressor = self.regressor.to(self.device)
         self.regressor.train()
 
+        # Pose / calibration refinement (reference :173-184): PyTorch-autograd models fed by the kernel's dL/dP, dL/dK.
+        from acezero_b200.refine import PoseRefiner, CalibrationRefiner
+        self.pose_refiner = PoseRefiner(dataset=self.dataset, device=self.device, options=options)
+        self.K_optimizer = CalibrationRefiner(dataset=self.dataset, learning_rate=options.refine_calibration_lr,
+                                              device=self.device) if options.refine_calibration else None
+
         self.iterations_output = options.iterations_output
         self.training_buffer = None
         self.training_buffer_size = options.max_training_buffer_size
@@ -116,8 +121,10 @@ class TrainerACE:
         base_file_name, _ = os.path.splitext(self.options.output_map_file)
         self.log_file = open(base_file_name + '.txt', 'w')
 
+        self.pose_refiner.create_pose_buffer()            # reference :231 (after the buffer: same RNG order)
         head = self.regressor.heads.engine(training=True, max_rows=self.options.batch_size)
-        self.loop = TrainLoop(head, self.options, self.training_buffer, use_depth=self.use_depth)
+        self.loop = TrainLoop(head, self.options, self.training_buffer, use_depth=self.use_depth,
+                              pose_refiner=self.pose_refiner, K_optimizer=self.K_optimizer)
         t0 = time.time()
         while self.loop.run_epoch(on_iteration=self._log_iteration):
             pass
@@ -144,7 +151,16 @@ class TrainerACE:
         _logger.info(f'Iteration: {loop.iteration:6d}|{loop.schedule.max_iterations:6d} / Epoch {loop.epoch:03d}, '
                      f'Loss: {loss:.1f}, Batch inliers ({self.options.learning_rate_cooldown_trigger_px_threshold}px): '
                      f'{inl * 100:.1f}%, Time: {t:.0f}s')
-        self.log_file.write(f"{loop.iteration} {t} {loss} {inl} 0.0 0.0 0.0\n")
+        orig, cur = self.pose_refiner.get_all_original_poses(), self.pose_refiner.get_all_current_poses()
+        dist = torch.linalg.norm(cur[:, :, 3] - orig[:, :, 3], dim=1)
+        _logger.info(f'Poses moved by: Avg={dist.mean() * 100:.1f}cm, Min={dist.min() * 100:.1f}cm, '
+                     f'Max={dist.max() * 100:.1f}cm')
+        line = f"{loop.iteration} {t} {loss} {inl} {dist.mean()} {dist.min()} {dist.max()}"
+        if self.K_optimizer is not None:
+            focal = float(self.K_optimizer.get_focal_length())
+            _logger.info(f"Current Focal Length: {focal:.1f}")
+            line += f" {focal}"
+        self.log_file.write(line + "\n")
 
     # ------------------------------------------------------------------------------------------------------------
     def create_training_buffer(self):
@@ -229,9 +245,11 @@ class TrainerACE:
         """reference ace_trainer.py:696-728: world-to-cam lines, confidence inf."""
         pose_file = self.options.output_map_file.parent / f"poses_{self.options.output_map_file.stem}_preliminary.txt"
         with open(pose_file, 'w') as f:
-            for i in range(len(self.dataset)):
-                pose_34 = torch.as_tensor(self.dataset.poses[i]).float().inverse()[:3].cpu().numpy()
-                posefile.write_pose_to_pose_file(f, rgb_file=self.dataset.rgb_files[i], pose=pose_34,
-                                                 confidence=float('inf'),
-                                                 focal_length=self.dataset.get_focal_length(i))
+            output_poses = self.pose_refiner.get_all_current_poses()
+            for i in range(output_poses.shape[0]):
+                focal = float(self.K_optimizer.get_focal_length()) if self.K_optimizer is not None \
+                    else self.dataset.get_focal_length(i)
+                posefile.write_pose_to_pose_file(f, rgb_file=self.dataset.rgb_files[i],
+                                                 pose=output_poses[i].cpu().detach().numpy(), confidence=float('inf'),
+                                                 focal_length=focal)
         _logger.info(f"Saved refined poses to: {pose_file}")

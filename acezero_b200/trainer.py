@@ -123,7 +123,7 @@ def loss_weight(o, iteration):
 # ----------------------------------------------------------------------------------------------------------------
 class TrainLoop:
     def __init__(self, head: HeadEngine, options, buffer, use_depth=False, rank=0, world_size=1, use_graph=True,
-                 device=None):
+                 device=None, pose_refiner=None, K_optimizer=None):
         self.o = options
         self.head = head
         self.lib = head.lib
@@ -140,7 +140,11 @@ class TrainLoop:
         self.epoch = 0
         self.training_generator = torch.Generator()
         self.training_generator.manual_seed(options.base_seed + 8191)  # ace_trainer.py:79-80
-        self.use_graph = use_graph
+        self.pose_refiner = pose_refiner if (pose_refiner is not None and pose_refiner.active) else None
+        self.K_optimizer = K_optimizer
+        self.refining = self.pose_refiner is not None or self.K_optimizer is not None
+        # pose / calibration refinement runs PyTorch autograd between the kernels: eager launches, no CUDA graph
+        self.use_graph = use_graph and not self.refining
         self._graph = None
         self._warm = 0
         self._graph_host = None
@@ -160,6 +164,9 @@ class TrainLoop:
             "intrinsics_inv": torch.empty((self.b, 3, 3), device=d), "target_crds": torch.empty((self.b, 3), device=d),
             "pose_idx": torch.empty((self.b, 1), dtype=torch.int16, device=d),
         }
+        if self.refining:
+            self.d_P = torch.zeros((self.b, 3, 4), device=d)
+            self.d_Kdiag = torch.zeros((self.b, 2), device=d)
         self.loss_w_host = None
         self.stats_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._last_lw = None
@@ -210,6 +217,60 @@ class TrainLoop:
             allreduce_training_state(h.grads, h.stats, h.found_inf)
         h.adamw_step(use_scaler=self.use_scaler)
 
+    def _enqueue_refined(self):
+        """Iteration with pose and / or calibration refinement (reference ace_trainer.py:527-540, 620-640): the refined
+        per-image poses and the refined intrinsics are PyTorch-autograd values; the fused kernel consumes the composed
+        P = A * T and K' and returns dL/dP, dL/dK00, dL/dK11, which are pushed back through autograd."""
+        o, h, bt = self.o, self.head, self.batch
+        self._gather()
+        lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
+                           float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
+                           o.depth_target, 1.0)
+        with torch.enable_grad():
+            if self.pose_refiner is not None:
+                cur_b34 = self.pose_refiner.current_poses_n34()[bt["pose_idx"].view(-1).long()]
+                poses_b44 = torch.cat([cur_b34, bt["poses_inv"][:, 3:4, :]], dim=1)        # refined [R|t], row (0,0,0,1)
+            else:
+                poses_b44 = bt["poses_inv"]
+            P = torch.bmm(bt["aug_poses_inv"], poses_b44)                                   # :530
+            K = self.K_optimizer.get_refined_calibration_matrices(bt["intrinsics"]) if self.K_optimizer is not None \
+                else bt["intrinsics"]                                                        # :536-540
+        h.train_fwd_bwd(self.b, lp, bt["target_px"], K.detach().contiguous(), bt["intrinsics_inv"],
+                        P=P.detach().contiguous(), target_crds=bt["target_crds"] if self.use_depth else None,
+                        features=None, d_P=self.d_P, d_Kdiag=self.d_Kdiag, use_device_scale=True,
+                        use_device_loss_weight=True)
+        if self.pose_refiner is not None:
+            self.pose_refiner.zero_grad(set_to_none=True)                                   # :621
+        if self.K_optimizer is not None:
+            self.K_optimizer.zero_grad()                                                    # :623-624
+        outs, grads = [], []
+        if P.requires_grad:
+            outs.append(P); grads.append(self.d_P)
+        if K.requires_grad:
+            gK = torch.zeros_like(K)
+            gK[:, 0, 0] = self.d_Kdiag[:, 0]
+            gK[:, 1, 1] = self.d_Kdiag[:, 1]
+            outs.append(K); grads.append(gK)
+        if outs:
+            torch.autograd.backward(outs, grads)
+        if self.world > 1:
+            import torch.distributed as dist
+            from .parallel import allreduce_training_state
+            allreduce_training_state(h.grads, h.stats, h.found_inf)
+            extra = []
+            if self.pose_refiner is not None and self.pose_refiner.pose_optimizer is not None:
+                extra += [p for g in self.pose_refiner.pose_optimizer.param_groups for p in g["params"]]
+            if self.K_optimizer is not None:
+                extra.append(self.K_optimizer.global_f)
+            for p in extra:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+        h.adamw_step(use_scaler=self.use_scaler)                                            # :632
+        if self.pose_refiner is not None and self.iteration > o.pose_refinement_wait:      # :634-636
+            self.pose_refiner.step()
+        if self.K_optimizer is not None:                                                    # :638-640
+            self.K_optimizer.step()
+
     def train_iteration(self, indices, want_stats=False):
         """indices: int64 CPU tensor of the GLOBAL batch (b_global entries of the epoch permutation)."""
         sch = self.schedule
@@ -221,7 +282,9 @@ class TrainLoop:
         self.idx_host.copy_(indices[lo:hi])
         self.idx_dev.copy_(self.idx_host, non_blocking=True)
         self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
-        if self.use_graph:
+        if self.refining:
+            self._enqueue_refined()
+        elif self.use_graph:
             self._run_graphed()
         else:
             self._enqueue_compute()

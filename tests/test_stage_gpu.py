@@ -155,3 +155,33 @@ def test_mapping_then_registration_recovers_held_out_poses(tmp_path):
     assert len(res) == 12
     assert rot < 5.0 and tra < 0.05, (rot, tra, errs)
     assert np.median([r["inliers"] for r in res]) > 300
+
+
+def test_mapping_with_pose_and_calibration_refinement(tmp_path):
+    """SURVEY §8f row 1 (ACE0's default `--pose_refinement mlp --refine_calibration True`): the fused step's dL/dP and
+    dL/dK drive the PyTorch refiners; starting from a 10 % focal error the refined focal length moves most of the way to
+    the true value, the written pose file carries it, and training still converges."""
+    from ace_trainer import TrainerACE
+    from acezero_b200.synthetic import SyntheticDataset
+    from acezero_b200.weights import random_encoder_state
+    from acezero_b200 import posefile
+    f_gt = 262.5
+    ds = SyntheticDataset(32, H=240, W=320, focal=f_gt, device="cuda")
+    ds.set_external_focal_length(f_gt * 1.1)   # the dataset reports a wrong focal length; images are rendered with f_gt
+    o = _options(tmp_path, iterations=2000, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
+                 pose_refinement="mlp", refine_calibration=True, refine_calibration_lr=0.001, pose_refinement_lr=0.001,
+                 learning_rate_schedule="1cyclepoly", learning_rate_max=0.003, learning_rate_warmup_iterations=200,
+                 learning_rate_cooldown_iterations=800)
+    o.encoder_state_dict = random_encoder_state(77)
+    tr = TrainerACE(o, dataset=ds)
+    tr.train()
+    f_end = float(tr.K_optimizer.get_focal_length())
+    assert abs(f_end - f_gt) < 0.5 * abs(1.1 * f_gt - f_gt), f"focal {f_end:.1f} (start {1.1 * f_gt:.1f}, true {f_gt})"
+    files, poses, focals = posefile.load_dataset_ace(tmp_path / "poses_map_preliminary.txt", 0)
+    assert len(files) == 32 and abs(focals[0] - f_end) < 1e-3
+    lines = (tmp_path / "map.txt").read_text().strip().splitlines()
+    assert len(lines[0].split()) == 8                      # iter time loss inliers mean min max focal
+    first, last = [float(x) for x in lines[0].split()], [float(x) for x in lines[-1].split()]
+    assert last[2] < 0.6 * first[2]
+    moved = tr.pose_refiner.get_all_current_poses()[:, :, 3] - tr.pose_refiner.get_all_original_poses()[:, :, 3]
+    assert float(moved.norm(dim=1).max()) > 0             # the pose MLP received gradients and stepped
