@@ -203,8 +203,11 @@ class TrainLoop:
         if part in ("all", "fwd_bwd") and gather:
             self._gather()
         bt = self.batch
+        # data parallel: the fp16-overflow check must see the SUMMED gradient (a per-rank partial can pass while the sum
+        # overflows), so the optimiser runs its own check pass; single GPU: the backward kernels' folded check is complete
+        flag_complete = self.world == 1
         if part == "optimizer":
-            h.adamw_step(use_scaler=self.use_scaler)
+            h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete)
             return
         h.train_fwd_bwd(self.b, lp, bt["target_px"], bt["intrinsics"], bt["intrinsics_inv"],
                         aug_inv=bt["aug_poses_inv"], pose_inv=bt["poses_inv"], P=P,
@@ -215,7 +218,7 @@ class TrainLoop:
         if self.world > 1:
             from .parallel import allreduce_training_state
             allreduce_training_state(h.grads, h.stats, h.found_inf)
-        h.adamw_step(use_scaler=self.use_scaler)
+        h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete)
 
     def _enqueue_refined(self):
         """Iteration with pose and / or calibration refinement (reference ace_trainer.py:527-540, 620-640): the refined
@@ -265,7 +268,7 @@ class TrainLoop:
             for p in extra:
                 if p.grad is not None:
                     dist.all_reduce(p.grad)
-        h.adamw_step(use_scaler=self.use_scaler)                                            # :632
+        h.adamw_step(use_scaler=self.use_scaler, flag_complete=self.world == 1)             # :632
         if self.pose_refiner is not None and self.iteration > o.pose_refinement_wait:      # :634-636
             self.pose_refiner.step()
         if self.K_optimizer is not None:                                                    # :638-640
