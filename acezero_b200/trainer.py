@@ -311,7 +311,7 @@ class TrainLoop:
         for k in BUFFER_KEYS[1:]:
             self.batch[k].copy_(host_batch[k], non_blocking=True)
         self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
-        if self.use_graph:
+        if self.use_graph and self.world == 1:   # (NCCL all-reduces are not captured: data parallel runs this path eagerly)
             if self._graph_host is None:
                 if self._warm_host < 2:
                     self._warm_host += 1
