@@ -45,7 +45,9 @@ class HeadEngine:
         self.n_params = int(self.lib.acez_head_param_count(C.byref(self.cfg)))
         assert self.n_params == self.L * LAYER_STRIDE + self.C3 * 512 + self.C3
         self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
-        self.grads = torch.zeros(self.n_params, device=self.device, dtype=torch.float32) if training else None
+        # 4 spare floats behind the gradient: data-parallel runs carry the GradScaler flag through the SAME all-reduce
+        self.grads_full = torch.zeros(self.n_params + 4, device=self.device, dtype=torch.float32) if training else None
+        self.grads = self.grads_full[:self.n_params] if training else None
         self.exp_avg = torch.zeros_like(self.params) if training else None
         self.exp_avg_sq = torch.zeros_like(self.params) if training else None
         self.plan = None

@@ -207,17 +207,21 @@ class TrainLoop:
         # overflows), so the optimiser runs its own check pass; single GPU: the backward kernels' folded check is complete
         flag_complete = self.world == 1
         if part == "optimizer":
+            if self.world > 1:
+                self._dp_unpack_flag()
             h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete)
             return
         h.train_fwd_bwd(self.b, lp, bt["target_px"], bt["intrinsics"], bt["intrinsics_inv"],
                         aug_inv=bt["aug_poses_inv"], pose_inv=bt["poses_inv"], P=P,
                         target_crds=bt["target_crds"] if self.use_depth else None, features=None, d_P=d_P,
                         d_Kdiag=d_Kdiag, use_device_scale=True, use_device_loss_weight=True)
+        if self.world > 1:
+            self._dp_pack_flag()
         if part == "fwd_bwd":
             return
         if self.world > 1:
-            from .parallel import allreduce_training_state
-            allreduce_training_state(h.grads, h.stats, h.found_inf)
+            self._dp_allreduce()
+            self._dp_unpack_flag()
         h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete)
 
     def _enqueue_refined(self):
@@ -274,6 +278,30 @@ class TrainLoop:
         if self.K_optimizer is not None:                                                    # :638-640
             self.K_optimizer.step()
 
+    # ---- data parallel: ONE all-reduce per iteration. The local GradScaler flag rides in a spare slot behind the
+    # gradient (+inf when set: any rank's inf makes the sum non-finite); statistics are reduced only when someone reads them
+    def _dp_pack_flag(self):
+        h = self.head
+        if not hasattr(self, "_inf_c"):
+            self._inf_c = torch.tensor([float("inf")], device=self.device)
+            self._zero_c = torch.zeros(1, device=self.device)
+        torch.where(h.found_inf > 0, self._inf_c, self._zero_c, out=h.grads_full[h.n_params:h.n_params + 1])
+
+    def _dp_allreduce(self):
+        import torch.distributed as dist
+        dist.all_reduce(self.head.grads_full)
+
+    def _dp_unpack_flag(self):
+        h = self.head
+        h.found_inf.copy_((h.grads_full[h.n_params:h.n_params + 1] != 0).to(torch.int32))
+
+    def _dp_reduce_stats(self):
+        import torch.distributed as dist
+        st = self.head.stats.clone()
+        dist.all_reduce(st)
+        st[3] = (st[3] > 0).float()
+        return st
+
     def train_iteration(self, indices, want_stats=False):
         """indices: int64 CPU tensor of the GLOBAL batch (b_global entries of the epoch permutation)."""
         sch = self.schedule
@@ -294,7 +322,8 @@ class TrainLoop:
         need = want_stats or sch.needs_inliers
         inl = 0.0
         if need:
-            self.stats_host.copy_(self.head.stats, non_blocking=True)
+            src = self._dp_reduce_stats() if (self.world > 1 and not self.refining) else self.head.stats
+            self.stats_host.copy_(src, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             self.last_stats = self.stats_host.clone()
             inl = float(self.stats_host[1]) / self.b_global
@@ -328,7 +357,7 @@ class TrainLoop:
             self._enqueue_compute(gather=False)
         out = None
         if read_loss:
-            self.stats_host.copy_(self.head.stats, non_blocking=True)
+            self.stats_host.copy_(self._dp_reduce_stats() if self.world > 1 else self.head.stats, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             out = (float(self.stats_host[0]), float(self.stats_host[1]) / self.b_global)
         sch.step(out[1] if out else 0.0)
@@ -359,9 +388,8 @@ class TrainLoop:
         if self.world == 1:
             self._graph[0].replay()
         else:
-            from .parallel import allreduce_training_state
             self._graph[0].replay()
-            allreduce_training_state(self.head.grads, self.head.stats, self.head.found_inf)
+            self._dp_allreduce()
             self._graph[1].replay()
 
     # ------------------------------------------------------------------ epochs
