@@ -22,6 +22,9 @@ def head_layer_names(num_head_blocks):
     return names + ["fc1", "fc2"]
 
 
+HYPER_RING = 64
+
+
 class HeadEngine:
     """Flat-buffer head. `params` is one fp32 CUDA tensor; `views()` exposes reference-named tensors aliasing it."""
 
@@ -58,7 +61,11 @@ class HeadEngine:
         self.scaler_state = torch.tensor([65536.0, 0.0, 0.0, 0.0], device=self.device, dtype=torch.float32)
         self.found_inf = torch.zeros(1, device=self.device, dtype=torch.int32)
         self.stats = torch.zeros(4, device=self.device, dtype=torch.float32)
-        self._hyper_host = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 50.0, 0.0, 0.0]).pin_memory()
+        # ring of pinned staging rows: the host may run many iterations ahead of the device, and every queued copy
+        # must still find ITS iteration's scalars when the DMA finally executes
+        self._hyper_host = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.01, 50.0, 0.0, 0.0]).repeat(HYPER_RING, 1).pin_memory()
+        self._hyper_events = [None] * HYPER_RING
+        self._hyper_slot = 0
 
     # ------------------------------------------------------------------ plan / buffers
     def _config(self):
@@ -194,11 +201,19 @@ class HeadEngine:
 
     def set_hyper(self, lr, loss_weight=None, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01):
         """Stage this iteration's host-computed scalars (pinned -> device, asynchronous, stream ordered)."""
-        h = self._hyper_host
+        slot = self._hyper_slot
+        prev = self._hyper_host[slot - 1]
+        self._hyper_slot = (slot + 1) % HYPER_RING
+        ev = self._hyper_events[slot]
+        if ev is None:
+            ev = self._hyper_events[slot] = torch.cuda.Event()
+        else:
+            ev.synchronize()          # the copy that last used this row (HYPER_RING iterations ago) has executed
+        h = self._hyper_host[slot]
         h[0], h[1], h[2], h[3], h[4] = lr, beta1, beta2, eps, weight_decay
-        if loss_weight is not None:
-            h[5] = loss_weight
+        h[5] = float(prev[5]) if loss_weight is None else loss_weight
         self.hyper.copy_(h, non_blocking=True)
+        ev.record()
 
     def adamw_step(self, use_scaler=True, flag_complete=True, stream=None):
         """flag_complete: found_inf already covers all gradients (true after train_fwd_bwd)."""

@@ -19,6 +19,7 @@ from .head import HeadEngine
 
 BUFFER_KEYS = ("features", "target_px", "aug_poses_inv", "poses_inv", "intrinsics", "intrinsics_inv", "target_crds",
                "pose_idx")
+IDX_RING = 16
 ROW_BYTES = {"features": 1024, "target_px": 8, "aug_poses_inv": 48, "poses_inv": 64, "intrinsics": 36,
              "intrinsics_inv": 36, "target_crds": 12, "pose_idx": 2}  # 1230 B / row (ace_trainer.py:330-340)
 
@@ -157,13 +158,19 @@ class TrainLoop:
         # static per-iteration tensors (graph-stable addresses)
         d = self.device
         self.idx_dev = torch.zeros(self.b, dtype=torch.int64, device=d)
-        self.idx_host = torch.zeros(self.b, dtype=torch.int64).pin_memory()
-        self.batch = {
-            "target_px": torch.empty((self.b, 2), device=d), "aug_poses_inv": torch.empty((self.b, 3, 4), device=d),
-            "poses_inv": torch.empty((self.b, 4, 4), device=d), "intrinsics": torch.empty((self.b, 3, 3), device=d),
-            "intrinsics_inv": torch.empty((self.b, 3, 3), device=d), "target_crds": torch.empty((self.b, 3), device=d),
-            "pose_idx": torch.empty((self.b, 1), dtype=torch.int16, device=d),
-        }
+        # ring of pinned index rows: queued H2D copies read the pinned row when the DMA executes, possibly many host
+        # iterations later, so a row is reused only after the copy that read it has completed
+        self.idx_host = torch.zeros((IDX_RING, self.b), dtype=torch.int64).pin_memory()
+        self._idx_events = [None] * IDX_RING
+        self._idx_slot = 0
+        # one packed allocation; the per-key tensors are typed views (so a host batch can arrive as ONE copy)
+        self._aux_off, off = {}, 0
+        for k in BUFFER_KEYS[1:]:
+            self._aux_off[k] = off
+            off += (ROW_BYTES[k] * self.b + 255) // 256 * 256
+        self._aux_bytes = off
+        self._aux = torch.zeros(off, dtype=torch.uint8, device=d)
+        self.batch = self._aux_views(self._aux)
         if self.refining:
             self.d_P = torch.zeros((self.b, 3, 4), device=d)
             self.d_Kdiag = torch.zeros((self.b, 2), device=d)
@@ -171,6 +178,29 @@ class TrainLoop:
         self.stats_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._last_lw = None
         self.last_stats = None
+
+    _AUX_SHAPES = {"target_px": ((2,), torch.float32), "aug_poses_inv": ((3, 4), torch.float32),
+                   "poses_inv": ((4, 4), torch.float32), "intrinsics": ((3, 3), torch.float32),
+                   "intrinsics_inv": ((3, 3), torch.float32), "target_crds": ((3,), torch.float32),
+                   "pose_idx": ((1,), torch.int16)}
+
+    def _aux_views(self, packed_u8):
+        out = {}
+        for k in BUFFER_KEYS[1:]:
+            shape, dt = self._AUX_SHAPES[k]
+            o = self._aux_off[k]
+            out[k] = packed_u8[o:o + ROW_BYTES[k] * self.b].view(dt).view((self.b,) + shape)
+        return out
+
+    def new_host_batch(self):
+        """A pinned host batch laid out like the device staging area: dict of typed views (fill them in place) over ONE
+        pinned allocation, so that `prefetch_host_batch` moves it with a single host->device copy."""
+        nf = self.b * ROW_BYTES["features"]
+        packed = torch.zeros(nf + self._aux_bytes, dtype=torch.uint8).pin_memory()
+        hb = {"features": packed[:nf].view(torch.float16).view(self.b, 512)}
+        hb.update(self._aux_views(packed[nf:]))
+        hb["_packed"] = packed
+        return hb
 
     # ------------------------------------------------------------------ buffer
     def set_buffer(self, buffer):
@@ -310,8 +340,15 @@ class TrainLoop:
             return False
         from .parallel import shard_bounds
         lo, hi = shard_bounds(self.rank, self.world, self.b_global)
-        self.idx_host.copy_(indices[lo:hi])
-        self.idx_dev.copy_(self.idx_host, non_blocking=True)
+        slot = self._idx_slot
+        self._idx_slot = (slot + 1) % IDX_RING
+        if self._idx_events[slot] is None:
+            self._idx_events[slot] = torch.cuda.Event()
+        else:
+            self._idx_events[slot].synchronize()
+        self.idx_host[slot].copy_(indices[lo:hi])
+        self.idx_dev.copy_(self.idx_host[slot], non_blocking=True)
+        self._idx_events[slot].record()
         self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
         if self.refining:
             self._enqueue_refined()
@@ -335,10 +372,15 @@ class TrainLoop:
         """End-to-end step with HOST inputs (the reference's `--training_buffer_cpu` path, ace_trainer.py:485-494):
         the batch rows arrive in pinned host memory, are copied to the device, trained on, and the loss statistics
         are read back. Returns (loss, inlier fraction)."""
-        sch = self.schedule
         self.head.input_buffer(self.b).copy_(host_batch["features"], non_blocking=True)
         for k in BUFFER_KEYS[1:]:
             self.batch[k].copy_(host_batch[k], non_blocking=True)
+        return self._step_on_static_batch(read_loss)
+
+    def _step_on_static_batch(self, read_loss):
+        """One iteration on whatever the static batch tensors hold (no gather); reads the loss statistics back."""
+        sch = self.schedule
+        sch.check_and_set_cooldown(self.iteration)                    # ace_trainer.py:506
         self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
         if self.use_graph and self.world == 1:   # (NCCL all-reduces are not captured: data parallel runs this path eagerly)
             if self._graph_host is None:
@@ -362,6 +404,80 @@ class TrainLoop:
             out = (float(self.stats_host[0]), float(self.stats_host[1]) / self.b_global)
         sch.step(out[1] if out else 0.0)
         self.iteration += 1
+        return out
+
+    # ---- pipelined host-batch path: the H2D copy of step i+1 runs on a copy stream while step i computes
+    def prefetch_host_batch(self, host_batch):
+        """Start the (asynchronous) host->device copy of a batch into the free staging slot. Call it for batch i+1 before
+        `train_step_prefetched()` of batch i so that the copy overlaps the compute. Batches made by `new_host_batch()`
+        travel as one copy; plain dicts of pinned tensors key by key."""
+        nf = self.b * ROW_BYTES["features"]
+        if not hasattr(self, "_stage"):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [torch.empty(nf + self._aux_bytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._stage_views = []
+            for st in self._stage:
+                v = {"features": st[:nf].view(torch.float16).view(self.b, 512)}
+                v.update(self._aux_views(st[nf:]))
+                self._stage_views.append(v)
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_w = 0   # next slot to fill
+            self._stage_r = 0   # next slot to consume
+            self._stage_used = [False, False]
+        slot = self._stage_w
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_used[slot]:
+                self._copy_stream.wait_event(self._stage_free[slot])   # the step that read this slot has consumed it
+            if "_packed" in host_batch:
+                self._stage[slot].copy_(host_batch["_packed"], non_blocking=True)
+            else:
+                for k in BUFFER_KEYS:
+                    self._stage_views[slot][k].copy_(host_batch[k], non_blocking=True)
+            self._stage_ev[slot].record(self._copy_stream)
+        self._stage_used[slot] = True
+        self._stage_w ^= 1
+
+    def train_step_prefetched(self, read_loss=True, lag=0):
+        """Train on the oldest prefetched batch (two device->device moves, 6.3 MB, into the graph's static tensors, then
+        the captured iteration) and read the loss statistics back: returns (loss, inlier fraction).
+
+        lag=0: the result of THIS step (host waits for the step). lag=1: this step is enqueued, then the result of the
+        PREVIOUS step is returned (None on the first call; `drain_prefetched()` returns the last one), so the host
+        never leaves the device idle. Every step's statistics are read in either mode. The 1cyclepoly schedule needs
+        the inlier fraction of step i before the learning rate of step i+1 (ace_schedule.py:91-101) and forces lag=0."""
+        slot = self._stage_r
+        nf = self.b * ROW_BYTES["features"]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._stage_ev[slot])
+        st = self._stage[slot]
+        self.head.input_buffer(self.b).view(torch.uint8).view(-1).copy_(st[:nf], non_blocking=True)
+        self._aux.copy_(st[nf:], non_blocking=True)
+        self._stage_free[slot].record(cur)
+        self._stage_r ^= 1
+        if not read_loss or lag == 0 or self.schedule.needs_inliers or self.world > 1:
+            return self._step_on_static_batch(read_loss)
+        if not hasattr(self, "_lag_stats"):
+            self._lag_stats = torch.zeros((2, 4), dtype=torch.float32).pin_memory()
+            self._lag_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._lag_n = 0
+        self._step_on_static_batch(False)
+        k = self._lag_n & 1
+        self._lag_stats[k].copy_(self.head.stats, non_blocking=True)
+        self._lag_ev[k].record(cur)
+        self._lag_n += 1
+        return self._read_lagged(k ^ 1) if self._lag_n > 1 else None
+
+    def _read_lagged(self, k):
+        self._lag_ev[k].synchronize()
+        return float(self._lag_stats[k, 0]), float(self._lag_stats[k, 1]) / self.b_global
+
+    def drain_prefetched(self):
+        """Result of the last step enqueued with lag=1 (None if there is none)."""
+        if getattr(self, "_lag_n", 0) == 0:
+            return None
+        out = self._read_lagged((self._lag_n - 1) & 1)
+        self._lag_n = 0
         return out
 
     def _run_graphed(self):

@@ -36,6 +36,10 @@ FLOP_PER_ITER = 61.80e9          # 12.07 MFLOP / patch x 5120
 FLOP_FWD_GEMM = 2 * 5120 * 512 * 512   # one hidden-layer GEMM launch
 DSAC_HYPS = 64
 DSAC_H, DSAC_W = 60, 80
+ENC_BATCH = 8
+# encoder MACs per 480x640 image (ace_network.py:14-59): conv1..4 + res1 + res2, 2 FLOP per MAC
+ENC_FLOP_PER_IMAGE = 2.0 * (9 * 32 * 480 * 640 + 9 * 32 * 64 * 240 * 320 + 9 * 64 * 128 * 120 * 160 + 4800 * (
+    9 * 128 * 256 + 9 * 256 * 256 + 256 * 256 + 9 * 256 * 256 + 9 * 256 * 512 + 512 * 512 + 9 * 512 * 512 + 256 * 512))
 DSAC_BATCH = 1024                # images per batched solver call
 
 
@@ -306,16 +310,34 @@ def run_ours(args):
     host_batches = []
     for i in range(4):
         idx = perm[i * B:(i + 1) * B].to(dev)
-        host_batches.append({k: buf[k][idx].cpu().pin_memory() for k in BUFFER_KEYS})
-    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        hb = loop.new_host_batch()             # pinned, packed: one host->device copy per step
+        for k in BUFFER_KEYS:
+            hb[k].copy_(buf[k][idx])
+        host_batches.append(hb)
+    torch.cuda.synchronize()
+    h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in BUFFER_KEYS)
     for i in range(4):
         loop.train_step_from_host(host_batches[i % 4])
     barrier()
     n_e2e = max(10, min(args.steps, 200))
+    # every step: H2D copy of ITS batch from pinned host memory (issued one step ahead on a copy stream so that it
+    # overlaps the previous step's compute), the training step, and a D2H read of the loss statistics: the host reads
+    # step i-1's loss while step i runs (lag 1; the last one is drained inside the timed region), so no step's result
+    # is skipped and the device never waits for the host
+    loop.prefetch_host_batch(host_batches[0])
+    for i in range(4):
+        loop.prefetch_host_batch(host_batches[(i + 1) % 4])
+        loop.train_step_prefetched(lag=1)
+    loop.drain_prefetched()
+    barrier()
     t0 = time.perf_counter()
+    n_read = 0
     for i in range(n_e2e):
-        loop.train_step_from_host(host_batches[i % 4])     # H2D copy, step, D2H of the loss statistics + sync
+        loop.prefetch_host_batch(host_batches[(i + 1) % 4])
+        n_read += loop.train_step_prefetched(lag=1) is not None
+    n_read += loop.drain_prefetched() is not None
     torch.cuda.synchronize()
+    assert n_read == n_e2e or world > 1, (n_read, n_e2e)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0 / n_e2e)
     e2e_ips = world * 1000.0 / e2e_ms
 
@@ -368,6 +390,46 @@ def run_ours(args):
         p_h, n_h = p.cpu(), n.cpu()
     dsac_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0 / d_steps)
 
+    # ---------------- encoder + head inference (the buffer-fill / registration front end, SURVEY.md §8 "next") ----------
+    from acezero_b200.encoder import EncoderEngine
+    from acezero_b200.weights import random_encoder_state
+    n_enc = ENC_BATCH
+    enc = EncoderEngine(random_encoder_state(7), max_n=n_enc, max_h=480, max_w=640, device=dev)
+    inf_head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=n_enc * 4800, training=False, device=dev)
+    inf_head.load_state(ace_ref.make_head_state(200, 1, True))
+    img_host = (torch.rand((4, n_enc, 1, 480, 640), generator=torch.Generator().manual_seed(3)) - 0.4).half().pin_memory()
+    img_dev = img_host.to(dev)
+    f_enc = torch.empty((n_enc, 60, 80, 512), device=dev, dtype=torch.float16)
+    sc_enc = torch.empty((n_enc * 4800, 3), device=dev, dtype=torch.float32)
+
+    def enc_step(img):
+        enc.forward_nhwc(img, out=f_enc)
+        inf_head.forward(f_enc.view(-1, 512), out=sc_enc)
+
+    for i in range(3):
+        enc_step(img_dev[i % 4])
+    barrier()
+    e_steps = max(5, min(args.steps, 40))
+    e0.record()
+    for i in range(e_steps):
+        enc_step(img_dev[i % 4])
+    e1.record()
+    barrier()
+    enc_ms = max_over_ranks(e0.elapsed_time(e1) / e_steps)
+    e0.record()
+    for i in range(e_steps):
+        enc.forward_nhwc(img_dev[i % 4], out=f_enc)
+    e1.record()
+    barrier()
+    enc_only_ms = max_over_ranks(e0.elapsed_time(e1) / e_steps)
+    sc_host = torch.empty((n_enc * 4800, 3), dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        enc_step(img_host[i % 4].to(dev, non_blocking=True))
+        sc_host.copy_(sc_enc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    enc_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0 / e_steps)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -410,6 +472,13 @@ def run_ours(args):
                          "h2d_bytes_per_step": n_img * 3 * DSAC_H * DSAC_W * 4, "d2h_bytes_per_step": n_img * 68},
                  "cpu_baseline": cpu_d,
                  "work": "13.8 MFLOP + 307 k exp per pose (scoring) + refinement; FP64/FP32 issue bound, 57.6 KB in / 68 B out"},
+        "encoder": {"images_per_s": world * n_enc * 1000.0 / enc_ms, "unit": "480x640 images/s (encoder + head -> scene coordinates)",
+                    "images_per_call": n_enc, "ms_per_call": enc_ms, "encoder_only_ms_per_call": enc_only_ms,
+                    "encoder_tflops": ENC_FLOP_PER_IMAGE * n_enc / (enc_only_ms * 1e-3) / 1e12,
+                    "encoder_frac_of_bf16_peak": ENC_FLOP_PER_IMAGE * n_enc / (enc_only_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+                    "e2e": {"value": world * n_enc * 1000.0 / enc_e2e_ms, "unit": "images/s",
+                            "h2d_bytes_per_step": n_enc * 480 * 640 * 2, "d2h_bytes_per_step": n_enc * 4800 * 12},
+                    "gpu_launches_per_call": 11 + 9},
         "clocks": clk,
     }
     print(json.dumps(line), flush=True)

@@ -153,3 +153,69 @@ def test_gather_rows_bit_exact():
     idx2 = idx % 777
     _lib.check(lib.acez_gather_rows(_lib.ptr(src2), _lib.ptr(idx2), 1280, 12, _lib.ptr(dst2), _lib.stream_ptr()))
     assert torch.equal(dst2, src2[idx2])
+
+
+@pytest.mark.gpu
+def test_host_batch_paths_match_device_buffer_path():
+    """The same rows fed (a) by index from the device-resident buffer, (b) from pinned host memory synchronously and
+    (c) through the pipelined prefetch path must give the same loss trajectory (ace_trainer.py:485-494: the reference's
+    --training_buffer_cpu switch changes where the buffer lives, not the result)."""
+    import bench
+    from acezero_b200.head import HeadEngine
+    from acezero_b200.trainer import TrainLoop, BUFFER_KEYS
+    dev = torch.device("cuda", 0)
+    rows, b, steps = 8192, 1024, 7
+    buf = bench.synth_buffer(rows, dev, 77)
+    losses = []
+    for mode in range(5):
+        o = bench.options(b, 400)
+        head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=b, training=True, device=dev)
+        head.load_state(ace_ref.make_head_state(200, 1, True))
+        loop = TrainLoop(head, o, buf, use_graph=True)
+        perm = torch.randperm(rows, generator=torch.Generator().manual_seed(5))
+        out = []
+        if mode == 0:
+            for i in range(steps):
+                loop.train_iteration(perm[i * b:(i + 1) * b])
+                torch.cuda.synchronize()
+                out.append(float(head.stats[0]))
+        elif mode == 3:    # host running ahead of the device: queued index / scalar uploads must not be overwritten
+            for i in range(steps):
+                loop.train_iteration(perm[i * b:(i + 1) * b])
+            torch.cuda.synchronize()
+            out = list(losses[0][:-1]) + [float(head.stats[0])]
+        elif mode == 4:    # packed pinned batches (one copy per step)
+            hb = []
+            for i in range(steps):
+                h = loop.new_host_batch()
+                for k in BUFFER_KEYS:
+                    h[k].copy_(buf[k][perm[i * b:(i + 1) * b].to(dev)])
+                hb.append(h)
+            torch.cuda.synchronize()
+            loop.prefetch_host_batch(hb[0])
+            for i in range(steps):     # lag 1: the call returns the previous step's statistics
+                if i + 1 < steps:
+                    loop.prefetch_host_batch(hb[i + 1])
+                r = loop.train_step_prefetched(lag=1)
+                assert (r is None) == (i == 0)
+                if r is not None:
+                    out.append(r[0])
+            out.append(loop.drain_prefetched()[0])
+            assert loop.drain_prefetched() is None
+        else:
+            hb = [{k: buf[k][perm[i * b:(i + 1) * b].to(dev)].cpu().pin_memory() for k in BUFFER_KEYS}
+                  for i in range(steps)]
+            if mode == 1:
+                out = [loop.train_step_from_host(h)[0] for h in hb]
+            else:
+                loop.prefetch_host_batch(hb[0])
+                for i in range(steps):
+                    if i + 1 < steps:
+                        loop.prefetch_host_batch(hb[i + 1])
+                    out.append(loop.train_step_prefetched()[0])
+        losses.append(np.array(out))
+    assert np.all(np.isfinite(losses[0]))
+    np.testing.assert_allclose(losses[1], losses[0], rtol=2e-3)
+    np.testing.assert_allclose(losses[2], losses[0], rtol=2e-3)
+    np.testing.assert_allclose(losses[3], losses[0], rtol=2e-3)
+    np.testing.assert_allclose(losses[4], losses[0], rtol=2e-3)
