@@ -10,11 +10,13 @@
 //   XTRA           : [nres][max_rows][512] fp16 post-ReLU output of the last conv of each residual block (ReLU mask)
 //   DZ             : [L][max_rows][512] fp16 gradient w.r.t. the pre-activation of each hidden layer (x grad_scale)
 //   GRES           : [max_rows][512] fp16 running skip-path gradient
+//   RESX           : [max_rows][512] fp16 residual stream of the fused layer chain (head_chain.cu)
 #include <stdlib.h>
 
 #include <vector>
 
 #include "gemm.cuh"
+#include "head_chain.cuh"
 #include "repro_loss.cuh"
 
 namespace acez {
@@ -38,6 +40,7 @@ struct acez_head_plan {
   __half* XTRA;
   __half* DZ;
   __half* GRES;
+  __half* RESX;
   float* G3;
   float* FC3PART;
   float* BLKPART;
@@ -50,6 +53,9 @@ struct acez_head_plan {
   std::vector<acez::GemmLaunch> dgrad;
   acez::GemmLaunch wgrad;                    // all layers in one launch (grid.z = layer)
   std::vector<acez::GemmLaunch> wgrad_layer;  // one launch per layer, run on a side stream under the dgrad chain
+  // fused layer chains (head_chain.cu): one launch for all hidden layers of a pass
+  int use_chain;
+  acez::ChainLaunch chain_fwd, chain_bwd;
   cudaStream_t side_stream;
   cudaEvent_t ev_dz[32];
   cudaEvent_t ev_join;
@@ -60,7 +66,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, g3, fc3part, blkpart, total;
+  size_t w16, w3h, act, resx, xtra, dz, gres, g3, fc3part, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -72,6 +78,7 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
   o.w16 = off; off = align_up(off + (size_t)L * kC * kC * 2, 1024);
   o.w3h = off; off = align_up(off + 4 * kC * 2, 1024);
   o.act = off; off = align_up(off + (size_t)(L + 1) * rows * kC * 2, 1024);
+  o.resx = off; off = align_up(off + rows * kC * 2, 1024);
   if (cfg.training) {
     o.xtra = off; off = align_up(off + (size_t)nres * rows * kC * 2, 1024);
     o.dz = off; off = align_up(off + (size_t)L * rows * kC * 2, 1024);
@@ -752,6 +759,51 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       if (rc) return rc;
     }
   }
+  if (h->use_chain) {
+    // ---- fused forward chain: step l = hidden layer l ----
+    int rc = chain_prepare(&h->chain_fwd, CHAIN_FWD, h->ACT, h->W16, L, h->ACT, (long long)h->act_stride, L + 1, rows);
+    if (rc) return rc;
+    ChainArgs& f = h->chain_fwd.args;
+    f.n_steps = L;
+    for (int l = 0; l < L; ++l) {
+      ChainStep st{};
+      st.w_layer = l;
+      st.relu = 1;
+      st.bias = h->params + (size_t)l * kLayerStride + (size_t)kC * kC;
+      st.out_slot = (h->XTRA != nullptr || l == L - 1) ? l + 1 : -1;  // inference plans keep the tiles on chip
+      const bool res_end = (l % 3 == 2) && (l < 3 * h->nres);
+      if (res_end) {
+        const int k = l / 3;
+        st.resid = (k == 0) ? h->ACT : h->RESX;                                          // res_k (ace_network.py:126,133)
+        st.xtra = (h->XTRA != nullptr) ? h->XTRA + (size_t)k * h->act_stride : nullptr;  // ReLU mask for the backward
+        st.res_save = (k + 1 < h->nres) ? h->RESX : nullptr;
+      }
+      f.step[l] = st;
+    }
+    if (training) {
+      // ---- fused dgrad chain: step s handles layer l = L-1-s (gradient w.r.t. ACT[l], through the ReLU below) ----
+      rc = chain_prepare(&h->chain_bwd, CHAIN_DGRAD, h->DZ + (size_t)(L - 1) * h->act_stride, h->W16, L, h->DZ,
+                         (long long)h->act_stride, L, rows);
+      if (rc) return rc;
+      ChainArgs& b = h->chain_bwd.args;
+      b.n_steps = L - 1;
+      for (int l = L - 1; l >= 1; --l) {
+        ChainStep st{};
+        st.w_layer = l;
+        st.out_slot = l - 1;
+        const bool is_res = (l % 3 == 0) && (l <= 3 * h->nres);
+        if (is_res) {
+          const int k = l / 3;
+          st.mask = h->XTRA + (size_t)(k - 1) * h->act_stride;
+          st.addend = (k < h->nres) ? h->GRES : nullptr;
+          st.out2 = (k >= 2) ? h->GRES : nullptr;
+        } else {
+          st.mask = h->ACT + (size_t)l * h->act_stride;
+        }
+        b.step[L - 1 - l] = st;
+      }
+    }
+  }
   h->prepared_rows = rows;
   h->prepared_training = training;
   return ACEZ_OK;
@@ -807,6 +859,13 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
 // stream joins at the end. Works eagerly and under stream capture (fork / join through events).
 static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfinite) {
   const int L = h->L;
+  if (h->use_chain && L >= 2) {
+    h->chain_bwd.args.nonfinite = nonfinite;
+    int rc = chain_launch(h->chain_bwd, s);
+    if (rc) return rc;
+    h->wgrad.args.nonfinite = nonfinite;
+    return gemm_launch(h->wgrad, s);
+  }
   if (!h->overlap_wgrad) {
     for (int l = L - 1; l >= 1; --l) {
       h->dgrad[l].args.nonfinite = nonfinite;
@@ -881,6 +940,7 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->W16 = reinterpret_cast<__half*>(base + lo.w16);
   h->W3h = reinterpret_cast<__half*>(base + lo.w3h);
   h->ACT = reinterpret_cast<__half*>(base + lo.act);
+  h->RESX = reinterpret_cast<__half*>(base + lo.resx);
   h->XTRA = cfg->training ? reinterpret_cast<__half*>(base + lo.xtra) : nullptr;
   h->DZ = cfg->training ? reinterpret_cast<__half*>(base + lo.dz) : nullptr;
   h->GRES = cfg->training ? reinterpret_cast<__half*>(base + lo.gres) : nullptr;
@@ -895,6 +955,11 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
     // measured on B200 (round 1): the 16-CTA per-layer kernels are bound by the per-SM L2 ingest rate (~20 us each)
     // and become the critical path (393 us / iteration vs 216 us batched), so the batched launch stays the default
     h->overlap_wgrad = (e == nullptr) ? 0 : atoi(e);
+  }
+  {
+    // ACEZ_HEAD_CHAIN=1: all hidden layers of the forward / dgrad pass in one cluster kernel (head_chain.cu)
+    const char* e = getenv("ACEZ_HEAD_CHAIN");
+    h->use_chain = (e != nullptr && atoi(e) != 0 && h->L <= kChainMaxSteps) ? 1 : 0;
   }
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;
@@ -931,6 +996,7 @@ static int head_run_forward(acez_head_plan* h, const void* features, int rows, i
   if (rc) return rc;
   if (features != nullptr && features != h->ACT)
     ACEZ_CUDA(cudaMemcpyAsync(h->ACT, features, (size_t)rows * kC * 2, cudaMemcpyDeviceToDevice, s));
+  if (h->use_chain) return chain_launch(h->chain_fwd, s);
   for (int l = 0; l < h->L; ++l) {
     rc = gemm_launch(h->fwd[l], s, /*pdl=*/l > 0);  // the first kernel of the call follows a copy / foreign work
     if (rc) return rc;

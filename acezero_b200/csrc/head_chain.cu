@@ -1,0 +1,404 @@
+// Fused layer chain of the ACE head on sm_100a: see head_chain.cuh for the design.
+//
+// Roles inside a CTA (320 threads, 1 CTA per SM, cluster of 2 CTAs = one 128-row tile):
+//   warp 0     : TMA producer. Loads the first A tile (8 boxes of 128 rows x 64 channels, SWIZZLE_128B) and streams
+//                the weight k-blocks of every layer through a 3-stage ring (it runs ahead across layer boundaries).
+//   warp 1     : TMEM owner and single-thread tcgen05.mma issuer (M = 128, N = 256, K = 16 per instruction).
+//   warps 2..9 : epilogue, two groups of four warps (one warp per TMEM lane quarter). A group drains one 64-column box
+//                at a time: TMEM -> registers -> bias/ReLU/residual (or ReLU mask) -> fp16 -> the box of the A buffer that
+//                is k-block (4 * rank + box) of the NEXT layer; then one thread publishes the box to the local MMA
+//                warp (mbarrier), copies it into the peer CTA's A buffer (bulk DSMEM copy completing on the peer's
+//                mbarrier) and stores it to HBM (TMA store).
+//
+// Shared memory: A buffer 128 KB (the whole 128 x 512 activation tile, 8 boxes) + weight ring 3 x 32 KB + bias slice.
+// TMEM: 2 x 256 columns (accumulator of layer s in buffer s & 1).
+//
+// Hazards and how they are ordered (s = step index, one step = one layer):
+//   * MMA s+1 reads box j            after  a_ready[j] phase s+1 (own box: epilogue arrive; peer box: complete_tx)
+//   * epilogue s overwrites own box  after  tmem_full[s&1] (all MMAs of step s retired => A_s fully consumed), after the
+//                                           TMA store that last read it (cp.async.bulk.wait_group.read) and after
+//                                           peer_free phase s (the peer consumed the DSMEM copy that read it)
+//   * copy into the peer's box       after  peer_free phase s (= the peer's MMAs of step s retired)
+//   * TMEM buffer s&1 rewritten by MMA s+2: needs every box of epilogue s+1, which follows epilogue s in program order
+#include "head_chain.cuh"
+
+namespace acez {
+
+static constexpr int kC = 512;
+static constexpr int CM = 128;                        // rows per cluster tile
+static constexpr int CN = 256;                        // output channels per CTA
+static constexpr int CK = 64;                         // k-block (64 fp16 = one 128-byte swizzle row)
+static constexpr int kKB = kC / CK;                   // 8 k-blocks per layer
+static constexpr int kBoxBytes = CM * CK * 2;         // 16384: one box = one k-block of A
+static constexpr int kABytes = kKB * kBoxBytes;       // 131072
+static constexpr int kBStage = CN * CK * 2;           // 32768
+static constexpr int kBStages = 3;
+static constexpr int kChainThreads = 320;
+static constexpr int kBiasBytes = 2 * CN * 2;         // double-buffered fp16 bias slice
+static constexpr int kChainSmem = kABytes + kBStages * kBStage + kBiasBytes + 256 /*barriers*/ + 1024 /*align*/;
+static_assert(kChainSmem <= 232448, "shared memory budget");
+static constexpr uint32_t kSw128 = 2;
+
+// ---- cluster / DSMEM primitives ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("acez: chain cluster-barrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// bulk copy local shared memory -> the peer CTA's shared memory; completion (bytes) is signalled on the peer's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// consumption order of the 8 k-blocks: the CTA's own 4 boxes first (they are ready first), then the peer's
+__device__ __forceinline__ int chunk_order(int i, int rank) { return i < 4 ? rank * 4 + i : (rank ^ 1) * 4 + (i - 4); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kChainThreads, 1)
+head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
+  constexpr bool kDgrad = (MODE == CHAIN_DGRAD);
+  extern __shared__ uint8_t smem_raw[];
+  // identical offset in both CTAs of the cluster (same kernel, same dynamic-smem base): mapa translates 1:1
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  __half* sBias = reinterpret_cast<__half*>(sB + kBStages * kBStage);
+  uint64_t* a_ready = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + kBiasBytes);
+  uint64_t* b_full = a_ready + kKB;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* tmem_full = b_empty + kBStages;
+  uint64_t* peer_free = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peer_free + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int peer = rank ^ 1;
+  const int m0 = (blockIdx.x >> 1) * CM;
+  const int n_base = rank * CN;
+  const int n_steps = args.n_steps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < kKB; ++i) mbar_init(&a_ready[i], 1);
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(peer_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / copy
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      for (int i = 0; i < kKB; ++i) {
+        const int j = chunk_order(i, rank);
+        mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+        tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int wl = args.step[s].w_layer;
+        for (int i = 0; i < kKB; ++i) {
+          const int j = chunk_order(i, rank);
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&b_full[stage], kBStage);
+          uint8_t* dst = sB + stage * kBStage;
+          if (!kDgrad) {
+            // forward: B = W[out, in] K-major; rows = this CTA's 256 output channels, k-block j of the input channels
+            tma_load_3d(dst, &tmW, &b_full[stage], j * CK, n_base, wl);
+          } else {
+            // dgrad: B = W[out, in] MN-major (N = input channels, contraction over the output-channel rows)
+#pragma unroll
+            for (int t = 0; t < CN / 64; ++t) tma_load_3d(dst + t * 8192, &tmW, &b_full[stage], n_base + 64 * t, j * CK, wl);
+          }
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer ------------------------------
+    constexpr uint32_t idesc = make_idesc_f16(CM, CN, false, kDgrad);
+    constexpr uint32_t b_lbo = kDgrad ? 8192u : 0u;
+    constexpr uint32_t b_kstep = kDgrad ? 2048u : 32u;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
+      for (int i = 0; i < kKB; ++i) {
+        const int j = chunk_order(i, rank);
+        mbar_wait(&a_ready[j], (uint32_t)(s & 1));
+        // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
+        if (i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+        mbar_wait(&b_full[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBStage);
+#pragma unroll
+          for (int k = 0; k < CK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
+            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
+            umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          tcgen05_commit(&b_empty[stage]);
+          if (i == kKB - 1) tcgen05_commit(&tmem_full[s & 1]);
+        }
+        __syncwarp();
+        if (++stage == kBStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int row = m0 + r;
+    const bool row_ok = row < args.rows;
+    const int etid = threadIdx.x - 64;  // 0..255
+    const bool issuer = (lane == 0) && (quarter == 2 - 2 * grp);
+    const uint32_t swz = (uint32_t)(r & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t peer_free_remote = mapa_u32(smem_u32(peer_free), (uint32_t)peer);
+    uint32_t badbits = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      const ChainStep& st = args.step[s];
+      const int tbuf = s & 1;
+      const bool last = (s == n_steps - 1);
+      if (!kDgrad) {
+        // autocast casts the fp32 bias to fp16 before the conv adds it
+        sBias[tbuf * CN + etid] = __float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f);
+      }
+      mbar_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1));
+      tcgen05_fence_after();
+      // My MMAs of step s have retired: the peer may overwrite my A buffer. Wait for the same from the peer: it has then
+      // consumed the boxes I copied to it during step s-1, so the copies no longer read the boxes rewritten below
+      // (this also holds for the last step, which sends nothing but still overwrites its own boxes).
+      if (etid == 0) mbar_arrive_remote(peer_free_remote);
+      mbar_wait_cluster(peer_free, (uint32_t)(s & 1));
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const __half* opnd = kDgrad ? st.mask : st.resid;
+#pragma unroll 1
+      for (int box = grp; box < CN / 64; box += 2) {
+        const int j = rank * 4 + box;
+        const int col0 = n_base + box * 64;
+        uint4 opv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) opv[q] = make_uint4(0, 0, 0, 0);
+        if (opnd != nullptr && row_ok) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) opv[q] = __ldcg(reinterpret_cast<const uint4*>(opnd + (size_t)row * kC + col0 + q * 8));
+        }
+        if (issuer) tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        uint32_t v[64];
+        tmem_ld_32x64(t_row + (uint32_t)(tbuf * CN + box * 64), v);
+        tmem_ld_wait();
+        // this TMEM buffer is rewritten by the MMAs of step s+2, which are released (transitively) by the barrier
+        // arrivals below: order the completed tcgen05.ld before them
+        tcgen05_fence_before();
+        uint8_t* dst = sA + j * kBoxBytes + r * 128;
+        const size_t goff = (size_t)row * kC + col0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __half2* ph = reinterpret_cast<const __half2*>(&opv[q]);
+          uint4 o, x;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+          __half2* xh = reinterpret_cast<__half2*>(&x);
+          if (!kDgrad) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = q * 8 + 2 * t;
+              const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&sBias[tbuf * CN + box * 64 + col]));
+              float a = __uint_as_float(v[col]) + bf.x;
+              float b = __uint_as_float(v[col + 1]) + bf.y;
+              if (st.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              const __half2 h = __floats2half2_rn(a, b);
+              xh[t] = h;
+              oh[t] = (st.resid != nullptr) ? __hadd2(ph[t], h) : h;  // residual sum in fp16, as the reference's `res + x`
+            }
+            if (row_ok) {
+              if (st.xtra != nullptr) *reinterpret_cast<uint4*>(st.xtra + goff + q * 8) = x;
+              if (st.res_save != nullptr) *reinterpret_cast<uint4*>(st.res_save + goff + q * 8) = o;
+            }
+          } else {
+            uint4 ad = make_uint4(0, 0, 0, 0);
+            if (st.addend != nullptr && row_ok) ad = __ldcg(reinterpret_cast<const uint4*>(st.addend + goff + q * 8));
+            const __half2* ah = reinterpret_cast<const __half2*>(&ad);
+            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = q * 8 + 2 * t;
+              // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+              __half2 h = __floats2half2_rn(__uint_as_float(v[col]), __uint_as_float(v[col + 1]));
+              if (st.addend != nullptr) h = __hadd2(h, ah[t]);
+              xh[t] = h;
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+              badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+              ob[t] = hb & __hgt2_mask(ph[t], zero2);                       // ReLU mask from the saved activation
+            }
+            if (st.out2 != nullptr && row_ok) *reinterpret_cast<uint4*>(st.out2 + goff + q * 8) = x;
+          }
+          *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+        }
+        // the box is complete in shared memory: publish it to the tensor core / copy engines (async proxy)
+        fence_proxy_async();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer) {
+          const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+          if (!last) {
+            mbar_arrive(&a_ready[j]);  // local MMA warp: k-block j of the next layer is in place
+            dsmem_bulk_copy(mapa_u32(box_addr, (uint32_t)peer), box_addr, kBoxBytes,
+                            mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
+          }
+          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
+          tma_store_commit();  // always one group per box (keeps the wait_group.read 1 accounting exact)
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all();
+    if (kDgrad && args.nonfinite != nullptr) {
+      if (__any_sync(0xffffffffu, badbits != 0) && lane == 0) atomicOr(args.nonfinite, 1);
+    }
+  }
+
+  // no CTA of the pair may exit while its partner can still reach into its shared memory / barriers
+  __syncwarp();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16, int L, __half* out_base,
+                  long long out_zstride, int out_slots, int rows) {
+  ACEZ_REQUIRE(C && in && W16 && out_base && rows >= 1 && L >= 1 && out_slots >= 1, "chain_prepare: bad arguments");
+  C->mode = mode;
+  int rc;
+  {
+    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, 1};
+    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)rows * kC * 2};
+    uint32_t box[3] = {64, (uint32_t)CM, 1};
+    rc = make_tensor_map(&C->tmIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, in, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)kC, (uint64_t)L};
+    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)kC * kC * 2};
+    uint32_t box[3] = {64, (uint32_t)(mode == CHAIN_FWD ? CN : 64), 1};
+    rc = make_tensor_map(&C->tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, W16, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, (uint64_t)out_slots};
+    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)out_zstride * 2};
+    uint32_t box[3] = {64, (uint32_t)CM, 1};
+    rc = make_tensor_map(&C->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out_base, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  C->args.rows = rows;
+  C->args.n_steps = 0;
+  C->args.nonfinite = nullptr;
+  return ACEZ_OK;
+}
+
+template <int MODE>
+static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
+  auto kern = head_chain_kernel<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    configured = true;
+  }
+  const int tiles = (C.args.rows + CM - 1) / CM;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * tiles);
+  cfg.blockDim = dim3(kChainThreads);
+  cfg.dynamicSmemBytes = kChainSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, C.tmW, C.tmOut, C.args));
+  return ACEZ_OK;
+}
+
+int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
+  ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain_launch: %d steps", C.args.n_steps);
+  if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD>(C, stream);
+  return chain_launch_mode<CHAIN_DGRAD>(C, stream);
+}
+
+}  // namespace acez

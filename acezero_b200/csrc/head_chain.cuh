@@ -1,0 +1,54 @@
+// Fused layer chain of the ACE head (reference ace_network.py:120-136 forward; its autograd transpose for the dgrad
+// pass): ALL hidden 512x512 layers of one pass in ONE kernel launch.
+//
+// The per-layer GEMMs (gemm.cu) are row-tile independent: output rows [m0, m0+128) of layer l+1 depend only on the
+// same rows of layer l. So a 128-row tile never has to leave the chip between layers. One thread-block cluster of two
+// CTAs owns a row tile; CTA c computes output channels [256c, 256c+256) of every layer (128 x 256 x 512 per layer on
+// tcgen05, accumulators double-buffered in TMEM) and the two CTAs exchange their halves of the new activation tile
+// through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster, completing on the peer's mbarrier),
+// 64-column box by box, so the next layer's MMAs start while the epilogue of the current one is still draining.
+// Weights stream from L2 through a TMA ring that runs ahead across layer boundaries. Every new activation tile is
+// also written to HBM (TMA store) because the weight-gradient GEMM contracts over ALL rows and stays a separate kernel.
+#pragma once
+#include "common.cuh"
+
+namespace acez {
+
+enum ChainMode : int { CHAIN_FWD = 0, CHAIN_DGRAD = 1 };
+static constexpr int kChainMaxSteps = 20;  // hidden layers handled by one launch (3 * res blocks + 2 <= 20)
+
+// One GEMM of the chain, in execution order. All row-major [rows, 512] fp16 unless noted.
+struct ChainStep {
+  int w_layer;           // index into W16 [L][512][512]
+  int out_slot;          // z index in the output tensor map the new tile is stored to; < 0: not stored
+  int relu;              // FWD
+  const float* bias;     // FWD: fp32 master bias [512] (rounded to fp16 before the add, autocast semantics)
+  const __half* resid;   // FWD residual-closing layer: tile = resid + x                    (nullable)
+  __half* xtra;          // FWD: pre-residual x, the ReLU mask of the backward              (nullable)
+  __half* res_save;      // FWD: copy of the residual sum for the next block's `resid`      (nullable)
+  const __half* mask;    // DGRAD: post-activation output of the layer whose ReLU is crossed
+  const __half* addend;  // DGRAD: skip-path gradient added before masking                  (nullable)
+  __half* out2;          // DGRAD: unmasked sum (skip-path gradient for the block below)    (nullable)
+};
+
+struct ChainArgs {
+  int rows;
+  int n_steps;
+  int* nonfinite;  // DGRAD: OR-ed with 1 if a stored gradient is inf / nan (nullable)
+  ChainStep step[kChainMaxSteps];
+};
+
+struct ChainLaunch {
+  CUtensorMap tmIn;   // first A tile: [rows, 512], box {64, 128, 1}
+  CUtensorMap tmW;    // W16 [L][512][512]: FWD box {64, 256, 1} (K-major B), DGRAD box {64, 64, 1} (MN-major B)
+  CUtensorMap tmOut;  // [slots][rows][512], box {64, 128, 1}
+  ChainArgs args;
+  int mode;
+};
+
+// in: the first A operand [rows,512]; out_base/out_zstride(elements)/out_slots: where new tiles are stored.
+int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16, int L, __half* out_base,
+                  long long out_zstride, int out_slots, int rows);
+int chain_launch(const ChainLaunch& C, cudaStream_t stream);
+
+}  // namespace acez
