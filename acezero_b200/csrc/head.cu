@@ -990,6 +990,8 @@ extern "C" int acez_head_sync_weights(acez_head_plan* h, acez_stream_t stream) {
 
 extern "C" void* acez_head_input_ptr(acez_head_plan* h) { return h ? h->ACT : nullptr; }
 
+extern "C" int acez_head_plan_fused_chain(const acez_head_plan* h) { return (h != nullptr && h->use_chain) ? 1 : 0; }
+
 static int head_run_forward(acez_head_plan* h, const void* features, int rows, int training, cudaStream_t s) {
   ACEZ_REQUIRE(rows >= 1 && rows <= h->cfg.max_rows, "head: rows=%d outside [1, %d]", rows, h->cfg.max_rows);
   int rc = head_prepare(h, rows, training);

@@ -175,6 +175,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     constexpr uint32_t idesc = make_idesc_f16(CM, CN, false, kDgrad);
     constexpr uint32_t b_lbo = kDgrad ? 8192u : 0u;
     constexpr uint32_t b_kstep = kDgrad ? 2048u : 32u;
+    const uint32_t peer_free_remote = mapa_u32(smem_u32(peer_free), (uint32_t)peer);
     int stage = 0;
     uint32_t phase = 0;
     for (int s = 0; s < n_steps; ++s) {
@@ -204,6 +205,12 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         __syncwarp();
         if (++stage == kBStages) { stage = 0; phase ^= 1; }
       }
+      // All MMAs of step s have retired once tmem_full completes: nothing reads this CTA's A buffer any more, so the
+      // peer may copy its boxes of the next tile into it. (Signalled from this warp: it idles here anyway until the
+      // epilogue has produced the first box of the next step, and it has no global stores the release would wait for.)
+      mbar_wait(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1));
+      if (lane == 0) mbar_arrive_remote(peer_free_remote);
+      __syncwarp();
     }
   } else {
     // ------------------------------ epilogue ------------------------------
@@ -216,7 +223,6 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     const bool issuer = (lane == 0) && (quarter == 2 - 2 * grp);
     const uint32_t swz = (uint32_t)(r & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t peer_free_remote = mapa_u32(smem_u32(peer_free), (uint32_t)peer);
     uint32_t badbits = 0;
     for (int s = 0; s < n_steps; ++s) {
       const ChainStep& st = args.step[s];
@@ -228,11 +234,6 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       }
       mbar_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1));
       tcgen05_fence_after();
-      // My MMAs of step s have retired: the peer may overwrite my A buffer. Wait for the same from the peer: it has then
-      // consumed the boxes I copied to it during step s-1, so the copies no longer read the boxes rewritten below
-      // (this also holds for the last step, which sends nothing but still overwrites its own boxes).
-      if (etid == 0) mbar_arrive_remote(peer_free_remote);
-      mbar_wait_cluster(peer_free, (uint32_t)(s & 1));
       asm volatile("bar.sync 3, 256;" ::: "memory");
       const __half* opnd = kDgrad ? st.mask : st.resid;
 #pragma unroll 1
@@ -246,7 +247,13 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
 #pragma unroll
           for (int q = 0; q < 8; ++q) opv[q] = __ldcg(reinterpret_cast<const uint4*>(opnd + (size_t)row * kC + col0 + q * 8));
         }
-        if (issuer) tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
+        if (issuer) {
+          // peer_free phase s: the PEER's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
+          // step s-1 (those copies no longer read the boxes rewritten below - also true for the last step, which sends
+          // nothing but still overwrites its own boxes) and its A buffer may be overwritten by this step's copies.
+          if (box == grp) mbar_wait_cluster(peer_free, (uint32_t)(s & 1));
+          tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
+        }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         uint32_t v[64];

@@ -97,6 +97,11 @@ class HeadEngine:
         in_ptr = self.lib.acez_head_input_ptr(self.plan)
         self._input_off = in_ptr - self.workspace.data_ptr()
 
+    @property
+    def fused_chain(self):
+        """True when the plan runs each pass over the hidden layers as one fused cluster kernel (head_chain.cu)."""
+        return bool(self.lib.acez_head_plan_fused_chain(self.plan))
+
     def resize(self, max_rows):
         if max_rows > self.max_rows:
             self.max_rows = int(max_rows)

@@ -149,6 +149,10 @@ void acez_head_plan_destroy(acez_head_plan* plan);
 int acez_head_sync_weights(acez_head_plan* plan, acez_stream_t stream);
 /* Device pointer of the plan's input activation buffer [max_rows,512] fp16 (gather target). */
 void* acez_head_input_ptr(acez_head_plan* plan);
+/* 1 if the plan runs all hidden layers of a pass (ace_network.py:120-136 and its autograd transpose) as ONE fused
+ * cluster kernel per pass (csrc/head_chain.cu), 0 if it launches one tcgen05 GEMM per layer (csrc/gemm.cu). Both are
+ * sm_100a paths with identical semantics; selected at plan creation by the environment variable ACEZ_HEAD_CHAIN. */
+int acez_head_plan_fused_chain(const acez_head_plan* plan);
 
 /* Forward only (registration; ace_network.py:120-149 under autocast): features -> scene coordinates.
  * features: fp16 [rows,512] (nullable = already in the plan's input buffer); sc_out: fp32 [rows,3]

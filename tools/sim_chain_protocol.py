@@ -168,6 +168,10 @@ class Sim:
                 if stage == BST:
                     stage, phase = 0, phase ^ 1
                 yield
+            # all MMAs of the step retired -> tell the peer its copies may overwrite this CTA's A buffer
+            yield from self.wait(c.tmem_full[tb], (s >> 1) & 1, s >> 1)
+            self.c[r ^ 1].peer_free.arrive()
+            yield
 
     def epi(self, r, g):
         c, p = self.c[r], self.c[r ^ 1]
@@ -176,9 +180,7 @@ class Sim:
             tb = s & 1
             last = s == self.n - 1
             yield from self.wait(c.tmem_full[tb], (s >> 1) & 1, s >> 1)
-            if g == 0:
-                p.peer_free.arrive()  # remote arrive (one thread of the CTA)
-            yield from self.wait(c.peer_free, s & 1, s)
+            yield from self.wait(c.peer_free, s & 1, s)  # (the group's issuer thread, before the group barrier)
             # bar.sync 3 (both groups)
             gen = self.bar3_gen[r]
             gen[g] += 1

@@ -1,0 +1,44 @@
+#!/bin/bash
+# One-shot GPU validation of the fused layer-chain kernels (head_chain.cu); everything lands in gpurun_out/.
+#   gpurun --timeout 600 -- 'bash tools/validate_chain.sh'
+set +e
+mkdir -p gpurun_out
+S=gpurun_out/chain_summary.txt
+: > $S
+t0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" >> $S; }
+
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> $S 2>&1
+
+# 1. where does the chain differ from the per-layer path (prints per layer / per box)?
+timeout 150 python tools/diag_chain.py 384 > gpurun_out/chain_diag.log 2>&1
+stamp "diag rc=$?"
+tail -n 40 gpurun_out/chain_diag.log >> $S
+
+# 2. parity tests of the chain
+ACEZ_TEST_CHAIN=1 timeout 300 python -m pytest tests/test_head_chain_gpu.py -m gpu -q -x > gpurun_out/chain_tests.log 2>&1
+rc_tests=$?
+stamp "chain tests rc=$rc_tests"
+tail -n 15 gpurun_out/chain_tests.log >> $S
+
+# 3. segment timings, per-layer path vs chain
+ACEZ_HEAD_CHAIN=0 timeout 120 python tools/probe_step_breakdown.py > gpurun_out/breakdown_layer.log 2>&1
+stamp "breakdown layer rc=$?"; cat gpurun_out/breakdown_layer.log >> $S
+ACEZ_HEAD_CHAIN=1 timeout 120 python tools/probe_step_breakdown.py > gpurun_out/breakdown_chain.log 2>&1
+stamp "breakdown chain rc=$?"; cat gpurun_out/breakdown_chain.log >> $S
+
+if [ $rc_tests -eq 0 ]; then
+  # 4. the bench line with the chain on
+  ACEZ_HEAD_CHAIN=1 timeout 240 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/bench_chain.json 2> gpurun_out/bench_chain.err
+  stamp "bench chain rc=$?"; cat gpurun_out/bench_chain.json >> $S
+  # 5. the whole GPU suite with the chain as the plan's path
+  ACEZ_HEAD_CHAIN=1 ACEZ_TEST_CHAIN=1 timeout 420 python -m pytest tests -m gpu -q -x > gpurun_out/suite_chain.log 2>&1
+  stamp "full suite (chain on) rc=$?"; tail -n 8 gpurun_out/suite_chain.log >> $S
+  # 6. launch list of a chain-enabled step
+  ACEZ_HEAD_CHAIN=1 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none \
+      -k regex:"gemm_tcgen05|head_chain|head_tail|fc3_|adamw|gather_rows" -s 30 -c 24 --csv \
+      --log-file gpurun_out/launches_chain.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+  stamp "ncu launch list rc=$?"
+fi
+stamp "done"
+cat $S
