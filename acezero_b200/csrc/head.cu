@@ -825,7 +825,14 @@ static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
 static int tail_grid(int rows) {
   const int per_block = kTailThreads / 32;
   int g = (rows + per_block - 1) / per_block;
-  const int cap = 2 * sm_count() < 4096 ? 2 * sm_count() : 4096;  // two CTAs per SM; per-block partial slots: 4096
+  // CTAs per SM (default 2; ACEZ_TAIL_BLOCKS_PER_SM to probe): fewer rows per warp shorten the serial per-row chain, more
+  // blocks lengthen the last-block reduction over the per-block partials (4096 slots)
+  static const int per_sm = [] {
+    const char* e = getenv("ACEZ_TAIL_BLOCKS_PER_SM");
+    const int v = e != nullptr ? atoi(e) : 2;
+    return v >= 1 && v <= 8 ? v : 2;
+  }();
+  const int cap = per_sm * sm_count() < 4096 ? per_sm * sm_count() : 4096;
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 

@@ -20,6 +20,8 @@
 //                                           peer_free phase s (the peer consumed the DSMEM copy that read it)
 //   * copy into the peer's box       after  peer_free phase s (= the peer's MMAs of step s retired)
 //   * TMEM buffer s&1 rewritten by MMA s+2: needs every box of epilogue s+1, which follows epilogue s in program order
+#include <stdlib.h>
+
 #include "head_chain.cuh"
 
 namespace acez {
@@ -71,14 +73,25 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+// Bounded waits with a tag (kind << 16 | step << 8 | index): a protocol bug traps with a message that names the wait
+// instead of hanging the GPU. kinds: 1 a_ready, 2 b_full, 3 b_empty, 4 tmem_full, 5 peer_free.
+__device__ __noinline__ void chain_wait_timeout(uint32_t tag, uint32_t parity) {
+  printf("acez: chain wait timeout: kind %u step %u index %u parity %u (block %d, cta rank %d, thread %d)\n", tag >> 16,
+         (tag >> 8) & 0xFF, tag & 0xFF, parity, blockIdx.x, (int)cluster_ctarank(), threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);  // ~1 s
+  }
+}
+__device__ __forceinline__ void chain_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t tag) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {
-      printf("acez: chain cluster-barrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);
   }
 }
 // bulk copy local shared memory -> the peer CTA's shared memory; completion (bytes) is signalled on the peer's mbarrier
@@ -89,12 +102,22 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint3
                "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
                : "memory");
 }
+// 16-byte generic store into the peer CTA's shared memory (fallback exchange path, see kXchgSt)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // consumption order of the 8 k-blocks: the CTA's own 4 boxes first (they are ready first), then the peer's
 __device__ __forceinline__ int chunk_order(int i, int rank) { return i < 4 ? rank * 4 + i : (rank ^ 1) * 4 + (i - 4); }
 
-template <int MODE>
+// XCHG_ST = false: boxes travel to the peer as bulk DSMEM copies (cp.async.bulk shared::cta -> shared::cluster) that
+//                   complete on the peer's mbarrier (transaction bytes).
+// XCHG_ST = true : fallback: every epilogue thread also stores its 8 x 16 B into the peer's box (st.shared::cluster) and
+//                   one thread arrives on the peer's mbarrier (release at cluster scope). Selected by ACEZ_CHAIN_XCHG=st.
+template <int MODE, bool XCHG_ST>
 __global__ void __launch_bounds__(kChainThreads, 1)
 head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
@@ -155,7 +178,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         const int wl = args.step[s].w_layer;
         for (int i = 0; i < kKB; ++i) {
           const int j = chunk_order(i, rank);
-          mbar_wait(&b_empty[stage], phase ^ 1);
+          chain_wait(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           mbar_arrive_expect_tx(&b_full[stage], kBStage);
           uint8_t* dst = sB + stage * kBStage;
           if (!kDgrad) {
@@ -182,10 +205,15 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
       for (int i = 0; i < kKB; ++i) {
         const int j = chunk_order(i, rank);
-        mbar_wait(&a_ready[j], (uint32_t)(s & 1));
+        if (XCHG_ST && i >= 4 && s > 0) {
+          chain_wait_cluster(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);  // peer's generic stores
+          fence_proxy_async_all();
+        } else {
+          chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+        }
         // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
-        if (i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
-        mbar_wait(&b_full[stage], phase);
+        if (!XCHG_ST && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+        chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
@@ -208,7 +236,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       // All MMAs of step s have retired once tmem_full completes: nothing reads this CTA's A buffer any more, so the
       // peer may copy its boxes of the next tile into it. (Signalled from this warp: it idles here anyway until the
       // epilogue has produced the first box of the next step, and it has no global stores the release would wait for.)
-      mbar_wait(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1));
+      chain_wait(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8) | 1u);
       if (lane == 0) mbar_arrive_remote(peer_free_remote);
       __syncwarp();
     }
@@ -232,7 +260,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         // autocast casts the fp32 bias to fp16 before the conv adds it
         sBias[tbuf * CN + etid] = __float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f);
       }
-      mbar_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1));
+      chain_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
       tcgen05_fence_after();
       asm volatile("bar.sync 3, 256;" ::: "memory");
       const __half* opnd = kDgrad ? st.mask : st.resid;
@@ -251,7 +279,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           // peer_free phase s: the PEER's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
           // step s-1 (those copies no longer read the boxes rewritten below - also true for the last step, which sends
           // nothing but still overwrites its own boxes) and its A buffer may be overwritten by this step's copies.
-          if (box == grp) mbar_wait_cluster(peer_free, (uint32_t)(s & 1));
+          if (box == grp) chain_wait_cluster(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
           tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
         }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -263,6 +291,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         // arrivals below: order the completed tcgen05.ld before them
         tcgen05_fence_before();
         uint8_t* dst = sA + j * kBoxBytes + r * 128;
+        const uint32_t dst_peer = mapa_u32(smem_u32(dst), (uint32_t)peer);
         const size_t goff = (size_t)row * kC + col0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -306,17 +335,22 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
             if (st.out2 != nullptr && row_ok) *reinterpret_cast<uint4*>(st.out2 + goff + q * 8) = x;
           }
           *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+          if (XCHG_ST && !last) st_cluster_v4(dst_peer + ((((uint32_t)q) ^ swz) << 4), o);
         }
         // the box is complete in shared memory: publish it to the tensor core / copy engines (async proxy)
-        fence_proxy_async();
+        if (XCHG_ST) fence_proxy_async_all();
+        else fence_proxy_async();
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
         if (issuer) {
           const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
           if (!last) {
             mbar_arrive(&a_ready[j]);  // local MMA warp: k-block j of the next layer is in place
-            dsmem_bulk_copy(mapa_u32(box_addr, (uint32_t)peer), box_addr, kBoxBytes,
-                            mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
+            if (XCHG_ST)
+              mbar_arrive_remote(mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
+            else
+              dsmem_bulk_copy(mapa_u32(box_addr, (uint32_t)peer), box_addr, kBoxBytes,
+                              mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
           }
           if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
           tma_store_commit();  // always one group per box (keeps the wait_group.read 1 accounting exact)
@@ -377,9 +411,9 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
   return ACEZ_OK;
 }
 
-template <int MODE>
+template <int MODE, bool XCHG_ST>
 static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
-  auto kern = head_chain_kernel<MODE>;
+  auto kern = head_chain_kernel<MODE, XCHG_ST>;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
@@ -404,8 +438,16 @@ static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
 
 int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
   ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain_launch: %d steps", C.args.n_steps);
-  if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD>(C, stream);
-  return chain_launch_mode<CHAIN_DGRAD>(C, stream);
+  static const bool xchg_st = [] {
+    const char* e = getenv("ACEZ_CHAIN_XCHG");
+    return e != nullptr && e[0] == 's';
+  }();
+  if (xchg_st) {
+    if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, true>(C, stream);
+    return chain_launch_mode<CHAIN_DGRAD, true>(C, stream);
+  }
+  if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, false>(C, stream);
+  return chain_launch_mode<CHAIN_DGRAD, false>(C, stream);
 }
 
 }  // namespace acez

@@ -50,17 +50,18 @@ def main():
         o = off + i * n
         return ws[o:o + rows * 512 * 2].view(torch.float16).view(rows, 512).float()
 
-    act_off = e0._input_off
-    # workspace layout (head.cu head_layout): act | resx | xtra | dz | gres ... ; each block 1024-aligned
+    # workspace layout (head.cu head_layout), offsets from the plan's 1024-aligned base: w16 | w3h | act | resx | xtra | dz
     def up(v):
         return (v + 1023) // 1024 * 1024
-    resx_off = up(act_off + (L + 1) * n)
-    xtra_off = up(resx_off + n)
-    dz_off = up(xtra_off + nres * n)
-    bufs = [("ACT", act_off, L + 1), ("XTRA", xtra_off, nres), ("DZ", dz_off, L)]
+    act_rel = up(L * 512 * 512 * 2) + up(4 * 512 * 2)
+    base0, base1 = e0._input_off - act_rel, e1._input_off - act_rel
+    resx_rel = up(act_rel + (L + 1) * n)
+    xtra_rel = up(resx_rel + n)
+    dz_rel = up(xtra_rel + nres * n)
+    bufs = [("ACT", act_rel, L + 1), ("XTRA", xtra_rel, nres), ("DZ", dz_rel, L)]
     for name, off, cnt in bufs:
         for i in range(cnt):
-            a, b = view(ws1, off, i), view(ws0, off, i)
+            a, b = view(ws1, base1 + off, i), view(ws0, base0 + off, i)
             scale = float(b.abs().max()) + 1e-20
             d = (a - b).abs() / scale
             per_box = [float(d[:, 64 * k:64 * k + 64].max()) for k in range(8)]
