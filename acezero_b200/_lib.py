@@ -81,7 +81,7 @@ _lib = None
 EXPORTS = [
     "acez_version", "acez_last_error", "acez_device_check", "acez_gemm_f16", "acez_repro_loss_fwd_bwd",
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
-    "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_plan_fused_chain", "acez_head_forward", "acez_head_forward_train",
+    "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_plan_fused_chain", "acez_debug_chain_clocks", "acez_head_forward", "acez_head_forward_train",
     "acez_head_backward", "acez_head_train_fwd_bwd",
     "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
@@ -114,6 +114,7 @@ def load():
     lib.acez_head_input_ptr.argtypes = [vp]
     lib.acez_head_input_ptr.restype = vp
     lib.acez_head_plan_fused_chain.argtypes = [vp]
+    lib.acez_debug_chain_clocks.argtypes = [vp, C.c_size_t, C.POINTER(i)]
     lib.acez_head_forward.argtypes = [vp, vp, i, vp, vp]
     lib.acez_head_forward_train.argtypes = [vp, vp, i, vp, vp]
     lib.acez_head_backward.argtypes = [vp, i, vp, vp, vp]

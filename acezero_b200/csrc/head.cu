@@ -999,6 +999,10 @@ extern "C" void* acez_head_input_ptr(acez_head_plan* h) { return h ? h->ACT : nu
 
 extern "C" int acez_head_plan_fused_chain(const acez_head_plan* h) { return (h != nullptr && h->use_chain) ? 1 : 0; }
 
+extern "C" int acez_debug_chain_clocks(long long* host_out, size_t max_slots, int* n_ctas) {
+  return chain_debug_read(host_out, max_slots, n_ctas);
+}
+
 static int head_run_forward(acez_head_plan* h, const void* features, int rows, int training, cudaStream_t s) {
   ACEZ_REQUIRE(rows >= 1 && rows <= h->cfg.max_rows, "head: rows=%d outside [1, %d]", rows, h->cfg.max_rows);
   int rc = head_prepare(h, rows, training);

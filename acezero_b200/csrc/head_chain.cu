@@ -60,6 +60,23 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Pure permission signal (nothing written by this thread has to become visible to the waiter): no fence.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -85,6 +102,13 @@ __device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity, uint3
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);  // ~1 s
+  }
+}
+__device__ __forceinline__ void chain_wait_cluster_relaxed(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  if (mbar_try_wait_cluster_relaxed(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster_relaxed(bar, parity)) {
+    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);
   }
 }
 __device__ __forceinline__ void chain_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t tag) {
@@ -142,6 +166,8 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const int m0 = (blockIdx.x >> 1) * CM;
   const int n_base = rank * CN;
   const int n_steps = args.n_steps;
+  const bool relaxed_free = (args.flags & 1) != 0;
+  long long* dbg = args.dbg != nullptr ? args.dbg + (size_t)blockIdx.x * kChainDbgSlots : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmIn);
@@ -163,6 +189,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / copy
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -211,6 +238,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         } else {
           chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
         }
+        if (dbg && lane == 0 && (i == 0 || i == 4 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 4 ? 1 : 2))] = clock64();
         // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
         if (!XCHG_ST && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
@@ -237,7 +265,11 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       // peer may copy its boxes of the next tile into it. (Signalled from this warp: it idles here anyway until the
       // epilogue has produced the first box of the next step, and it has no global stores the release would wait for.)
       chain_wait(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8) | 1u);
-      if (lane == 0) mbar_arrive_remote(peer_free_remote);
+      if (lane == 0) {
+        if (relaxed_free) mbar_arrive_remote_relaxed(peer_free_remote);
+        else mbar_arrive_remote(peer_free_remote);
+        if (dbg) dbg[8 + 8 * s + 3] = clock64();
+      }
       __syncwarp();
     }
   } else {
@@ -262,6 +294,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       }
       chain_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
       tcgen05_fence_after();
+      if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
       asm volatile("bar.sync 3, 256;" ::: "memory");
       const __half* opnd = kDgrad ? st.mask : st.resid;
 #pragma unroll 1
@@ -279,8 +312,12 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           // peer_free phase s: the PEER's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
           // step s-1 (those copies no longer read the boxes rewritten below - also true for the last step, which sends
           // nothing but still overwrites its own boxes) and its A buffer may be overwritten by this step's copies.
-          if (box == grp) chain_wait_cluster(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+          if (box == grp) {
+            if (relaxed_free) chain_wait_cluster_relaxed(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+            else chain_wait_cluster(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+          }
           tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
+          if (dbg && grp == 0 && box == 0) dbg[8 + 8 * s + 5] = clock64();
         }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -354,6 +391,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           }
           if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
           tma_store_commit();  // always one group per box (keeps the wait_group.read 1 accounting exact)
+          if (dbg && grp == 0) dbg[8 + 8 * s + (box == 0 ? 6 : 7)] = clock64();
         }
       }
     }
@@ -363,6 +401,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     }
   }
 
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   // no CTA of the pair may exit while its partner can still reach into its shared memory / barriers
   __syncwarp();
   tcgen05_fence_before();
@@ -408,6 +447,28 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
   C->args.rows = rows;
   C->args.n_steps = 0;
   C->args.nonfinite = nullptr;
+  C->args.dbg = nullptr;
+  {
+    // measured on B200 (round 1): see DESIGN.md; 1 = no fence around the buffer-free handshake
+    const char* e = getenv("ACEZ_CHAIN_RELAXED");
+    C->args.flags = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return ACEZ_OK;
+}
+
+static long long* g_chain_dbg = nullptr;
+static int g_chain_dbg_ctas = 0;
+static constexpr int kChainDbgMaxCtas = 1024;
+
+int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas) {
+  ACEZ_REQUIRE(host_out != nullptr && n_ctas != nullptr, "chain_debug_read: null argument");
+  *n_ctas = 0;
+  if (g_chain_dbg == nullptr) return ACEZ_OK;
+  ACEZ_CUDA(cudaDeviceSynchronize());
+  size_t n = (size_t)g_chain_dbg_ctas * kChainDbgSlots;
+  if (n > max_slots) n = max_slots;
+  ACEZ_CUDA(cudaMemcpy(host_out, g_chain_dbg, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  *n_ctas = g_chain_dbg_ctas;
   return ACEZ_OK;
 }
 
@@ -432,7 +493,17 @@ static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, C.tmW, C.tmOut, C.args));
+  ChainArgs args = C.args;
+  static const bool want_dbg = [] {
+    const char* e = getenv("ACEZ_CHAIN_DBG");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (want_dbg && 2 * tiles <= kChainDbgMaxCtas) {
+    if (g_chain_dbg == nullptr) ACEZ_CUDA(cudaMalloc(&g_chain_dbg, (size_t)kChainDbgMaxCtas * kChainDbgSlots * sizeof(long long)));
+    args.dbg = g_chain_dbg;
+    g_chain_dbg_ctas = 2 * tiles;
+  }
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, C.tmW, C.tmOut, args));
   return ACEZ_OK;
 }
 

@@ -31,10 +31,14 @@ struct ChainStep {
   __half* out2;          // DGRAD: unmasked sum (skip-path gradient for the block below)    (nullable)
 };
 
+static constexpr int kChainDbgSlots = 8 + 8 * kChainMaxSteps;  // clock64 stamps per CTA (profiling probe)
+
 struct ChainArgs {
   int rows;
   int n_steps;
+  int flags;       // bit 0: relaxed (instead of release / acquire) cluster-scope signalling of the "A buffer free" barrier
   int* nonfinite;  // DGRAD: OR-ed with 1 if a stored gradient is inf / nan (nullable)
+  long long* dbg;  // nullable: [gridDim.x][kChainDbgSlots] clock64 stamps (ACEZ_CHAIN_DBG=1, tools/probe_chain_time.py)
   ChainStep step[kChainMaxSteps];
 };
 
@@ -50,5 +54,7 @@ struct ChainLaunch {
 int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16, int L, __half* out_base,
                   long long out_zstride, int out_slots, int rows);
 int chain_launch(const ChainLaunch& C, cudaStream_t stream);
+// profiling probe: copies the stamps of the most recent launch with ACEZ_CHAIN_DBG=1 to host memory
+int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas);
 
 }  // namespace acez

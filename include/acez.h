@@ -153,6 +153,9 @@ void* acez_head_input_ptr(acez_head_plan* plan);
  * cluster kernel per pass (csrc/head_chain.cu), 0 if it launches one tcgen05 GEMM per layer (csrc/gemm.cu). Both are
  * sm_100a paths with identical semantics; selected at plan creation by the environment variable ACEZ_HEAD_CHAIN. */
 int acez_head_plan_fused_chain(const acez_head_plan* plan);
+/* Profiling probe of the fused chain kernel (ACEZ_CHAIN_DBG=1): clock64 stamps of the most recent launch,
+ * [n_ctas][8 + 8 * 20] (layout in csrc/head_chain.cu), copied to host memory. */
+int acez_debug_chain_clocks(long long* host_out, size_t max_slots, int* n_ctas);
 
 /* Forward only (registration; ace_network.py:120-149 under autocast): features -> scene coordinates.
  * features: fp16 [rows,512] (nullable = already in the plan's input buffer); sc_out: fp32 [rows,3]

@@ -11,10 +11,15 @@ stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" >> $S; }
 
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> $S 2>&1
 
+# 0. timings + in-kernel timeline of the chain kernels (bulk-copy exchange; release/acquire vs relaxed handshake)
+timeout 150 python tools/probe_chain_time.py > gpurun_out/chain_probe.log 2>&1
+stamp "chain probe rc=$?"
+cat gpurun_out/chain_probe.log >> $S
+
 # 1. where does the chain differ from the per-layer path (prints per layer / per box)?
 timeout 150 python tools/diag_chain.py 384 > gpurun_out/chain_diag.log 2>&1
 stamp "diag (bulk DSMEM copies) rc=$?"
-tail -n 40 gpurun_out/chain_diag.log >> $S
+tail -n 4 gpurun_out/chain_diag.log >> $S
 
 # 2. parity tests of the chain (fallback exchange variant if the bulk-copy variant fails)
 XCHG=bulk
