@@ -131,6 +131,18 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// 32-byte global accesses (sm_100 has 256-bit LDG / STG): a thread's two adjacent 16-byte chunks = one full L2 sector
+__device__ __forceinline__ void ldcg_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -167,6 +179,8 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const int n_base = rank * CN;
   const int n_steps = args.n_steps;
   const bool relaxed_free = (args.flags & 1) != 0;
+  const bool abl_xchg = (args.flags & 2) != 0, abl_store = (args.flags & 4) != 0, abl_w = (args.flags & 8) != 0;
+  const bool abl_opnd = (args.flags & 16) != 0, abl_box = (args.flags & 32) != 0;
   long long* dbg = args.dbg != nullptr ? args.dbg + (size_t)blockIdx.x * kChainDbgSlots : nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -206,6 +220,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         for (int i = 0; i < kKB; ++i) {
           const int j = chunk_order(i, rank);
           chain_wait(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
+          if (abl_w) { mbar_arrive(&b_full[stage]); if (++stage == kBStages) { stage = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&b_full[stage], kBStage);
           uint8_t* dst = sB + stage * kBStage;
           if (!kDgrad) {
@@ -232,7 +247,9 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
       for (int i = 0; i < kKB; ++i) {
         const int j = chunk_order(i, rank);
-        if (XCHG_ST && i >= 4 && s > 0) {
+        if (abl_xchg && i >= 4 && s > 0) {
+          // ablation: the peer's boxes are never sent
+        } else if (XCHG_ST && i >= 4 && s > 0) {
           chain_wait_cluster(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);  // peer's generic stores
           fence_proxy_async_all();
         } else {
@@ -240,7 +257,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         }
         if (dbg && lane == 0 && (i == 0 || i == 4 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 4 ? 1 : 2))] = clock64();
         // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
-        if (!XCHG_ST && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+        if (!XCHG_ST && !abl_xchg && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -296,7 +313,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       tcgen05_fence_after();
       if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
       asm volatile("bar.sync 3, 256;" ::: "memory");
-      const __half* opnd = kDgrad ? st.mask : st.resid;
+      const __half* opnd = abl_opnd ? nullptr : (kDgrad ? st.mask : st.resid);
 #pragma unroll 1
       for (int box = grp; box < CN / 64; box += 2) {
         const int j = rank * 4 + box;
@@ -306,7 +323,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         for (int q = 0; q < 8; ++q) opv[q] = make_uint4(0, 0, 0, 0);
         if (opnd != nullptr && row_ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) opv[q] = __ldcg(reinterpret_cast<const uint4*>(opnd + (size_t)row * kC + col0 + q * 8));
+          for (int q = 0; q < 8; q += 2) ldcg_256(opnd + (size_t)row * kC + col0 + q * 8, opv[q], opv[q + 1]);
         }
         if (issuer) {
           // peer_free phase s: the PEER's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
@@ -331,48 +348,57 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
         const uint32_t dst_peer = mapa_u32(smem_u32(dst), (uint32_t)peer);
         const size_t goff = (size_t)row * kC + col0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const __half2* ph = reinterpret_cast<const __half2*>(&opv[q]);
-          uint4 o, x;
-          __half2* oh = reinterpret_cast<__half2*>(&o);
-          __half2* xh = reinterpret_cast<__half2*>(&x);
-          if (!kDgrad) {
+        for (int qp = 0; qp < 8; qp += 2) {
+          uint4 o2[2], x2[2];
+          uint4 ad2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (kDgrad && st.addend != nullptr && row_ok && !abl_opnd) ldcg_256(st.addend + goff + qp * 8, ad2[0], ad2[1]);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int col = q * 8 + 2 * t;
-              const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&sBias[tbuf * CN + box * 64 + col]));
-              float a = __uint_as_float(v[col]) + bf.x;
-              float b = __uint_as_float(v[col + 1]) + bf.y;
-              if (st.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              const __half2 h = __floats2half2_rn(a, b);
-              xh[t] = h;
-              oh[t] = (st.resid != nullptr) ? __hadd2(ph[t], h) : h;  // residual sum in fp16, as the reference's `res + x`
-            }
-            if (row_ok) {
-              if (st.xtra != nullptr) *reinterpret_cast<uint4*>(st.xtra + goff + q * 8) = x;
-              if (st.res_save != nullptr) *reinterpret_cast<uint4*>(st.res_save + goff + q * 8) = o;
-            }
-          } else {
-            uint4 ad = make_uint4(0, 0, 0, 0);
-            if (st.addend != nullptr && row_ok) ad = __ldcg(reinterpret_cast<const uint4*>(st.addend + goff + q * 8));
-            const __half2* ah = reinterpret_cast<const __half2*>(&ad);
-            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+          for (int hq = 0; hq < 2; ++hq) {
+            const int q = qp + hq;
+            const __half2* ph = reinterpret_cast<const __half2*>(&opv[q]);
+            uint4& o = o2[hq];
+            uint4& x = x2[hq];
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+            __half2* xh = reinterpret_cast<__half2*>(&x);
+            if (!kDgrad) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int col = q * 8 + 2 * t;
-              // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
-              __half2 h = __floats2half2_rn(__uint_as_float(v[col]), __uint_as_float(v[col + 1]));
-              if (st.addend != nullptr) h = __hadd2(h, ah[t]);
-              xh[t] = h;
-              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-              badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
-              ob[t] = hb & __hgt2_mask(ph[t], zero2);                       // ReLU mask from the saved activation
+              for (int t = 0; t < 4; ++t) {
+                const int col = q * 8 + 2 * t;
+                const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&sBias[tbuf * CN + box * 64 + col]));
+                float a = __uint_as_float(v[col]) + bf.x;
+                float b = __uint_as_float(v[col + 1]) + bf.y;
+                if (st.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                const __half2 h = __floats2half2_rn(a, b);
+                xh[t] = h;
+                oh[t] = (st.resid != nullptr) ? __hadd2(ph[t], h) : h;  // residual sum in fp16, as the reference's `res + x`
+              }
+            } else {
+              const __half2* ah = reinterpret_cast<const __half2*>(&ad2[hq]);
+              const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+              uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int col = q * 8 + 2 * t;
+                // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+                __half2 h = __floats2half2_rn(__uint_as_float(v[col]), __uint_as_float(v[col + 1]));
+                if (st.addend != nullptr) h = __hadd2(h, ah[t]);
+                xh[t] = h;
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+                ob[t] = hb & __hgt2_mask(ph[t], zero2);                       // ReLU mask from the saved activation
+              }
             }
-            if (st.out2 != nullptr && row_ok) *reinterpret_cast<uint4*>(st.out2 + goff + q * 8) = x;
+            if (!abl_box) *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+            if (XCHG_ST && !last) st_cluster_v4(dst_peer + ((((uint32_t)q) ^ swz) << 4), o);
           }
-          *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
-          if (XCHG_ST && !last) st_cluster_v4(dst_peer + ((((uint32_t)q) ^ swz) << 4), o);
+          if (row_ok && !abl_opnd) {
+            if (!kDgrad) {
+              if (st.xtra != nullptr) st_256(st.xtra + goff + qp * 8, x2[0], x2[1]);
+              if (st.res_save != nullptr) st_256(st.res_save + goff + qp * 8, o2[0], o2[1]);
+            } else if (st.out2 != nullptr) {
+              st_256(st.out2 + goff + qp * 8, x2[0], x2[1]);
+            }
+          }
         }
         // the box is complete in shared memory: publish it to the tensor core / copy engines (async proxy)
         if (XCHG_ST) fence_proxy_async_all();
@@ -383,13 +409,14 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
           if (!last) {
             mbar_arrive(&a_ready[j]);  // local MMA warp: k-block j of the next layer is in place
-            if (XCHG_ST)
+            if (abl_xchg) {
+            } else if (XCHG_ST)
               mbar_arrive_remote(mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
             else
               dsmem_bulk_copy(mapa_u32(box_addr, (uint32_t)peer), box_addr, kBoxBytes,
                               mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
           }
-          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
+          if (st.out_slot >= 0 && !abl_store) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
           tma_store_commit();  // always one group per box (keeps the wait_group.read 1 accounting exact)
           if (dbg && grp == 0) dbg[8 + 8 * s + (box == 0 ? 6 : 7)] = clock64();
         }
@@ -452,6 +479,8 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
     // measured on B200 (round 1): see DESIGN.md; 1 = no fence around the buffer-free handshake
     const char* e = getenv("ACEZ_CHAIN_RELAXED");
     C->args.flags = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    const char* a = getenv("ACEZ_CHAIN_ABLATE");  // timing ablations (wrong results), see head_chain.cuh
+    if (a != nullptr) C->args.flags |= atoi(a) & 62;
   }
   return ACEZ_OK;
 }

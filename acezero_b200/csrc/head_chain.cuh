@@ -37,6 +37,8 @@ struct ChainArgs {
   int rows;
   int n_steps;
   int flags;       // bit 0: relaxed (instead of release / acquire) cluster-scope signalling of the "A buffer free" barrier
+                   // bits 1..5: TIMING ABLATIONS (results are wrong; ACEZ_CHAIN_ABLATE, tools/probe_chain_time.py):
+                   //   2 no DSMEM exchange, 4 no TMA stores, 8 no weight loads, 16 no epilogue global operands, 32 no box write
   int* nonfinite;  // DGRAD: OR-ed with 1 if a stored gradient is inf / nan (nullable)
   long long* dbg;  // nullable: [gridDim.x][kChainDbgSlots] clock64 stamps (ACEZ_CHAIN_DBG=1, tools/probe_chain_time.py)
   ChainStep step[kChainMaxSteps];

@@ -60,8 +60,13 @@ def show(st, cta, n_steps, title):
 def main():
     print(f"XCHG={os.environ.get('ACEZ_CHAIN_XCHG', 'bulk')}", flush=True)
     bt = {k: v.to(dev) for k, v in ace_ref.synth_batch(5, B).items()}
-    for relaxed in (0, 1):
+    # (relaxed handshake, ablation bits): 2 no DSMEM exchange, 4 no TMA stores, 8 no weight loads, 16 no epilogue global
+    # operands (residual / mask / xtra ...), 32 no box write. Ablated runs compute garbage: timing only.
+    combos = [(0, 0), (1, 0), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (1, 2 | 4), (1, 2 | 4 | 16), (1, 2 | 4 | 16 | 32),
+              (1, 2 | 4 | 8 | 16 | 32)]
+    for relaxed, abl in combos:
         os.environ["ACEZ_CHAIN_RELAXED"] = str(relaxed)
+        os.environ["ACEZ_CHAIN_ABLATE"] = str(abl)
         head = HeadEngine(1, True, (0, 0, 0), max_rows=B, training=True)
         head.load_state(ace_ref.make_head_state(200, 1, True))
         assert head.fused_chain
@@ -78,20 +83,20 @@ def main():
 
         t_f = timeit(fwd)
         t_a = timeit(full)
-        print(f"relaxed={relaxed}: forward chain {t_f:7.1f} us   fwd + tail + bwd {t_a:7.1f} us", flush=True)
         fwd()
         torch.cuda.synchronize()
         st = stamps(lib)
-        tot = st[:, 1] - st[:, 0]
-        print(f"  forward chain, {st.shape[0]} CTAs: cycles per CTA min {tot.min()} median {int(np.median(tot))} max {tot.max()}")
-        show(st, 0, head.L, "fwd")
-        show(st, 1, head.L, "fwd")
+        tot_f = st[:, 1] - st[:, 0]
+        st_f = st.copy()
         full()
         torch.cuda.synchronize()
         st = stamps(lib)   # the last chain launch of `full` is the dgrad chain
-        tot = st[:, 1] - st[:, 0]
-        print(f"  dgrad chain, {st.shape[0]} CTAs: cycles per CTA min {tot.min()} median {int(np.median(tot))} max {tot.max()}")
-        show(st, 0, head.L - 1, "dgrad")
+        tot_d = st[:, 1] - st[:, 0]
+        print(f"relaxed={relaxed} ablate={abl:2d}: forward chain {t_f:7.1f} us  fwd+tail+bwd {t_a:7.1f} us | median CTA cycles "
+              f"fwd {int(np.median(tot_f))} dgrad {int(np.median(tot_d))}", flush=True)
+        if abl == 0 and relaxed == 1 or abl == (2 | 4 | 16):
+            show(st_f, 0, head.L, "fwd")
+            show(st, 0, head.L - 1, "dgrad")
         del head
 
 
