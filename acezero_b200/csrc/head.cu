@@ -10,7 +10,8 @@
 //   XTRA           : [nres][max_rows][512] fp16 post-ReLU output of the last conv of each residual block (ReLU mask)
 //   DZ             : [L][max_rows][512] fp16 gradient w.r.t. the pre-activation of each hidden layer (x grad_scale)
 //   GRES           : [max_rows][512] fp16 running skip-path gradient
-//   RESX           : [max_rows][512] fp16 residual stream of the fused layer chain (head_chain.cu)
+//   MASKB          : [L+1][max_rows][64 B] one bit per channel: ReLU masks written by the fused forward chain and read
+//                    by the fused dgrad chain (head_chain.cu); MASKB[l] belongs to ACT[l]
 #include <stdlib.h>
 
 #include <vector>
@@ -40,7 +41,7 @@ struct acez_head_plan {
   __half* XTRA;
   __half* DZ;
   __half* GRES;
-  __half* RESX;
+  uint8_t* MASKB;
   float* G3;
   float* FC3PART;
   float* BLKPART;
@@ -66,7 +67,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, resx, xtra, dz, gres, g3, fc3part, blkpart, total;
+  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -78,11 +79,11 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
   o.w16 = off; off = align_up(off + (size_t)L * kC * kC * 2, 1024);
   o.w3h = off; off = align_up(off + 4 * kC * 2, 1024);
   o.act = off; off = align_up(off + (size_t)(L + 1) * rows * kC * 2, 1024);
-  o.resx = off; off = align_up(off + rows * kC * 2, 1024);
   if (cfg.training) {
     o.xtra = off; off = align_up(off + (size_t)nres * rows * kC * 2, 1024);
     o.dz = off; off = align_up(off + (size_t)L * rows * kC * 2, 1024);
     o.gres = off; off = align_up(off + rows * kC * 2, 1024);
+    o.maskb = off; off = align_up(off + (size_t)(L + 1) * rows * 64, 1024);
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
     o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
   }
@@ -765,19 +766,16 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
     if (rc) return rc;
     ChainArgs& f = h->chain_fwd.args;
     f.n_steps = L;
+    f.flags |= kChainFlagResInit;
+    const size_t mask_stride = (size_t)h->cfg.max_rows * 64;
     for (int l = 0; l < L; ++l) {
       ChainStep st{};
       st.w_layer = l;
       st.relu = 1;
       st.bias = h->params + (size_t)l * kLayerStride + (size_t)kC * kC;
       st.out_slot = (h->XTRA != nullptr || l == L - 1) ? l + 1 : -1;  // inference plans keep the tiles on chip
-      const bool res_end = (l % 3 == 2) && (l < 3 * h->nres);
-      if (res_end) {
-        const int k = l / 3;
-        st.resid = (k == 0) ? h->ACT : h->RESX;                                          // res_k (ace_network.py:126,133)
-        st.xtra = (h->XTRA != nullptr) ? h->XTRA + (size_t)k * h->act_stride : nullptr;  // ReLU mask for the backward
-        st.res_save = (k + 1 < h->nres) ? h->RESX : nullptr;
-      }
+      st.res_add = ((l % 3 == 2) && (l < 3 * h->nres)) ? 1 : 0;        // res_{k+1} = res_k + x (ace_network.py:126,133)
+      st.mask_out = (h->MASKB != nullptr) ? h->MASKB + (size_t)(l + 1) * mask_stride : nullptr;
       f.step[l] = st;
     }
     if (training) {
@@ -791,14 +789,12 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
         ChainStep st{};
         st.w_layer = l;
         st.out_slot = l - 1;
+        st.mask_in = h->MASKB + (size_t)l * mask_stride;  // (x > 0) of the layer that produced ACT[l]
         const bool is_res = (l % 3 == 0) && (l <= 3 * h->nres);
         if (is_res) {
-          const int k = l / 3;
-          st.mask = h->XTRA + (size_t)(k - 1) * h->act_stride;
-          st.addend = (k < h->nres) ? h->GRES : nullptr;
-          st.out2 = (k >= 2) ? h->GRES : nullptr;
-        } else {
-          st.mask = h->ACT + (size_t)l * h->act_stride;
+          const int k = l / 3;              // ACT[l] = res_k = res_{k-1} + x_{l-1}
+          st.res_add = (k < h->nres) ? 1 : 0;   // + skip gradient from res_{k+1}
+          st.res_save = (k >= 2) ? 1 : 0;       // res_{k-1} needs it (res_0 = features has no gradient)
         }
         b.step[L - 1 - l] = st;
       }
@@ -947,10 +943,10 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->W16 = reinterpret_cast<__half*>(base + lo.w16);
   h->W3h = reinterpret_cast<__half*>(base + lo.w3h);
   h->ACT = reinterpret_cast<__half*>(base + lo.act);
-  h->RESX = reinterpret_cast<__half*>(base + lo.resx);
   h->XTRA = cfg->training ? reinterpret_cast<__half*>(base + lo.xtra) : nullptr;
   h->DZ = cfg->training ? reinterpret_cast<__half*>(base + lo.dz) : nullptr;
   h->GRES = cfg->training ? reinterpret_cast<__half*>(base + lo.gres) : nullptr;
+  h->MASKB = cfg->training ? base + lo.maskb : nullptr;
   h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
   h->FC3PART = cfg->training ? reinterpret_cast<float*>(base + lo.fc3part) : nullptr;
   h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);

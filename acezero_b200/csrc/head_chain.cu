@@ -301,6 +301,28 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     const uint32_t swz = (uint32_t)(r & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t badbits = 0;
+    // Residual stream of the forward pass (res_k, ace_network.py:126,133) / skip-path gradient of the dgrad pass for
+    // THIS thread's row and its two 64-column boxes, as packed half2: it never leaves the registers, so the epilogue
+    // issues no scattered global loads / stores for it (measured: those cost 20 us per pass).
+    uint32_t res[2][32];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+      for (int t = 0; t < 32; ++t) res[sl][t] = 0u;
+    if (!kDgrad && (args.flags & kChainFlagResInit)) {
+      // res_0 = the input tile: this thread's row of its two boxes, from the TMA-loaded A buffer
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = rank * 4 + grp + 2 * sl;
+        chain_wait(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
+        const uint8_t* src = sA + j * kBoxBytes + r * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 t = *reinterpret_cast<const uint4*>(src + ((((uint32_t)q) ^ swz) << 4));
+          res[sl][4 * q] = t.x; res[sl][4 * q + 1] = t.y; res[sl][4 * q + 2] = t.z; res[sl][4 * q + 3] = t.w;
+        }
+      }
+    }
     for (int s = 0; s < n_steps; ++s) {
       const ChainStep& st = args.step[s];
       const int tbuf = s & 1;
@@ -313,93 +335,84 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       tcgen05_fence_after();
       if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
       asm volatile("bar.sync 3, 256;" ::: "memory");
-      const __half* opnd = abl_opnd ? nullptr : (kDgrad ? st.mask : st.resid);
-#pragma unroll 1
-      for (int box = grp; box < CN / 64; box += 2) {
+      const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int box = grp + 2 * sl;
         const int j = rank * 4 + box;
         const int col0 = n_base + box * 64;
-        uint4 opv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) opv[q] = make_uint4(0, 0, 0, 0);
-        if (opnd != nullptr && row_ok) {
-#pragma unroll
-          for (int q = 0; q < 8; q += 2) ldcg_256(opnd + (size_t)row * kC + col0 + q * 8, opv[q], opv[q + 1]);
-        }
+        // ReLU mask of the activation this gradient flows into: one bit per column (written by the forward chain)
+        uint2 mw = make_uint2(0u, 0u);
+        if (kDgrad && row_ok && !abl_opnd) mw = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + j * 8));
         if (issuer) {
           // peer_free phase s: the PEER's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
           // step s-1 (those copies no longer read the boxes rewritten below - also true for the last step, which sends
           // nothing but still overwrites its own boxes) and its A buffer may be overwritten by this step's copies.
-          if (box == grp) {
+          if (sl == 0) {
             if (relaxed_free) chain_wait_cluster_relaxed(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
             else chain_wait_cluster(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
           }
           tma_store_wait_read1();  // the TMA store that last read this box's memory has finished reading
-          if (dbg && grp == 0 && box == 0) dbg[8 + 8 * s + 5] = clock64();
+          if (dbg && grp == 0 && sl == 0) dbg[8 + 8 * s + 5] = clock64();
         }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-        uint32_t v[64];
-        tmem_ld_32x64(t_row + (uint32_t)(tbuf * CN + box * 64), v);
+        uint8_t* dst = sA + j * kBoxBytes + r * 128;
+        const uint32_t dst_peer = mapa_u32(smem_u32(dst), (uint32_t)peer);
+        uint32_t bits_lo = 0u, bits_hi = 0u;  // forward: (x > 0) per column of this row's box
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+        // 32 accumulator columns at a time (register budget: 168 per thread with 3 warps on one SM sub-partition)
+        uint32_t vv[32];
+        tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + box * 64 + hf * 32), vv);
         tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int q = hf * 4 + q4;
+          uint4 o;
+          uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int col = q * 8 + 2 * t;  // column inside the box; packed pair index = col / 2
+            const int vc = col - hf * 32;   // ... inside this 32-column TMEM load
+            uint32_t& rs = res[sl][4 * q + t];
+            if (!kDgrad) {
+              const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&sBias[tbuf * CN + box * 64 + col]));
+              float a = __uint_as_float(vv[vc]) + bf.x;
+              float b = __uint_as_float(vv[vc + 1]) + bf.y;
+              if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              __half2 h = __floats2half2_rn(a, b);
+              const uint32_t m = __hgt2_mask(h, zero2);  // 0xFFFF per half that is > 0
+              const uint32_t two = (m & 1u) | ((m >> 15) & 2u);
+              if (col < 32) bits_lo |= two << col;
+              else bits_hi |= two << (col - 32);
+              if (res_add) {
+                h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);  // residual sum in fp16, as the reference's `res + x`
+                rs = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              ob[t] = *reinterpret_cast<const uint32_t*>(&h);
+            } else {
+              // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+              __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
+              if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+              if (res_save) rs = hb;  // the unmasked sum is the skip-path gradient of the block below
+              badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+              const uint32_t w = (col < 32) ? (mw.x >> col) : (mw.y >> (col - 32));
+              const uint32_t m = ((w & 1u) ? 0x0000FFFFu : 0u) | ((w & 2u) ? 0xFFFF0000u : 0u);
+              ob[t] = hb & m;  // ReLU mask of the saved activation
+            }
+          }
+          if (!abl_box) *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+          if (XCHG_ST && !last) st_cluster_v4(dst_peer + ((((uint32_t)q) ^ swz) << 4), o);
+        }
+        }
         // this TMEM buffer is rewritten by the MMAs of step s+2, which are released (transitively) by the barrier
         // arrivals below: order the completed tcgen05.ld before them
         tcgen05_fence_before();
-        uint8_t* dst = sA + j * kBoxBytes + r * 128;
-        const uint32_t dst_peer = mapa_u32(smem_u32(dst), (uint32_t)peer);
-        const size_t goff = (size_t)row * kC + col0;
-#pragma unroll
-        for (int qp = 0; qp < 8; qp += 2) {
-          uint4 o2[2], x2[2];
-          uint4 ad2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-          if (kDgrad && st.addend != nullptr && row_ok && !abl_opnd) ldcg_256(st.addend + goff + qp * 8, ad2[0], ad2[1]);
-#pragma unroll
-          for (int hq = 0; hq < 2; ++hq) {
-            const int q = qp + hq;
-            const __half2* ph = reinterpret_cast<const __half2*>(&opv[q]);
-            uint4& o = o2[hq];
-            uint4& x = x2[hq];
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-            __half2* xh = reinterpret_cast<__half2*>(&x);
-            if (!kDgrad) {
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int col = q * 8 + 2 * t;
-                const float2 bf = __half22float2(*reinterpret_cast<const __half2*>(&sBias[tbuf * CN + box * 64 + col]));
-                float a = __uint_as_float(v[col]) + bf.x;
-                float b = __uint_as_float(v[col + 1]) + bf.y;
-                if (st.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                const __half2 h = __floats2half2_rn(a, b);
-                xh[t] = h;
-                oh[t] = (st.resid != nullptr) ? __hadd2(ph[t], h) : h;  // residual sum in fp16, as the reference's `res + x`
-              }
-            } else {
-              const __half2* ah = reinterpret_cast<const __half2*>(&ad2[hq]);
-              const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
-              uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int col = q * 8 + 2 * t;
-                // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
-                __half2 h = __floats2half2_rn(__uint_as_float(v[col]), __uint_as_float(v[col + 1]));
-                if (st.addend != nullptr) h = __hadd2(h, ah[t]);
-                xh[t] = h;
-                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
-                ob[t] = hb & __hgt2_mask(ph[t], zero2);                       // ReLU mask from the saved activation
-              }
-            }
-            if (!abl_box) *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
-            if (XCHG_ST && !last) st_cluster_v4(dst_peer + ((((uint32_t)q) ^ swz) << 4), o);
-          }
-          if (row_ok && !abl_opnd) {
-            if (!kDgrad) {
-              if (st.xtra != nullptr) st_256(st.xtra + goff + qp * 8, x2[0], x2[1]);
-              if (st.res_save != nullptr) st_256(st.res_save + goff + qp * 8, o2[0], o2[1]);
-            } else if (st.out2 != nullptr) {
-              st_256(st.out2 + goff + qp * 8, x2[0], x2[1]);
-            }
-          }
-        }
+        if (!kDgrad && st.mask_out != nullptr && row_ok && !abl_opnd)
+          *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
         // the box is complete in shared memory: publish it to the tensor core / copy engines (async proxy)
         if (XCHG_ST) fence_proxy_async_all();
         else fence_proxy_async();
@@ -418,7 +431,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           }
           if (st.out_slot >= 0 && !abl_store) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
           tma_store_commit();  // always one group per box (keeps the wait_group.read 1 accounting exact)
-          if (dbg && grp == 0) dbg[8 + 8 * s + (box == 0 ? 6 : 7)] = clock64();
+          if (dbg && grp == 0) dbg[8 + 8 * s + (sl == 0 ? 6 : 7)] = clock64();
         }
       }
     }
@@ -476,9 +489,10 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
   C->args.nonfinite = nullptr;
   C->args.dbg = nullptr;
   {
-    // measured on B200 (round 1): see DESIGN.md; 1 = no fence around the buffer-free handshake
+    // relaxed (fence-free) buffer-free handshake by default: measured 78.0 vs 80.4 us per forward chain on B200
+    // (round 1); ACEZ_CHAIN_RELAXED=0 selects release / acquire at cluster scope
     const char* e = getenv("ACEZ_CHAIN_RELAXED");
-    C->args.flags = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    C->args.flags = (e == nullptr || atoi(e) != 0) ? 1 : 0;
     const char* a = getenv("ACEZ_CHAIN_ABLATE");  // timing ablations (wrong results), see head_chain.cuh
     if (a != nullptr) C->args.flags |= atoi(a) & 62;
   }

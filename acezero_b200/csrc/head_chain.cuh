@@ -15,20 +15,20 @@
 namespace acez {
 
 enum ChainMode : int { CHAIN_FWD = 0, CHAIN_DGRAD = 1 };
-static constexpr int kChainMaxSteps = 20;  // hidden layers handled by one launch (3 * res blocks + 2 <= 20)
+static constexpr int kChainMaxSteps = 20;      // hidden layers handled by one launch (3 * res blocks + 2 <= 20)
+static constexpr int kChainFlagResInit = 64;   // ChainArgs.flags: FWD has residual layers, res_0 = the input tile
 
-// One GEMM of the chain, in execution order. All row-major [rows, 512] fp16 unless noted.
+// One GEMM of the chain, in execution order.
 struct ChainStep {
-  int w_layer;           // index into W16 [L][512][512]
-  int out_slot;          // z index in the output tensor map the new tile is stored to; < 0: not stored
-  int relu;              // FWD
-  const float* bias;     // FWD: fp32 master bias [512] (rounded to fp16 before the add, autocast semantics)
-  const __half* resid;   // FWD residual-closing layer: tile = resid + x                    (nullable)
-  __half* xtra;          // FWD: pre-residual x, the ReLU mask of the backward              (nullable)
-  __half* res_save;      // FWD: copy of the residual sum for the next block's `resid`      (nullable)
-  const __half* mask;    // DGRAD: post-activation output of the layer whose ReLU is crossed
-  const __half* addend;  // DGRAD: skip-path gradient added before masking                  (nullable)
-  __half* out2;          // DGRAD: unmasked sum (skip-path gradient for the block below)    (nullable)
+  int w_layer;             // index into W16 [L][512][512]
+  int out_slot;            // z index in the output tensor map the new tile is stored to; < 0: not stored
+  int relu;                // FWD
+  int res_add;             // FWD: residual-closing layer, tile = res + x and res = tile (ace_network.py:126,133)
+                           // DGRAD: add the skip-path gradient before masking
+  int res_save;            // DGRAD: keep the unmasked sum as the skip-path gradient for the block below
+  const float* bias;       // FWD: fp32 master bias [512] (rounded to fp16 before the add, autocast semantics)
+  uint8_t* mask_out;       // FWD: [rows][64 B] one bit per channel, (pre-residual x > 0): the ReLU mask of the backward (nullable)
+  const uint8_t* mask_in;  // DGRAD: the bit mask of the activation the gradient flows into
 };
 
 static constexpr int kChainDbgSlots = 8 + 8 * kChainMaxSteps;  // clock64 stamps per CTA (profiling probe)
@@ -37,6 +37,7 @@ struct ChainArgs {
   int rows;
   int n_steps;
   int flags;       // bit 0: relaxed (instead of release / acquire) cluster-scope signalling of the "A buffer free" barrier
+                   // bit 6 (kChainFlagResInit): see above
                    // bits 1..5: TIMING ABLATIONS (results are wrong; ACEZ_CHAIN_ABLATE, tools/probe_chain_time.py):
                    //   2 no DSMEM exchange, 4 no TMA stores, 8 no weight loads, 16 no epilogue global operands, 32 no box write
   int* nonfinite;  // DGRAD: OR-ed with 1 if a stored gradient is inf / nan (nullable)

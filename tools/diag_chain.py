@@ -55,10 +55,10 @@ def main():
         return (v + 1023) // 1024 * 1024
     act_rel = up(L * 512 * 512 * 2) + up(4 * 512 * 2)
     base0, base1 = e0._input_off - act_rel, e1._input_off - act_rel
-    resx_rel = up(act_rel + (L + 1) * n)
-    xtra_rel = up(resx_rel + n)
+    xtra_rel = up(act_rel + (L + 1) * n)
     dz_rel = up(xtra_rel + nres * n)
-    bufs = [("ACT", act_rel, L + 1), ("XTRA", xtra_rel, nres), ("DZ", dz_rel, L)]
+    # (XTRA is only written by the per-layer path: the chain keeps ReLU masks as bit words)
+    bufs = [("ACT", act_rel, L + 1), ("DZ", dz_rel, L)]
     for name, off, cnt in bufs:
         for i in range(cnt):
             a, b = view(ws1, base1 + off, i), view(ws0, base0 + off, i)

@@ -64,6 +64,8 @@ def main():
     # operands (residual / mask / xtra ...), 32 no box write. Ablated runs compute garbage: timing only.
     combos = [(0, 0), (1, 0), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (1, 2 | 4), (1, 2 | 4 | 16), (1, 2 | 4 | 16 | 32),
               (1, 2 | 4 | 8 | 16 | 32)]
+    if os.environ.get("ACEZ_PROBE_COMBOS"):   # e.g. "1:0,1:16"
+        combos = [tuple(int(x) for x in c.split(":")) for c in os.environ["ACEZ_PROBE_COMBOS"].split(",")]
     for relaxed, abl in combos:
         os.environ["ACEZ_CHAIN_RELAXED"] = str(relaxed)
         os.environ["ACEZ_CHAIN_ABLATE"] = str(abl)
