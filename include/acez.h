@@ -151,7 +151,8 @@ int acez_head_sync_weights(acez_head_plan* plan, acez_stream_t stream);
 void* acez_head_input_ptr(acez_head_plan* plan);
 /* 1 if the plan runs all hidden layers of a pass (ace_network.py:120-136 and its autograd transpose) as ONE fused
  * cluster kernel per pass (csrc/head_chain.cu), 0 if it launches one tcgen05 GEMM per layer (csrc/gemm.cu). Both are
- * sm_100a paths with identical semantics; selected at plan creation by the environment variable ACEZ_HEAD_CHAIN. */
+ * sm_100a paths with identical semantics; the fused chain is the default, ACEZ_HEAD_CHAIN=0 at plan creation selects
+ * the per-layer path. */
 int acez_head_plan_fused_chain(const acez_head_plan* plan);
 /* Profiling probe of the fused chain kernel (ACEZ_CHAIN_DBG=1): clock64 stamps of the most recent launch,
  * [n_ctas][8 + 8 * 20] (layout in csrc/head_chain.cu), copied to host memory. */

@@ -14,10 +14,7 @@ import torch
 
 from oracle import ace_ref
 
-# Opt-in until the chain is the default path of the plan: ACEZ_TEST_CHAIN=1 python -m pytest tests/test_head_chain_gpu.py -m gpu
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ACEZ_TEST_CHAIN", "0") != "1" and os.environ.get("ACEZ_HEAD_CHAIN", "0") != "1",
-                                 reason="fused layer chain not enabled (set ACEZ_TEST_CHAIN=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _engine(monkeypatch, chain, nb, homog, rows, training, mean=(0.0, 0.0, 0.0), seed=200):
