@@ -377,6 +377,14 @@ def run_ours(args):
         launches = {"gather": 1, "fwd_gemm": 8, "tail": 1, "fc3_wgrad_partial": 1, "fc3_reduce": 1,
                     "dgrad_gemm": 7, "wgrad_gemm": 1, "adamw": 1}
     clk = clocks.stop() if rank == 0 else None
+    # DRAM traffic of the roofline kernel from the committed `ncu --set full` capture (profiles/), per launch
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        if chain and tj.get("kernel", "").startswith("head_chain_kernel<FWD>"):
+            traffic = int(tj["dram_bytes_per_launch"])   # bytes; algorithmic: 9 tiles x 5.24 MB + 4.19 MB of fp16 weights
+    except Exception:
+        traffic = None
 
     # ---------------- DSAC* ----------------
     n_img = DSAC_BATCH
@@ -468,7 +476,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (1.26 GB patch buffer, fresh random rows gathered every step)"},
         "roofline": {"bound": "tensor", "kernel": roof_kernel,
                      "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["bf16_tflops"], "traffic": None, "us_per_launch": gemm_us,
+                     "frac": achieved_tf / pk["bf16_tflops"], "traffic": traffic, "us_per_launch": gemm_us,
                      "peak_source": pk["source"] + " burst bf16 (kernel timed alone)",
                      "step_frac_of_sustained": FLOP_PER_ITER / (ms_per_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]},
         "cpu_baseline": cpu,
