@@ -148,12 +148,21 @@ __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.
 
 // consumption order of the 8 k-blocks: the CTA's own 4 boxes first (they are ready first), then the peer's
 __device__ __forceinline__ int chunk_order(int i, int rank) { return i < 4 ? rank * 4 + i : (rank ^ 1) * 4 + (i - 4); }
+// V3: by arrival time: own 0,1 | peer 0,1 | own 2,3 | peer 2,3 (a group publishes its second box ~one box time after the
+// first, and the peer's boxes land one DSMEM copy later than the own ones)
+__device__ __forceinline__ int chunk_order_v3(int i, int rank) {
+  const int b = ((i >> 2) << 1) | (i & 1);
+  return ((i & 2) ? (rank ^ 1) : rank) * 4 + b;
+}
 
 // XCHG_ST = false: boxes travel to the peer as bulk DSMEM copies (cp.async.bulk shared::cta -> shared::cluster) that
 //                   complete on the peer's mbarrier (transaction bytes).
 // XCHG_ST = true : fallback: every epilogue thread also stores its 8 x 16 B into the peer's box (st.shared::cluster) and
 //                   one thread arrives on the peer's mbarrier (release at cluster scope). Selected by ACEZ_CHAIN_XCHG=st.
-template <int MODE, bool XCHG_ST>
+// V3 (ACEZ_CHAIN_V3=1, NOT yet validated on hardware - round 2): (a) k-blocks consumed in arrival order, (b) own boxes
+//   published to the local MMA warp in 32-column halves, (c) epilogue instruction diet: fp32 bias slice in shared memory,
+//   ReLU after packing (HMNMX2), mask bits only when a mask is stored, ablation flags compiled out.
+template <int MODE, bool XCHG_ST, bool V3>
 __global__ void __launch_bounds__(kChainThreads, 1)
 head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
@@ -170,6 +179,8 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   uint64_t* tmem_full = b_empty + kBStages;
   uint64_t* peer_free = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peer_free + 1);
+  uint64_t* a_half = reinterpret_cast<uint64_t*>(tmem_ptr + 2);  // V3: first 32 columns of own box b are in place
+  static_assert(!(V3 && XCHG_ST), "V3 supports the bulk-copy exchange only");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -195,6 +206,9 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(peer_free, 1);
+    if (V3) {
+      for (int i = 0; i < 4; ++i) mbar_init(&a_half[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -209,7 +223,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       for (int i = 0; i < kKB; ++i) {
-        const int j = chunk_order(i, rank);
+        const int j = V3 ? chunk_order_v3(i, rank) : chunk_order(i, rank);
         mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
       }
@@ -218,7 +232,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       for (int s = 0; s < n_steps; ++s) {
         const int wl = args.step[s].w_layer;
         for (int i = 0; i < kKB; ++i) {
-          const int j = chunk_order(i, rank);
+          const int j = V3 ? chunk_order_v3(i, rank) : chunk_order(i, rank);
           chain_wait(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           if (abl_w) { mbar_arrive(&b_full[stage]); if (++stage == kBStages) { stage = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&b_full[stage], kBStage);
@@ -245,38 +259,84 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     uint32_t phase = 0;
     for (int s = 0; s < n_steps; ++s) {
       const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
-      for (int i = 0; i < kKB; ++i) {
-        const int j = chunk_order(i, rank);
-        if (abl_xchg && i >= 4 && s > 0) {
-          // ablation: the peer's boxes are never sent
-        } else if (XCHG_ST && i >= 4 && s > 0) {
-          chain_wait_cluster(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);  // peer's generic stores
-          fence_proxy_async_all();
-        } else {
-          chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
-        }
-        if (dbg && lane == 0 && (i == 0 || i == 4 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 4 ? 1 : 2))] = clock64();
-        // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
-        if (!XCHG_ST && !abl_xchg && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
-        chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
-        tcgen05_fence_after();
-        if (elect_one()) {
+      if constexpr (V3) {
+        for (int i = 0; i < kKB; ++i) {
+          const int j = chunk_order_v3(i, rank);
+          const bool is_peer = (i & 2) != 0;
+          const int b = ((i >> 2) << 1) | (i & 1);  // box index inside its owner's half
+          const bool halves = !is_peer && s > 0;     // own boxes written by the epilogue arrive in two 32-column halves
+          if (halves) chain_wait(&a_half[b], (uint32_t)((s - 1) & 1), (6u << 16) | ((uint32_t)s << 8) | (uint32_t)b);
+          else chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+          if (dbg && lane == 0 && (i == 0 || i == 2 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 2 ? 1 : 2))] = clock64();
+          // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
+          if (is_peer && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+          chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
+          tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
           const uint32_t b_addr = smem_u32(sB + stage * kBStage);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CK / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
-            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
-            umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
+              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
+              umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
+          __syncwarp();
+          if (halves) {
+            chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+            tcgen05_fence_after();
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 2; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
+              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
+              umma_f16(d_tmem, da, db, idesc, 1u);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) {
+            tcgen05_commit(&b_empty[stage]);
+            if (i == kKB - 1) tcgen05_commit(&tmem_full[s & 1]);
+          }
+          __syncwarp();
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (elect_one()) {
-          tcgen05_commit(&b_empty[stage]);
-          if (i == kKB - 1) tcgen05_commit(&tmem_full[s & 1]);
+      } else {
+      for (int i = 0; i < kKB; ++i) {
+          const int j = chunk_order(i, rank);
+          if (abl_xchg && i >= 4 && s > 0) {
+            // ablation: the peer's boxes are never sent
+          } else if (XCHG_ST && i >= 4 && s > 0) {
+            chain_wait_cluster(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);  // peer's generic stores
+            fence_proxy_async_all();
+          } else {
+            chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+          }
+          if (dbg && lane == 0 && (i == 0 || i == 4 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 4 ? 1 : 2))] = clock64();
+          // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
+          if (!XCHG_ST && !abl_xchg && i >= 4 && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+          chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
+            const uint32_t b_addr = smem_u32(sB + stage * kBStage);
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
+              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
+              umma_f16(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) {
+            tcgen05_commit(&b_empty[stage]);
+            if (i == kKB - 1) tcgen05_commit(&tmem_full[s & 1]);
+          }
+          __syncwarp();
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kBStages) { stage = 0; phase ^= 1; }
       }
       // All MMAs of step s have retired once tmem_full completes: nothing reads this CTA's A buffer any more, so the
       // peer may copy its boxes of the next tile into it. (Signalled from this warp: it idles here anyway until the
@@ -329,13 +389,119 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const bool last = (s == n_steps - 1);
       if (!kDgrad) {
         // autocast casts the fp32 bias to fp16 before the conv adds it
-        sBias[tbuf * CN + etid] = __float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f);
+        if constexpr (V3) {
+          // single fp32 copy of the rounded slice (no per-element conversion in the box loop): every epilogue warp must
+          // have finished the previous step's boxes before it is overwritten
+          if (s > 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+          reinterpret_cast<float*>(sBias)[etid] =
+              __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
+        } else {
+          sBias[tbuf * CN + etid] = __float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f);
+        }
       }
       chain_wait(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
       tcgen05_fence_after();
       if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
       asm volatile("bar.sync 3, 256;" ::: "memory");
       const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
+      if constexpr (V3) {
+      const bool want_mask = !kDgrad && st.mask_out != nullptr;
+      const float* sBiasF = reinterpret_cast<const float*>(sBias);
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int box = grp + 2 * sl;
+        const int j = rank * 4 + box;
+        const int col0 = n_base + box * 64;
+        uint2 mw = make_uint2(0u, 0u);
+        if (kDgrad && row_ok) mw = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + j * 8));
+        if (issuer) {
+          if (sl == 0) {
+            if (relaxed_free) chain_wait_cluster_relaxed(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+            else chain_wait_cluster(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+          }
+          tma_store_wait_read1();
+          if (dbg && grp == 0 && sl == 0) dbg[8 + 8 * s + 5] = clock64();
+        }
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        uint8_t* dst = sA + j * kBoxBytes + r * 128;
+        uint32_t bits_lo = 0u, bits_hi = 0u;
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t vv[32];
+          tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + box * 64 + hf * 32), vv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int q = hf * 4 + q4;
+            uint4 o;
+            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+            float4 bf0 = make_float4(0.f, 0.f, 0.f, 0.f), bf1 = bf0;
+            if (!kDgrad) {
+              bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
+              bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
+            }
+            const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = q * 8 + 2 * t;
+              const int vc = col - hf * 32;
+              uint32_t& rs = res[sl][4 * q + t];
+              if (!kDgrad) {
+                // single rounding of (acc + bias) to fp16; ReLU on the rounded value gives the same result as before it
+                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]) + bq[2 * t], __uint_as_float(vv[vc + 1]) + bq[2 * t + 1]);
+                if (relu) h = __hmax2(h, zero2);
+                if (want_mask) {
+                  const uint32_t m = __hgt2_mask(h, zero2);
+                  const uint32_t two = (m & 1u) | ((m >> 15) & 2u);
+                  if (col < 32) bits_lo |= two << col;
+                  else bits_hi |= two << (col - 32);
+                }
+                if (res_add) {
+                  h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);
+                  rs = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                ob[t] = *reinterpret_cast<const uint32_t*>(&h);
+              } else {
+                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
+                if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                if (res_save) rs = hb;
+                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;
+                const uint32_t w = (col < 32) ? (mw.x >> col) : (mw.y >> (col - 32));
+                const uint32_t m = ((w & 1u) ? 0x0000FFFFu : 0u) | ((w & 2u) ? 0xFFFF0000u : 0u);
+                ob[t] = hb & m;
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+          }
+          if (hf == 0 && !last) {
+            // first 32 columns of the box (k-steps 0, 1 of the next layer's k-block j) are in place: let the UMMAs start
+            tcgen05_fence_before();
+            fence_proxy_async();
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (issuer) mbar_arrive(&a_half[box]);
+          }
+        }
+        tcgen05_fence_before();
+        if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
+        fence_proxy_async();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer) {
+          const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+          if (!last) {
+            mbar_arrive(&a_ready[j]);
+            dsmem_bulk_copy(mapa_u32(box_addr, (uint32_t)peer), box_addr, kBoxBytes, mapa_u32(smem_u32(&a_ready[j]), (uint32_t)peer));
+          }
+          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
+          tma_store_commit();
+          if (dbg && grp == 0) dbg[8 + 8 * s + (sl == 0 ? 6 : 7)] = clock64();
+        }
+      }
+      } else {
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
         const int box = grp + 2 * sl;
@@ -434,6 +600,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
           if (dbg && grp == 0) dbg[8 + 8 * s + (sl == 0 ? 6 : 7)] = clock64();
         }
       }
+      }
     }
     if (issuer) tma_store_wait_all();
     if (kDgrad && args.nonfinite != nullptr) {
@@ -515,9 +682,9 @@ int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas) {
   return ACEZ_OK;
 }
 
-template <int MODE, bool XCHG_ST>
+template <int MODE, bool XCHG_ST, bool V3>
 static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
-  auto kern = head_chain_kernel<MODE, XCHG_ST>;
+  auto kern = head_chain_kernel<MODE, XCHG_ST, V3>;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
@@ -556,12 +723,20 @@ int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
     const char* e = getenv("ACEZ_CHAIN_XCHG");
     return e != nullptr && e[0] == 's';
   }();
+  static const bool v3 = [] {
+    const char* e = getenv("ACEZ_CHAIN_V3");  // not yet validated on hardware (round 2): see the kernel header
+    return e != nullptr && atoi(e) != 0;
+  }();
   if (xchg_st) {
-    if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, true>(C, stream);
-    return chain_launch_mode<CHAIN_DGRAD, true>(C, stream);
+    if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, true, false>(C, stream);
+    return chain_launch_mode<CHAIN_DGRAD, true, false>(C, stream);
   }
-  if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, false>(C, stream);
-  return chain_launch_mode<CHAIN_DGRAD, false>(C, stream);
+  if (v3) {
+    if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, false, true>(C, stream);
+    return chain_launch_mode<CHAIN_DGRAD, false, true>(C, stream);
+  }
+  if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, false, false>(C, stream);
+  return chain_launch_mode<CHAIN_DGRAD, false, false>(C, stream);
 }
 
 }  // namespace acez

@@ -51,6 +51,8 @@ class CTA:
         self.b_empty = [MBar(f"c{rank}.b_empty{i}") for i in range(BST)]
         self.tmem_full = [MBar(f"c{rank}.tmem_full{i}") for i in range(2)]
         self.peer_free = MBar(f"c{rank}.peer_free")
+        self.a_half = [MBar(f"c{rank}.a_half{b}") for b in range(4)]
+        self.A_h0 = [None] * KB       # V3: tag of the FIRST half (32 columns) of the box
         self.A = [None] * KB          # tag: step whose INPUT k-block j the box currently holds
         self.A_readers = [0] * KB     # in-flight asynchronous readers of the box
         self.A_writers = [0] * KB
@@ -63,8 +65,18 @@ class CTA:
         self.drained = {}             # step -> boxes whose TMEM read has finished
 
 
+V3 = False  # set by main(): arrival-order consumption + own boxes published in two halves (head_chain.cu V3)
+
+
 def order(i, rank):
+    if V3:
+        b = ((i >> 2) << 1) | (i & 1)
+        return ((rank ^ 1) if (i & 2) else rank) * 4 + b
     return rank * 4 + i if i < 4 else (rank ^ 1) * 4 + (i - 4)
+
+
+def is_peer_slot(i):
+    return bool(i & 2) if V3 else i >= 4
 
 
 class Sim:
@@ -99,6 +111,7 @@ class Sim:
             def land(j=j):
                 assert c.A_readers[j] == 0
                 c.A[j] = 0
+                c.A_h0[j] = 0
                 c.A_writers[j] -= 1
                 c.a_ready[j].complete_tx(1)
             self.later(land)
@@ -139,10 +152,21 @@ class Sim:
             tb = s & 1
             for i in range(KB):
                 j = order(i, r)
-                yield from self.wait(c.a_ready[j], s & 1, s)
-                if i >= 4 and s + 1 < self.n:
+                halves = V3 and (not is_peer_slot(i)) and s > 0
+                if halves:
+                    b = j - r * 4
+                    yield from self.wait(c.a_half[b], (s - 1) & 1, s - 1)
+                else:
+                    yield from self.wait(c.a_ready[j], s & 1, s)
+                if is_peer_slot(i) and s + 1 < self.n:
                     c.a_ready[j].arrive_expect_tx(1)
                 yield from self.wait(c.b_full[stage], phase, uses // BST)
+                if halves:
+                    # first two k-steps read the first half only
+                    assert c.A_h0[j] == s, f"c{r} step {s}: first half of box {j} holds input of step {c.A_h0[j]}"
+                    assert c.B[stage] == (s, i)
+                    yield
+                    yield from self.wait(c.a_ready[j], s & 1, s)
                 # issue: checks at issue time
                 assert c.A[j] == s, f"c{r} step {s}: box {j} holds input of step {c.A[j]}"
                 assert c.A_writers[j] == 0, f"c{r} step {s}: box {j} is being written"
@@ -200,7 +224,14 @@ class Sim:
                 # write the own box
                 assert c.A_readers[j] == 0, f"c{r} step {s}: overwriting box {j} with {c.A_readers[j]} readers in flight"
                 assert c.A_writers[j] == 0
+                if V3:
+                    c.A_h0[j] = s + 1
+                    yield
+                    if not last:
+                        c.a_half[box].arrive()
+                    yield
                 c.A[j] = s + 1
+                c.A_h0[j] = s + 1
                 yield
                 if not last:
                     c.a_ready[j].arrive()
@@ -212,6 +243,7 @@ class Sim:
                     def land(j=j, s=s):
                         assert p.A_readers[j] == 0, f"copy landing: peer box {j} has readers"
                         p.A[j] = s + 1
+                        p.A_h0[j] = s + 1
                         p.A_writers[j] -= 1
                         c.A_readers[j] -= 1
                         p.a_ready[j].complete_tx(1)
@@ -252,12 +284,14 @@ class Sim:
 
 
 def main():
+    global V3
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-    for seed in range(runs):
-        for n in {n_steps, 1, 2, 3}:
-            Sim(n, seed).run()
-    print(f"ok: {runs} random schedules x steps {{1,2,3,{n_steps}}}")
+    for V3 in (False, True):
+        for seed in range(runs):
+            for n in {n_steps, 1, 2, 3}:
+                Sim(n, seed).run()
+        print(f"ok ({'V3' if V3 else 'default'} protocol): {runs} random schedules x steps {{1,2,3,{n_steps}}}")
 
 
 if __name__ == "__main__":
