@@ -1,0 +1,286 @@
+// EXPERIMENTAL (round 2; not yet run on hardware, not used by any default path): tcgen05 GEMM with cta_group::2.
+//
+//   D[z][M,N] (fp32) = A[z] * B[z]      fp16 operands, fp32 accumulation in TMEM, operand layouts as in gemm.cuh
+//
+// One thread-block CLUSTER of two CTAs (an SM pair of one TPC) computes one 256 x 256 output tile with
+// tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA; N = 256). CTA r of the pair stages, per 64-wide k-block,
+//   * its own half of A (rows m0 + 128 r ..) : 16 KB - read only by its own tensor core
+//   * ITS HALF OF B (rows n0 + 128 r ..)     : 16 KB - the hardware feeds both tensor cores from both halves
+// i.e. 32 KB per CTA and k-block for 128 x 256 x 64 MACs per CTA: half the shared-memory fill and half the operand reads
+// per MAC of the cta_group::1 kernel with 128 x 128 tiles (round-1 measurement: the batched weight-gradient GEMM and the
+// fused layer chain are bound by the shared-memory port). This file is the probe that validates
+// the 2-CTA primitives in isolation before they go into those kernels:
+//   - tcgen05.alloc / dealloc .cta_group::2 (same warp index in both CTAs, same destination offset)
+//   - cp.async.bulk.tensor .cta_group::2 : both CTAs' loads complete on the LEADER's (rank 0) full barrier (peer bit cleared)
+//   - tcgen05.mma.cta_group::2 issued by the leader's MMA warp only
+//   - tcgen05.commit.cta_group::2 ... multicast::cluster : stage release / accumulator-ready to BOTH CTAs
+// PTX forms follow the vendored CUTLASS headers (cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp,
+// tmem_allocator_sm100.hpp, cutlass/arch/barrier.h).
+#include "gemm.cuh"
+
+namespace acez {
+
+static constexpr int T2_BM = 128;   // rows per CTA (256 per pair)
+static constexpr int T2_BN = 256;   // columns per pair (128 staged per CTA)
+static constexpr int T2_BK = 64;
+static constexpr int T2_STAGES = 6;
+static constexpr int T2_ASTAGE = T2_BM * T2_BK * 2;        // 16 KB
+static constexpr int T2_BSTAGE = (T2_BN / 2) * T2_BK * 2;  // 16 KB (this CTA's half of B)
+static constexpr int T2_STAGE = T2_ASTAGE + T2_BSTAGE;
+static constexpr int T2_THREADS = 320;
+static constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 256 + 1024;
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t t2_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void t2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void t2_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void t2_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load whose completion (bytes) is signalled on the LEADER CTA's barrier of the same offset
+__device__ __forceinline__ void t2_tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// plain arrive on the leader's barrier (executed by the non-leader CTA)
+__device__ __forceinline__ void t2_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void t2_umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior UMMAs retire) on the barrier of this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void t2_commit_both(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+struct Gemm2Args {
+  int M, N, k_blocks;
+  int tiles_n;           // 256-column tiles per row of tiles
+  float* out32;          // [z][M][ldo32]
+  long long out32_zstride;
+  int ldo32;
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(T2_THREADS, 1)
+gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + T2_STAGES * T2_ASTAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
+  uint64_t* empty_bar = full_bar + T2_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + T2_STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)t2_cluster_ctarank();
+  const bool leader = rank == 0;
+  const int tile = blockIdx.x >> 1;
+  const int m0 = (tile / args.tiles_n) * (2 * T2_BM) + rank * T2_BM;  // this CTA's 128 rows
+  const int n0 = (tile % args.tiles_n) * T2_BN;
+  const int nb0 = n0 + rank * (T2_BN / 2);                            // this CTA's half of B
+  const int z = blockIdx.z;
+  const int k_blocks = args.k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader: arrive.expect_tx (all bytes of the pair) + the peer's arrive
+      mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA warp
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) t2_tmem_alloc(tmem_ptr, 256);
+  tcgen05_fence_before();
+  __syncwarp();
+  t2_cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * T2_STAGE);
+        else t2_arrive_leader(&full_bar[stage]);
+        uint8_t* a_dst = sA + stage * T2_ASTAGE;
+        uint8_t* b_dst = sB + stage * T2_BSTAGE;
+        if (A_MN) {
+#pragma unroll
+          for (int i = 0; i < T2_BM / 64; ++i) t2_tma_load_3d(a_dst + i * 8192, &tmA, &full_bar[stage], m0 + 64 * i, kb * T2_BK, z);
+        } else {
+          t2_tma_load_3d(a_dst, &tmA, &full_bar[stage], kb * T2_BK, m0, z);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int i = 0; i < T2_BN / 128; ++i) t2_tma_load_3d(b_dst + i * 8192, &tmB, &full_bar[stage], nb0 + 64 * i, kb * T2_BK, z);
+        } else {
+          t2_tma_load_3d(b_dst, &tmB, &full_bar[stage], kb * T2_BK, nb0, z);
+        }
+        if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
+    constexpr uint32_t idesc = make_idesc_f16(2 * T2_BM, T2_BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(sA + stage * T2_ASTAGE);
+        const uint32_t b_addr = smem_u32(sB + stage * T2_BSTAGE);
+#pragma unroll
+        for (int k = 0; k < T2_BK / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * args.a_kstep, args.a_lbo, args.a_sbo, 2);
+          const uint64_t db = make_smem_desc(b_addr + k * args.b_kstep, args.b_lbo, args.b_sbo, 2);
+          t2_umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        t2_commit_both(&empty_bar[stage]);
+        if (kb == k_blocks - 1) t2_commit_both(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------ epilogue (both CTAs: 128 rows x 256 columns each) ------------------------------
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c = grp; c < T2_BN / 32; c += 2) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+      const int ncol = n0 + c * 32;
+      if (row >= args.M || ncol >= args.N) continue;
+      float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  t2_cluster_sync();  // both tensor cores are done with both CTAs' shared memory and TMEM
+  if (warp == 1) {
+    tcgen05_fence_after();
+    t2_tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int encode2(CUtensorMap* tm, const __half* base, int mn_major, int rows_mn, int K, int ld, int batch, long long zstride,
+                   int tile_mn) {
+  uint64_t dims[3];
+  uint64_t strides[2];
+  uint32_t box[3];
+  if (!mn_major) {
+    dims[0] = (uint64_t)K; dims[1] = (uint64_t)rows_mn; dims[2] = (uint64_t)batch;
+    box[0] = 64; box[1] = (uint32_t)tile_mn; box[2] = 1;
+  } else {
+    dims[0] = (uint64_t)rows_mn; dims[1] = (uint64_t)K; dims[2] = (uint64_t)batch;
+    box[0] = 64; box[1] = 64; box[2] = 1;
+  }
+  strides[0] = (uint64_t)ld * 2;
+  strides[1] = (uint64_t)(batch > 1 ? zstride : (long long)dims[1] * ld) * 2;
+  return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& a, int batch, cudaStream_t stream) {
+  auto kern = gemm2cta_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    configured = true;
+  }
+  const int tiles_m = (a.M + 2 * T2_BM - 1) / (2 * T2_BM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * tiles_m * a.tiles_n, 1, batch);
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = T2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
+  return ACEZ_OK;
+}
+
+}  // namespace acez
+
+// C ABI: experimental entry (same descriptor as acez_gemm_f16; epilogue must be ACEZ_EPI_F32, plain fp32 store)
+extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) {
+  using namespace acez;
+  ACEZ_REQUIRE(d != nullptr, "gemm2cta: null desc");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  ACEZ_REQUIRE(d->epilogue == ACEZ_EPI_F32 && d->out32 != nullptr && d->ldo32 % 4 == 0, "gemm2cta: fp32 output only");
+  ACEZ_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->K % T2_BK == 0 && d->N % 32 == 0, "gemm2cta: bad shape");
+  ACEZ_REQUIRE(d->a_mn_major == d->b_mn_major, "gemm2cta: probe supports K-major x K-major and MN-major x MN-major");
+  const int batch = d->batch > 0 ? d->batch : 1;
+  CUtensorMap tmA, tmB;
+  rc = encode2(&tmA, reinterpret_cast<const __half*>(d->A), d->a_mn_major, d->M, d->K, d->lda, batch, d->a_zstride, T2_BM);
+  if (rc) return rc;
+  rc = encode2(&tmB, reinterpret_cast<const __half*>(d->B), d->b_mn_major, d->N, d->K, d->ldb, batch, d->b_zstride, T2_BN / 2);
+  if (rc) return rc;
+  Gemm2Args a{};
+  a.M = d->M; a.N = d->N; a.k_blocks = d->K / T2_BK;
+  a.tiles_n = (d->N + T2_BN - 1) / T2_BN;
+  a.out32 = d->out32; a.out32_zstride = d->out32_zstride; a.ldo32 = d->ldo32;
+  a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
+  a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;
+  if (d->a_lbo) a.a_lbo = d->a_lbo;
+  if (d->a_sbo) a.a_sbo = d->a_sbo;
+  if (d->a_kstep) a.a_kstep = d->a_kstep;
+  if (d->b_lbo) a.b_lbo = d->b_lbo;
+  if (d->b_sbo) a.b_sbo = d->b_sbo;
+  if (d->b_kstep) a.b_kstep = d->b_kstep;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->a_mn_major) return launch2<true, true>(tmA, tmB, a, batch, s);
+  return launch2<false, false>(tmA, tmB, a, batch, s);
+}

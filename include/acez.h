@@ -80,6 +80,11 @@ typedef struct acez_gemm_desc {
 } acez_gemm_desc;
 
 int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream);
+/* EXPERIMENTAL probe (csrc/gemm2cta.cu; not used by any default path): the same GEMM with tcgen05 cta_group::2 — one cluster of
+ * two CTAs per 256 x 256 tile, the B tile shared between the SM pair. fp32 epilogue (ACEZ_EPI_F32) only; operands both K-major
+ * or both MN-major. Exists to validate the 2-CTA primitives the next versions of the weight-gradient GEMM and of the fused layer
+ * chain are built on. */
+int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused reprojection loss + backward.
