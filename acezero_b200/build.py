@@ -33,7 +33,7 @@ def _stale(target: Path, deps) -> bool:
 def build(verbose: bool = False, force: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
-    headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "acez.h"]
+    headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [HERE.parent / "include" / "acez.h"]
     jobs = []
     for src in sources:
         obj = OBJ / (src.stem + ".o")

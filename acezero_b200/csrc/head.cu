@@ -208,224 +208,13 @@ struct TailArgs {
 static constexpr int kTailThreads = 256;
 
 __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
-  __shared__ float sRed[3][kTailThreads / 32];
-  __shared__ float sGeo[kTailThreads / 32][48];  // per-warp staging of one row's geometry (one load per lane)
-  __shared__ int sLast;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_wait();
-  pdl_launch_dependents();
-  // this lane's slice of the fc3 weights: 4 rows x 16 columns, packed fp16
-  __half2 w[4][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4* wp = reinterpret_cast<const uint4*>(a.W3h + j * kC + lane * 16);
-    uint4 t0 = wp[0], t1 = wp[1];
-    const __half2* h0 = reinterpret_cast<const __half2*>(&t0);
-    const __half2* h1 = reinterpret_cast<const __half2*>(&t1);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { w[j][k] = h0[k]; w[j][4 + k] = h1[k]; }
-  }
-  float b3[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) b3[j] = (j < a.C3) ? __half2float(__float2half_rn(a.b3[j])) : 0.f;
-
-  acez_loss_params lp = a.lp;
-  if (a.training && a.grad_scale_dev != nullptr) lp.grad_scale = *a.grad_scale_dev;
-  if (a.training && a.loss_weight_dev != nullptr) lp.loss_weight = *a.loss_weight_dev;
-
-  float loss_sum = 0.f, inl_sum = 0.f, valid_sum = 0.f;
-  bool bad = false, bad_g = false;
-
-  const int warps_total = gridDim.x * (kTailThreads / 32);
-  // software pipeline: the next row's activations and geometry are in flight while the current row is processed
-  uint4 xn[2];
-  float gvn = 0.f, gv2n = 0.f;
-  auto prefetch = [&](int rr) {
-    if (rr >= a.rows) return;
-    const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)rr * kC + lane * 16);
-    xn[0] = xp[0]; xn[1] = xp[1];
-    if (a.training == 1) {
-      gvn = 0.f; gv2n = 0.f;
-      if (a.Pin != nullptr) {
-        if (lane < 12) gvn = a.Pin[12 * (size_t)rr + lane];
-      } else if (lane < 12) gvn = a.A[12 * (size_t)rr + lane];
-      else if (lane < 28) gvn = a.T[16 * (size_t)rr + (lane - 12)];
-      // second wave: K (9), Kinv (9), target px (2) -> 20 values on lanes 0..19
-      if (lane < 9) gv2n = a.K[9 * (size_t)rr + lane];
-      else if (lane < 18) gv2n = a.Kinv[9 * (size_t)rr + (lane - 9)];
-      else if (lane < 20) gv2n = a.tpx[2 * (size_t)rr + (lane - 18)];
-    }
-  };
-  prefetch(blockIdx.x * (kTailThreads / 32) + warp);
-  for (int row = blockIdx.x * (kTailThreads / 32) + warp; row < a.rows; row += warps_total) {
-    uint4 xr[2] = {xn[0], xn[1]};
-    const float gv = gvn, gv2 = gv2n;
-    prefetch(row + warps_total);
-    const __half2* xh = reinterpret_cast<const __half2*>(xr);
-    float2 xf[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) xf[k] = __half22float2(xh[k]);
-    // ---- fc3: 4 dot products (fp32 accumulate, fp16 output as the autocast conv produces) ----
-    float s[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float d = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float2 wf = __half22float2(w[j][k]);
-        d = fmaf(xf[k].x, wf.x, d);
-        d = fmaf(xf[k].y, wf.y, d);
-      }
-      d = warp_sum(d);
-      s[j] = __half2float(__float2half_rn(d + b3[j]));
-    }
-    // ---- homogeneous -> 3-D (ace_network.py:139-147), fp32 ----
-    float X[3], h = 1.f, sig = 0.f;
-    bool h_pass = true;
-    if (a.use_homogeneous) {
-      const float bx = a.h_beta * s[3];
-      float sp;
-      if (bx > 20.f) { sp = s[3]; sig = 1.f; }               // torch softplus threshold
-      else { sp = log1pf(expf(bx)) / a.h_beta; sig = 1.f / (1.f + expf(-bx)); }
-      h = sp + a.max_inv_scale;
-      h_pass = h <= a.min_inv_scale;                          // clamp_(max=) backward mask
-      h = fminf(h, a.min_inv_scale);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) X[i] = s[i] / h + a.mean[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) X[i] = s[i] + a.mean[i];
-    }
-    if (a.sc_out != nullptr && lane < 3) a.sc_out[(size_t)row * 3 + lane] = X[lane];
-    if (!a.training) continue;
-
-    RowLoss o;
-    if (a.training == 2) {
-      // external gradient (torch.autograd through the Regressor module): skip the loss, take dL/dX from the caller
-#pragma unroll
-      for (int i = 0; i < 3; ++i) o.gX[i] = a.d_sc_in[3 * (size_t)row + i];
-      o.loss = 0.f; o.valid = true; o.inlier = false; o.gK00 = o.gK11 = 0.f;
-      o.gc[0] = o.gc[1] = o.gc[2] = 0.f;
-    } else {
-    // ---- reprojection loss + backward (all lanes redundantly). The row's geometry (46 + 2 floats from 5 arrays) is
-    // fetched with ONE load per lane, issued before the fc3 dot products above complete, and broadcast through smem.
-    float P[12];
-    float Kr[9], Ki[9];
-    {
-      __syncwarp();
-      if (lane < 28) sGeo[warp][lane] = gv;
-      if (lane < 20) sGeo[warp][28 + lane] = gv2;
-      __syncwarp();
-      if (a.Pin != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 12; ++k) P[k] = sGeo[warp][k];
-      } else {
-        float A[12], T[16];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) A[k] = sGeo[warp][k];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) T[k] = sGeo[warp][12 + k];
-        compose_pose(A, T, P);
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) { Kr[k] = sGeo[warp][28 + k]; Ki[k] = sGeo[warp][37 + k]; }
-    }
-    const float tpx0 = sGeo[warp][46], tpx1 = sGeo[warp][47];
-    repro_row(lp, X, P, Kr, Ki, tpx0, tpx1,
-              (lp.use_depth && a.G) ? a.G + 3 * (size_t)row : nullptr, o);
-    }
-    if (lane == 0 && a.training == 1) {
-      loss_sum += o.loss / (float)lp.divisor;
-      inl_sum += o.inlier ? 1.f : 0.f;
-      valid_sum += o.valid ? 1.f : 0.f;
-      bad |= !isfinite(o.loss);
-      if (a.d_Kdiag != nullptr) { a.d_Kdiag[2 * (size_t)row] = o.gK00; a.d_Kdiag[2 * (size_t)row + 1] = o.gK11; }
-    }
-    if (a.training == 1 && a.d_P != nullptr && lane < 12) {
-      const int r = lane >> 2, c = lane & 3;
-      a.d_P[12 * (size_t)row + lane] = o.gc[r] * (c < 3 ? X[c] : 1.f);
-    }
-    // ---- back through the de-homogenisation to the 4 fc3 outputs; rounded to fp16 like autograd's cast ----
-    float g[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.use_homogeneous) {
-      const float ih = 1.f / h;
-      float gh = 0.f;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { g[i] = o.gX[i] * ih; gh -= o.gX[i] * s[i] * ih * ih; }
-      g[3] = h_pass ? gh * sig : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) g[i] = o.gX[i];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      g[j] = __half2float(__float2half_rn(g[j]));
-      bad_g |= !isfinite(g[j]);
-    }
-    if (lane == 0) *reinterpret_cast<float4*>(a.g3 + 4 * (size_t)row) = make_float4(g[0], g[1], g[2], g[3]);
-    // ---- dX8 = g W3 (fp16 result), masked by the ReLU of x8 -> DZ[L-1] ----
-    uint4 outv[2];
-    __half2* oh = reinterpret_cast<__half2*>(outv);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 wf = __half22float2(w[j][k]);
-        d0 = fmaf(g[j], wf.x, d0);
-        d1 = fmaf(g[j], wf.y, d1);
-      }
-      __half2 hv = __floats2half2_rn(d0, d1);
-      const float2 hf = __half22float2(hv);
-      bad_g |= !(isfinite(hf.x) && isfinite(hf.y));
-      if (!(xf[k].x > 0.f)) hv.x = __float2half_rn(0.f);
-      if (!(xf[k].y > 0.f)) hv.y = __float2half_rn(0.f);
-      oh[k] = hv;
-    }
-    uint4* dzp = reinterpret_cast<uint4*>(a.dz + (size_t)row * kC + lane * 16);
-    dzp[0] = outv[0];
-    dzp[1] = outv[1];
-  }
-  if (!a.training) return;
-
-  if (lane == 0) { sRed[0][warp] = loss_sum; sRed[1][warp] = inl_sum; sRed[2][warp] = valid_sum; }
-  const int any_bad = __syncthreads_or(bad ? 1 : 0);
-  const int any_bad_g = __syncthreads_or(bad_g ? 1 : 0);
-  // per-block partials, then the last block to finish writes the totals (no pre-zeroing, deterministic order)
-  if (tid == 0) {
-    float l = 0.f, n = 0.f, v = 0.f;
-    for (int k = 0; k < kTailThreads / 32; ++k) { l += sRed[0][k]; n += sRed[1][k]; v += sRed[2][k]; }
-    float* p = a.blk_part + 8 * (size_t)blockIdx.x;
-    p[0] = l; p[1] = n; p[2] = v; p[3] = any_bad ? 1.f : 0.f; p[4] = any_bad_g ? 1.f : 0.f;
-    __threadfence();
-    const unsigned int done = atomicAdd(a.blk_count, 1u);
-    sLast = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (sLast) {
-    __threadfence();
-    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int b = tid; b < (int)gridDim.x; b += kTailThreads) {
-      const volatile float* p = a.blk_part + 8 * (size_t)b;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) acc[k] += p[k];
-    }
-    __shared__ float sTot[5][kTailThreads / 32];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const float w = warp_sum(acc[k]);
-      if (lane == 0) sTot[k][warp] = w;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int k = 0; k < 5; ++k)
-        for (int w = 0; w < kTailThreads / 32; ++w) t[k] += sTot[k][w];
-      if (a.stats != nullptr) { a.stats[0] = t[0]; a.stats[1] = t[1]; a.stats[2] = t[2]; a.stats[3] = t[3] > 0.f ? 1.f : 0.f; }
-      if (a.nonfinite != nullptr) *a.nonfinite = t[4] > 0.f ? 1 : 0;
-      *a.blk_count = 0u;  // ready for the next launch
-    }
-  }
+#include "head_tail_body.inc"
+}
+// ACEZ_TAIL_OCC2=1 (experimental, round 2): the same body capped at 128 registers (184 otherwise; a few hundred bytes of
+// spills) so that two CTAs = 16 warps fit per SM and the whole grid is resident in one wave (round-1 profile: 12.7 % of the
+// warp slots active, two waves of 148 CTAs).
+__global__ void __launch_bounds__(kTailThreads, 2) head_tail_kernel_occ2(const TailArgs a) {
+#include "head_tail_body.inc"
 }
 
 // dW3[j][c] = sum_rows G3[row][j] * x8[row][c], db3[j] = sum_rows G3[row][j].
@@ -842,7 +631,12 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
   }
   t.blk_part = h->BLKPART;
   t.blk_count = h->BLKCOUNT;
-  int rc = launch_pdl(head_tail_kernel, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t);
+  static const bool occ2 = [] {
+    const char* e = getenv("ACEZ_TAIL_OCC2");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  int rc = occ2 ? launch_pdl(head_tail_kernel_occ2, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t)
+                : launch_pdl(head_tail_kernel, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t);
   if (rc) return rc;
   if (with_fc3_grad) {
     const int nblk = (rows + kFc3Rows - 1) / kFc3Rows;

@@ -148,6 +148,8 @@ class TrainLoop:
         self.use_graph = use_graph and not self.refining
         self._graph = None
         self._warm = 0
+        import os
+        self._dp_one_graph = world_size > 1 and os.environ.get("ACEZ_DP_ONE_GRAPH", "0") == "1"
         self._graph_host = None
         self._warm_host = 0
         self.set_buffer(buffer)
@@ -488,7 +490,10 @@ class TrainLoop:
                 self._warm += 1
                 self._enqueue_compute()
                 return
-            if self.world == 1:
+            if self.world == 1 or self._dp_one_graph:
+                # (data parallel + ACEZ_DP_ONE_GRAPH=1: the NCCL all-reduce is captured inside the graph as well —
+                # experimental, to be measured at N >= 2; the communicator exists by now: the eager warm-up
+                # iterations above have run an all-reduce)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue_compute()
@@ -501,7 +506,7 @@ class TrainLoop:
                 with torch.cuda.graph(gb):
                     self._enqueue_compute(part="optimizer")
                 self._graph = (ga, gb)
-        if self.world == 1:
+        if len(self._graph) == 1:
             self._graph[0].replay()
         else:
             self._graph[0].replay()
