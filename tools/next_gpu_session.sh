@@ -1,0 +1,51 @@
+#!/bin/bash
+# First GPU call of the next session: validates every opt-in experiment written without GPU time at the end of round 1.
+#   gpurun --timeout 900 -- 'bash tools/next_gpu_session.sh'          (about 5-6 minutes of run time, one GPU)
+# Everything lands in gpurun_out/next_*.{log,txt}; the summary is printed at the end. Ordered by value.
+set +e
+mkdir -p gpurun_out
+S=gpurun_out/next_summary.txt
+: > $S
+t0=$(date +%s)
+stamp() { echo "[$(( $(date +%s) - t0 )) s] $*" >> $S; }
+
+# 0. baseline of the box: default path (fused chain v2), tests + step breakdown
+timeout 200 python -m pytest tests -m gpu -x -q > gpurun_out/next_suite_default.log 2>&1
+stamp "GPU suite, default path rc=$?"; tail -n 2 gpurun_out/next_suite_default.log >> $S
+timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_default.log 2>&1
+stamp "breakdown default rc=$?"; cat gpurun_out/next_breakdown_default.log >> $S
+
+# 1. chain V3 (arrival-order k-blocks, half-box publication, epilogue diet): parity, then timing + timeline
+ACEZ_CHAIN_V3=1 timeout 200 python -m pytest tests/test_head_chain_gpu.py tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_v3_tests.log 2>&1
+rc_v3=$?
+stamp "chain V3 tests rc=$rc_v3"; tail -n 6 gpurun_out/next_v3_tests.log >> $S
+if [ $rc_v3 -ne 0 ]; then
+  ACEZ_CHAIN_V3=1 timeout 100 python tools/diag_chain.py 384 > gpurun_out/next_v3_diag.log 2>&1
+  stamp "chain V3 diag rc=$?"; tail -n 24 gpurun_out/next_v3_diag.log >> $S
+fi
+ACEZ_CHAIN_V3=1 ACEZ_PROBE_COMBOS="1:0" timeout 100 python tools/probe_chain_time.py > gpurun_out/next_v3_probe.log 2>&1
+stamp "chain V3 probe rc=$?"; cat gpurun_out/next_v3_probe.log >> $S
+ACEZ_PROBE_COMBOS="1:0" timeout 100 python tools/probe_chain_time.py > gpurun_out/next_v2_probe.log 2>&1
+stamp "chain v2 probe (same box) rc=$?"; head -n 3 gpurun_out/next_v2_probe.log >> $S
+
+# 2. cta_group::2 probe GEMM (correctness cases, then timing on the weight-gradient shape)
+timeout 120 python tools/probe_gemm2cta.py > gpurun_out/next_gemm2cta.log 2>&1
+stamp "gemm2cta probe rc=$?"; cat gpurun_out/next_gemm2cta.log >> $S
+
+# 3. tail kernel at 2 CTAs / SM
+ACEZ_TAIL_OCC2=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_occ2_tests.log 2>&1
+stamp "tail occ2 tests rc=$?"; tail -n 2 gpurun_out/next_occ2_tests.log >> $S
+ACEZ_TAIL_OCC2=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_occ2.log 2>&1
+stamp "breakdown tail occ2 rc=$?"; cat gpurun_out/next_breakdown_occ2.log >> $S
+
+# 4. everything that passed, together: bench line
+if [ $rc_v3 -eq 0 ]; then
+  ACEZ_CHAIN_V3=1 ACEZ_TAIL_OCC2=1 timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_v3_occ2.json 2> gpurun_out/next_bench_v3_occ2.err
+  stamp "bench V3 + occ2 rc=$?"; cut -c1-400 gpurun_out/next_bench_v3_occ2.json >> $S
+fi
+timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_default.json 2> gpurun_out/next_bench_default.err
+stamp "bench default rc=$?"; cut -c1-400 gpurun_out/next_bench_default.json >> $S
+stamp done
+cat $S
+# Data parallel (costs 2x): gpurun --gpus 2 --timeout 600 -- 'for g in 0 1; do ACEZ_DP_ONE_GRAPH=$g python -m torch.distributed.run --nnodes=1 \
+#   --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 --warmup 5 > gpurun_out/next_dp2_onegraph$g.json; done'
