@@ -38,6 +38,10 @@ stamp "tail occ2 tests rc=$?"; tail -n 2 gpurun_out/next_occ2_tests.log >> $S
 ACEZ_TAIL_OCC2=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_occ2.log 2>&1
 stamp "breakdown tail occ2 rc=$?"; cat gpurun_out/next_breakdown_occ2.log >> $S
 
+# 3b. stress cases of configs[4] (hypothesis sweep to 4096, 4096 images per call, 1 M-row buffer epochs)
+ACEZ_TEST_EXTRA=1 timeout 300 python -m pytest tests/test_stress_gpu.py -m gpu -q > gpurun_out/next_stress.log 2>&1
+stamp "stress tests rc=$?"; tail -n 4 gpurun_out/next_stress.log >> $S
+
 # 4. everything that passed, together: bench line
 if [ $rc_v3 -eq 0 ]; then
   ACEZ_CHAIN_V3=1 ACEZ_TAIL_OCC2=1 timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_v3_occ2.json 2> gpurun_out/next_bench_v3_occ2.err
