@@ -21,14 +21,17 @@
 namespace acez {
 
 static constexpr int T2_BM = 128;   // rows per CTA (256 per pair)
-static constexpr int T2_BN = 256;   // columns per pair (128 staged per CTA)
 static constexpr int T2_BK = 64;
 static constexpr int T2_STAGES = 6;
 static constexpr int T2_ASTAGE = T2_BM * T2_BK * 2;        // 16 KB
-static constexpr int T2_BSTAGE = (T2_BN / 2) * T2_BK * 2;  // 16 KB (this CTA's half of B)
-static constexpr int T2_STAGE = T2_ASTAGE + T2_BSTAGE;
 static constexpr int T2_THREADS = 320;
-static constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 256 + 1024;
+// BN = columns per pair (256 or 128); each CTA stages BN / 2 rows of B per k-block
+template <int BN>
+struct T2Cfg {
+  static constexpr int kBStage = (BN / 2) * T2_BK * 2;  // 16 KB / 8 KB (this CTA's half of B)
+  static constexpr int kStage = T2_ASTAGE + kBStage;
+  static constexpr int kSmem = T2_STAGES * kStage + 256 + 1024;
+};
 static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
 
 __device__ __forceinline__ uint32_t t2_cluster_ctarank() {
@@ -86,11 +89,13 @@ struct Gemm2Args {
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int T2_BN>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int T2_BSTAGE = T2Cfg<T2_BN>::kBStage;
+  constexpr int T2_STAGE = T2Cfg<T2_BN>::kStage;
   uint8_t* sA = smem;
   uint8_t* sB = smem + T2_STAGES * T2_ASTAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
@@ -226,9 +231,10 @@ static int encode2(CUtensorMap* tm, const __half* base, int mn_major, int rows_m
   return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& a, int batch, cudaStream_t stream) {
-  auto kern = gemm2cta_kernel<A_MN, B_MN>;
+  auto kern = gemm2cta_kernel<A_MN, B_MN, BN>;
+  constexpr int T2_SMEM = T2Cfg<BN>::kSmem;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
@@ -266,11 +272,12 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   CUtensorMap tmA, tmB;
   rc = encode2(&tmA, reinterpret_cast<const __half*>(d->A), d->a_mn_major, d->M, d->K, d->lda, batch, d->a_zstride, T2_BM);
   if (rc) return rc;
-  rc = encode2(&tmB, reinterpret_cast<const __half*>(d->B), d->b_mn_major, d->N, d->K, d->ldb, batch, d->b_zstride, T2_BN / 2);
+  const int bn = (d->bn == 128) ? 128 : 256;  // columns per pair
+  rc = encode2(&tmB, reinterpret_cast<const __half*>(d->B), d->b_mn_major, d->N, d->K, d->ldb, batch, d->b_zstride, bn / 2);
   if (rc) return rc;
   Gemm2Args a{};
   a.M = d->M; a.N = d->N; a.k_blocks = d->K / T2_BK;
-  a.tiles_n = (d->N + T2_BN - 1) / T2_BN;
+  a.tiles_n = (d->N + bn - 1) / bn;
   a.out32 = d->out32; a.out32_zstride = d->out32_zstride; a.ldo32 = d->ldo32;
   a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
   a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;
@@ -281,6 +288,10 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   if (d->b_sbo) a.b_sbo = d->b_sbo;
   if (d->b_kstep) a.b_kstep = d->b_kstep;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (d->a_mn_major) return launch2<true, true>(tmA, tmB, a, batch, s);
-  return launch2<false, false>(tmA, tmB, a, batch, s);
+  if (bn == 128) {
+    if (d->a_mn_major) return launch2<true, true, 128>(tmA, tmB, a, batch, s);
+    return launch2<false, false, 128>(tmA, tmB, a, batch, s);
+  }
+  if (d->a_mn_major) return launch2<true, true, 256>(tmA, tmB, a, batch, s);
+  return launch2<false, false, 256>(tmA, tmB, a, batch, s);
 }

@@ -31,7 +31,7 @@ def run(fn_name, A, B, mn, M, N, K, batch=1, bn=128):
     return out, d
 
 
-def case(name, mn, M, N, K, batch=1):
+def case(name, mn, M, N, K, batch=1, bn=0):
     g = torch.Generator(device="cuda").manual_seed(1)
     shpA = (K, M) if mn else (M, K)
     shpB = (K, N) if mn else (N, K)
@@ -40,7 +40,7 @@ def case(name, mn, M, N, K, batch=1):
     A = (torch.randn(shpA, device="cuda", generator=g) * 0.5).half()
     B = (torch.randn(shpB, device="cuda", generator=g) * 0.5).half()
     try:
-        out, _ = run("acez_gemm2cta_f16", A, B, mn, M, N, K, batch)
+        out, _ = run("acez_gemm2cta_f16", A, B, mn, M, N, K, batch, bn)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         print(f"{name}: ERROR {e}", flush=True)
@@ -64,7 +64,8 @@ def timing():
     g = torch.Generator(device="cuda").manual_seed(2)
     A = (torch.randn((L, rows, C5), device="cuda", generator=g) * 0.1).half()   # DZ  [K=rows][M]
     B = (torch.randn((L, rows, C5), device="cuda", generator=g) * 0.1).half()   # ACT [K=rows][N]
-    for name, fn, bn in (("cta_group::1 128x128", "acez_gemm_f16", 128), ("cta_group::2 256x256 per pair", "acez_gemm2cta_f16", 0)):
+    for name, fn, bn in (("cta_group::1 128x128", "acez_gemm_f16", 128), ("cta_group::2 256x256 per pair (64 CTAs)", "acez_gemm2cta_f16", 0),
+                         ("cta_group::2 256x128 per pair (128 CTAs)", "acez_gemm2cta_f16", 128)):
         for _ in range(3):
             run(fn, A, B, 1, C5, C5, rows, L, bn)
         torch.cuda.synchronize()
@@ -88,6 +89,8 @@ def main():
     ok &= case("MN/MN 256x256x64", 1, 256, 256, 64)
     ok &= case("MN/MN 512x512x5120", 1, 512, 512, 5120)
     ok &= case("MN/MN batched x8 K=640", 1, 512, 512, 640, batch=8)
+    ok &= case("K/K   512x512x512  256x128 tiles", 0, 512, 512, 512, bn=128)
+    ok &= case("MN/MN batched x8 K=640, 256x128 tiles", 1, 512, 512, 640, batch=8, bn=128)
     print("RESULT", "PASS" if ok else "FAIL", flush=True)
     if ok:
         timing()
