@@ -16,7 +16,7 @@
 //   - tcgen05.commit.cta_group::2 ... multicast::cluster : stage release / accumulator-ready to BOTH CTAs
 // PTX forms follow the vendored CUTLASS headers (cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp,
 // tmem_allocator_sm100.hpp, cutlass/arch/barrier.h).
-#include "gemm.cuh"
+#include "gemm2cta.cuh"
 
 namespace acez {
 
@@ -30,7 +30,7 @@ template <int BN>
 struct T2Cfg {
   static constexpr int kBStage = (BN / 2) * T2_BK * 2;  // 16 KB / 8 KB (this CTA's half of B)
   static constexpr int kStage = T2_ASTAGE + kBStage;
-  static constexpr int kSmem = T2_STAGES * kStage + 256 + 1024;
+  static constexpr int kSmem = T2_STAGES * kStage + 1024 /*ones tile*/ + 256 + 1024;
 };
 static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the even CTA of the pair
 
@@ -80,15 +80,6 @@ __device__ __forceinline__ void t2_commit_both(uint64_t* bar) {
                : "memory");
 }
 
-struct Gemm2Args {
-  int M, N, k_blocks;
-  int tiles_n;           // 256-column tiles per row of tiles
-  float* out32;          // [z][M][ldo32]
-  long long out32_zstride;
-  int ldo32;
-  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
-};
-
 template <bool A_MN, bool B_MN, int T2_BN>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
@@ -98,7 +89,8 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int T2_STAGE = T2Cfg<T2_BN>::kStage;
   uint8_t* sA = smem;
   uint8_t* sB = smem + T2_STAGES * T2_ASTAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE);
+  uint8_t* sOnes = smem + T2_STAGES * T2_STAGE;  // 8 rows x 64 halves of 1.0: this CTA's half of the N = 16 bias-gradient operand
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOnes + 1024);
   uint64_t* empty_bar = full_bar + T2_STAGES;
   uint64_t* tmem_full_bar = empty_bar + T2_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -123,7 +115,14 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) t2_tmem_alloc(tmem_ptr, 256);
+  constexpr uint32_t kTmemCols = (T2_BN + 32 <= 256) ? 256u : 512u;  // accumulator + the bias-gradient column block
+  if (warp == 1) t2_tmem_alloc(tmem_ptr, kTmemCols);
+  const bool bias_col = args.bias_grad != nullptr && n0 == 0;  // dZ^T 1: one extra N = 16 UMMA per k-step (TMEM columns BN..BN+15)
+  if (bias_col && warp >= 2) {
+    __half2* o = reinterpret_cast<__half2*>(sOnes);
+    for (int i = threadIdx.x - 64; i < 1024 / 4; i += 256) o[i] = __floats2half2_rn(1.f, 1.f);
+    fence_proxy_async();
+  }
   tcgen05_fence_before();
   __syncwarp();
   t2_cluster_sync();
@@ -159,6 +158,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1 && leader) {
     // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
     constexpr uint32_t idesc = make_idesc_f16(2 * T2_BM, T2_BN, A_MN, B_MN);
+    constexpr uint32_t idesc_ones = make_idesc_f16(2 * T2_BM, 16, A_MN, false);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
@@ -172,6 +172,10 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t da = make_smem_desc(a_addr + k * args.a_kstep, args.a_lbo, args.a_sbo, 2);
           const uint64_t db = make_smem_desc(b_addr + k * args.b_kstep, args.b_lbo, args.b_sbo, 2);
           t2_umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (bias_col) {
+            const uint64_t d1 = make_smem_desc(smem_u32(sOnes) + k * 32, 0, 1024, 2);
+            t2_umma_f16(tmem_base + T2_BN, da, d1, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+          }
         }
       }
       __syncwarp();
@@ -190,6 +194,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    bool bad = false;
 #pragma unroll 1
     for (int c = grp; c < T2_BN / 32; c += 2) {
       uint32_t v[32];
@@ -202,6 +207,27 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int j = 0; j < 8; ++j)
         dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                              __uint_as_float(v[4 * j + 3]));
+      if (args.nonfinite != nullptr) {
+        // GradScaler check folded in: autocast materialises weight gradients in fp16, so |g| > 65504 is an overflow
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = __uint_as_float(v[j]);
+          bad |= !isfinite(g) || fabsf(g) > 65504.f;
+        }
+      }
+    }
+    if (bias_col && grp == 0) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + T2_BN, v);  // columns BN..BN+15 hold the row sum (all equal); 32 columns are allocated
+      tmem_ld_wait();
+      if (row < args.M) {
+        const float g = __uint_as_float(v[0]);
+        args.bias_grad[(long long)z * args.bias_grad_zstride + row] = g;
+        bad |= !isfinite(g) || fabsf(g) > 65504.f;
+      }
+    }
+    if (args.nonfinite != nullptr) {
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
   }
 
@@ -210,7 +236,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   t2_cluster_sync();  // both tensor cores are done with both CTAs' shared memory and TMEM
   if (warp == 1) {
     tcgen05_fence_after();
-    t2_tmem_dealloc(tmem_base, 256);
+    t2_tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -257,6 +283,17 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Ar
   return ACEZ_OK;
 }
 
+int gemm2_launch(const Gemm2Launch& L, cudaStream_t s) {
+  ACEZ_REQUIRE(L.a_mn == L.b_mn, "gemm2cta: operands must both be K-major or both MN-major");
+  ACEZ_REQUIRE(L.bn == 128 || L.bn == 256, "gemm2cta: bn must be 128 or 256");
+  if (L.bn == 128) {
+    if (L.a_mn) return launch2<true, true, 128>(L.tmA, L.tmB, L.args, L.batch, s);
+    return launch2<false, false, 128>(L.tmA, L.tmB, L.args, L.batch, s);
+  }
+  if (L.a_mn) return launch2<true, true, 256>(L.tmA, L.tmB, L.args, L.batch, s);
+  return launch2<false, false, 256>(L.tmA, L.tmB, L.args, L.batch, s);
+}
+
 }  // namespace acez
 
 // C ABI: experimental entry (same descriptor as acez_gemm_f16; epilogue must be ACEZ_EPI_F32, plain fp32 store)
@@ -268,17 +305,20 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   ACEZ_REQUIRE(d->epilogue == ACEZ_EPI_F32 && d->out32 != nullptr && d->ldo32 % 4 == 0, "gemm2cta: fp32 output only");
   ACEZ_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->K % T2_BK == 0 && d->N % 32 == 0, "gemm2cta: bad shape");
   ACEZ_REQUIRE(d->a_mn_major == d->b_mn_major, "gemm2cta: probe supports K-major x K-major and MN-major x MN-major");
-  const int batch = d->batch > 0 ? d->batch : 1;
-  CUtensorMap tmA, tmB;
-  rc = encode2(&tmA, reinterpret_cast<const __half*>(d->A), d->a_mn_major, d->M, d->K, d->lda, batch, d->a_zstride, T2_BM);
+  Gemm2Launch L{};
+  L.batch = d->batch > 0 ? d->batch : 1;
+  L.bn = (d->bn == 128) ? 128 : 256;  // columns per pair
+  L.a_mn = d->a_mn_major; L.b_mn = d->b_mn_major;
+  rc = encode2(&L.tmA, reinterpret_cast<const __half*>(d->A), d->a_mn_major, d->M, d->K, d->lda, L.batch, d->a_zstride, T2_BM);
   if (rc) return rc;
-  const int bn = (d->bn == 128) ? 128 : 256;  // columns per pair
-  rc = encode2(&tmB, reinterpret_cast<const __half*>(d->B), d->b_mn_major, d->N, d->K, d->ldb, batch, d->b_zstride, bn / 2);
+  rc = encode2(&L.tmB, reinterpret_cast<const __half*>(d->B), d->b_mn_major, d->N, d->K, d->ldb, L.batch, d->b_zstride, L.bn / 2);
   if (rc) return rc;
-  Gemm2Args a{};
+  Gemm2Args& a = L.args;
   a.M = d->M; a.N = d->N; a.k_blocks = d->K / T2_BK;
-  a.tiles_n = (d->N + bn - 1) / bn;
+  a.tiles_n = (d->N + L.bn - 1) / L.bn;
   a.out32 = d->out32; a.out32_zstride = d->out32_zstride; a.ldo32 = d->ldo32;
+  a.bias_grad = d->bias_grad; a.bias_grad_zstride = d->bias_grad_zstride;
+  a.nonfinite = d->nonfinite;
   a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
   a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;
   if (d->a_lbo) a.a_lbo = d->a_lbo;
@@ -287,11 +327,5 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   if (d->b_lbo) a.b_lbo = d->b_lbo;
   if (d->b_sbo) a.b_sbo = d->b_sbo;
   if (d->b_kstep) a.b_kstep = d->b_kstep;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 128) {
-    if (d->a_mn_major) return launch2<true, true, 128>(tmA, tmB, a, batch, s);
-    return launch2<false, false, 128>(tmA, tmB, a, batch, s);
-  }
-  if (d->a_mn_major) return launch2<true, true, 256>(tmA, tmB, a, batch, s);
-  return launch2<false, false, 256>(tmA, tmB, a, batch, s);
+  return gemm2_launch(L, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,29 @@
+// EXPERIMENTAL cta_group::2 GEMM (gemm2cta.cu): launch descriptor shared with head.cu (opt-in weight-gradient path).
+#pragma once
+#include "gemm.cuh"
+
+namespace acez {
+
+struct Gemm2Args {
+  int M, N, k_blocks;
+  int tiles_n;           // column tiles (bn wide) per row of tiles
+  float* out32;          // [z][M][ldo32]
+  long long out32_zstride;
+  int ldo32;
+  float* bias_grad;      // [z][M] nullable: column sum over the contraction dimension of A 
+  long long bias_grad_zstride;
+  int* nonfinite;        // nullable: OR-ed with 1 if a stored value is non-finite or exceeds the fp16 range
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+};
+
+struct Gemm2Launch {
+  CUtensorMap tmA, tmB;  // A: box of this CTA's 128 rows; B: box of this CTA's bn / 2 rows (K-major) or 64 x 64 boxes (MN-major)
+  Gemm2Args args;
+  int batch;
+  int bn;                // 128 or 256 columns per CTA pair
+  int a_mn, b_mn;        // 0 = K-major, 1 = MN-major (both equal)
+};
+
+int gemm2_launch(const Gemm2Launch& L, cudaStream_t stream);
+
+}  // namespace acez

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "gemm2cta.cuh"
 #include "head_chain.cuh"
 #include "repro_loss.cuh"
 
@@ -57,6 +58,8 @@ struct acez_head_plan {
   // fused layer chains (head_chain.cu): one launch for all hidden layers of a pass
   int use_chain;
   acez::ChainLaunch chain_fwd, chain_bwd;
+  int use_wgrad2;              // ACEZ_WGRAD_2CTA=1 (experimental): batched weight gradient on cta_group::2 tiles (gemm2cta.cu)
+  acez::Gemm2Launch wgrad2;
   cudaStream_t side_stream;
   cudaEvent_t ev_dz[32];
   cudaEvent_t ev_join;
@@ -511,6 +514,26 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
                            CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
+    if (h->use_wgrad2) {
+      // the same operands (MN-major DZ / ACT, rows beyond `rows` zero-filled by TMA) on 256 x bn tiles of CTA pairs
+      Gemm2Launch& W = h->wgrad2;
+      W = Gemm2Launch{};
+      W.tmA = h->wgrad.tmA;
+      W.tmB = h->wgrad.tmB;
+      W.batch = L;
+      W.a_mn = W.b_mn = 1;
+      {
+        const char* e = getenv("ACEZ_WGRAD_2CTA_BN");
+        W.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;  // 128: 64 pairs = 128 CTAs without split-K
+      }
+      Gemm2Args& g = W.args;
+      g.M = kC; g.N = kC; g.k_blocks = (rows + 63) / 64;
+      g.tiles_n = kC / W.bn;
+      g.out32 = h->grads; g.out32_zstride = (long long)kLayerStride; g.ldo32 = kC;
+      g.bias_grad = h->grads + (size_t)kC * kC; g.bias_grad_zstride = (long long)kLayerStride;
+      g.a_lbo = 8192; g.a_sbo = 1024; g.a_kstep = 2048;
+      g.b_lbo = 8192; g.b_sbo = 1024; g.b_kstep = 2048;
+    }
     GemmArgs& a = h->wgrad.args;
     a.out32 = h->grads;
     a.out32_zstride = (long long)kLayerStride;
@@ -660,6 +683,10 @@ static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfini
     h->chain_bwd.args.nonfinite = nonfinite;
     int rc = chain_launch(h->chain_bwd, s);
     if (rc) return rc;
+    if (h->use_wgrad2) {
+      h->wgrad2.args.nonfinite = nonfinite;
+      return gemm2_launch(h->wgrad2, s);
+    }
     h->wgrad.args.nonfinite = nonfinite;
     return gemm_launch(h->wgrad, s);
   }
@@ -759,6 +786,10 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
     // ACEZ_HEAD_CHAIN=0 selects the per-layer tcgen05 GEMM path (also used when the head is deeper than the chain holds).
     const char* e = getenv("ACEZ_HEAD_CHAIN");
     h->use_chain = ((e == nullptr || atoi(e) != 0) && h->L <= kChainMaxSteps) ? 1 : 0;
+  }
+  {
+    const char* e = getenv("ACEZ_WGRAD_2CTA");
+    h->use_wgrad2 = (e != nullptr && atoi(e) != 0) ? 1 : 0;
   }
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;

@@ -32,6 +32,12 @@ stamp "chain v2 probe (same box) rc=$?"; head -n 3 gpurun_out/next_v2_probe.log 
 timeout 120 python tools/probe_gemm2cta.py > gpurun_out/next_gemm2cta.log 2>&1
 stamp "gemm2cta probe rc=$?"; cat gpurun_out/next_gemm2cta.log >> $S
 
+# 2b. the batched weight-gradient GEMM on cta_group::2 tiles (only meaningful if the probe passed)
+ACEZ_WGRAD_2CTA=1 timeout 200 python -m pytest tests/test_head_gpu.py tests/test_head_chain_gpu.py -m gpu -x -q > gpurun_out/next_wgrad2_tests.log 2>&1
+stamp "wgrad 2-CTA tests rc=$?"; tail -n 3 gpurun_out/next_wgrad2_tests.log >> $S
+ACEZ_WGRAD_2CTA=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_wgrad2.log 2>&1
+stamp "breakdown wgrad 2-CTA (256x128 tiles) rc=$?"; cat gpurun_out/next_breakdown_wgrad2.log >> $S
+
 # 3. tail kernel at 2 CTAs / SM
 ACEZ_TAIL_OCC2=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_occ2_tests.log 2>&1
 stamp "tail occ2 tests rc=$?"; tail -n 2 gpurun_out/next_occ2_tests.log >> $S

@@ -14,10 +14,12 @@ from acezero_b200 import _lib  # noqa: E402
 from tools.probe_gemm import ref  # noqa: E402
 
 
-def run(fn_name, A, B, mn, M, N, K, batch=1, bn=128):
+def run(fn_name, A, B, mn, M, N, K, batch=1, bn=128, bias=None):
     lib = _lib.load()
     out = torch.full((batch, M, N), float("nan"), device="cuda", dtype=torch.float32)
     d = _lib.GemmDesc()
+    if bias is not None:
+        d.bias_grad, d.bias_grad_zstride = bias.data_ptr(), M
     d.A, d.B = A.data_ptr(), B.data_ptr()
     d.a_mn_major = d.b_mn_major = mn
     d.M, d.N, d.K, d.batch = M, N, K, batch
@@ -31,7 +33,7 @@ def run(fn_name, A, B, mn, M, N, K, batch=1, bn=128):
     return out, d
 
 
-def case(name, mn, M, N, K, batch=1, bn=0):
+def case(name, mn, M, N, K, batch=1, bn=0, bias_grad=False):
     g = torch.Generator(device="cuda").manual_seed(1)
     shpA = (K, M) if mn else (M, K)
     shpB = (K, N) if mn else (N, K)
@@ -40,7 +42,8 @@ def case(name, mn, M, N, K, batch=1, bn=0):
     A = (torch.randn(shpA, device="cuda", generator=g) * 0.5).half()
     B = (torch.randn(shpB, device="cuda", generator=g) * 0.5).half()
     try:
-        out, _ = run("acez_gemm2cta_f16", A, B, mn, M, N, K, batch, bn)
+        bg = torch.full((batch, M), float("nan"), device="cuda") if bias_grad else None
+        out, _ = run("acez_gemm2cta_f16", A, B, mn, M, N, K, batch, bn, bg)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         print(f"{name}: ERROR {e}", flush=True)
@@ -55,6 +58,11 @@ def case(name, mn, M, N, K, batch=1, bn=0):
         e0 = err[0]
         loc = " | max err by (row half, col half) of the first 256x256 tile: " + " ".join(
             f"{e0[128 * i:128 * i + 128, 128 * j:128 * j + 128].nan_to_num(9e9).max().item():.3g}" for i in range(2) for j in range(2))
+    if bias_grad:
+        Af = (A.float().transpose(-1, -2) if mn else A.float()).reshape(batch, M, K)
+        e2 = (bg - Af.sum(-1)).abs().nan_to_num(9e9).max().item()
+        ok = ok and e2 < 1e-2
+        loc += f" bias_grad_err={e2:.4g}"
     print(f"{name}: max_abs_err={err.nan_to_num(9e9).max().item():.4g} (ref max {scale:.4g}) {'OK' if ok else 'FAIL'}{loc}", flush=True)
     return ok
 
@@ -91,6 +99,9 @@ def main():
     ok &= case("MN/MN batched x8 K=640", 1, 512, 512, 640, batch=8)
     ok &= case("K/K   512x512x512  256x128 tiles", 0, 512, 512, 512, bn=128)
     ok &= case("MN/MN batched x8 K=640, 256x128 tiles", 1, 512, 512, 640, batch=8, bn=128)
+    ok &= case("MN/MN batched x8 K=5120, 256x128 tiles + bias column (the weight-gradient launch)", 1, 512, 512, 5120, batch=8, bn=128,
+               bias_grad=True)
+    ok &= case("MN/MN batched x2 K=640, 256x256 tiles + bias column", 1, 512, 512, 640, batch=2, bn=256, bias_grad=True)
     print("RESULT", "PASS" if ok else "FAIL", flush=True)
     if ok:
         timing()
