@@ -136,3 +136,18 @@ def test_dsac_oracle_recovers_pose():
     r = D.forward_rgb(sc, 32, 10.0, f, px, py, 100.0, 100.0, 8, 1305, 16, nan_to_max=True)
     rot, tr = D.pose_error(r["pose"], Tgt)
     assert r["inliers"] > 2500 and rot < 0.5 and tr < 0.02
+
+
+def test_chain_protocol_model_check():
+    """The mbarrier protocol of the fused layer-chain kernel (csrc/head_chain.cu), default and V3 variants, under random
+    interleavings of its agents and asynchronous engines: no stale / aliased phase, no box written under a reader, no
+    TMEM buffer overwritten before it is drained, no deadlock (tools/sim_chain_protocol.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sim_chain_protocol", ROOT / "tools" / "sim_chain_protocol.py")
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for v3 in (False, True):
+        sim.V3 = v3
+        for seed in range(24):
+            for n in (1, 2, 3, 8):
+                sim.Sim(n, seed).run()
