@@ -48,6 +48,12 @@ stamp "breakdown tail occ2 rc=$?"; cat gpurun_out/next_breakdown_occ2.log >> $S
 ACEZ_TEST_EXTRA=1 timeout 300 python -m pytest tests/test_stress_gpu.py -m gpu -q > gpurun_out/next_stress.log 2>&1
 stamp "stress tests rc=$?"; tail -n 4 gpurun_out/next_stress.log >> $S
 
+# 3c. optimiser state (34 MB) pinned in L2
+ACEZ_L2_PERSIST=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_l2_tests.log 2>&1
+stamp "L2 persistence tests rc=$?"; tail -n 2 gpurun_out/next_l2_tests.log >> $S
+ACEZ_L2_PERSIST=1 timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_l2.json 2> gpurun_out/next_bench_l2.err
+stamp "bench L2 persistence rc=$?"; cut -c1-260 gpurun_out/next_bench_l2.json >> $S
+
 # 4. everything that passed, together: bench line
 if [ $rc_v3 -eq 0 ]; then
   ACEZ_CHAIN_V3=1 ACEZ_TAIL_OCC2=1 timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_out/next_bench_v3_occ2.json 2> gpurun_out/next_bench_v3_occ2.err
