@@ -65,6 +65,8 @@ struct acez_head_plan {
   cudaEvent_t ev_join;
   bool side_ready;
   int overlap_wgrad;
+  int fc3_overlap;     // ACEZ_FC3_OVERLAP=1 (experimental): the fc3 weight-gradient kernels run on the side stream, under the dgrad chain
+  bool fc3_pending;    // a join with the side stream is due at the end of the backward
 };
 
 namespace acez {
@@ -644,6 +646,16 @@ static int tail_grid(int rows) {
   return g < cap ? (g < 1 ? 1 : g) : cap;
 }
 
+static int ensure_side_stream(acez_head_plan* h) {
+  if (!h->side_ready) {
+    ACEZ_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < h->L; ++i) ACEZ_CUDA(cudaEventCreateWithFlags(&h->ev_dz[i], cudaEventDisableTiming));
+    ACEZ_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->side_ready = true;
+  }
+  return ACEZ_OK;
+}
+
 // tail (+ fc3 gradient) launch sequence shared by the training entries
 static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s, int* nonfinite, bool with_fc3_grad,
                        bool pdl) {
@@ -664,10 +676,23 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
   if (with_fc3_grad) {
     const int nblk = (rows + kFc3Rows - 1) / kFc3Rows;
     float* gW3 = h->grads + (size_t)h->L * kLayerStride;
-    rc = launch_pdl(fc3_wgrad_partial_kernel, dim3(nblk), dim3(kFc3Threads), 0, s, true, t.x, (const float*)h->G3, rows, h->FC3PART);
+    cudaStream_t fs = s;
+    bool first_pdl = true;
+    if (h->fc3_overlap) {
+      // fork: the two fc3 gradient kernels (10 us, 160 + 65 small CTAs) only need G3 and ACT[L] from the tail; they run on
+      // the SMs the 80-CTA dgrad chain leaves idle and are joined at the end of launch_backward_gemms
+      rc = ensure_side_stream(h);
+      if (rc) return rc;
+      ACEZ_CUDA(cudaEventRecord(h->ev_dz[0], s));
+      ACEZ_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_dz[0], 0));
+      fs = h->side_stream;
+      first_pdl = false;  // predecessor on that stream is an event wait, not a kernel
+      h->fc3_pending = true;
+    }
+    rc = launch_pdl(fc3_wgrad_partial_kernel, dim3(nblk), dim3(kFc3Threads), 0, fs, first_pdl, t.x, (const float*)h->G3, rows, h->FC3PART);
     if (rc) return rc;
     const int total = 4 * kC + 4;
-    rc = launch_pdl(fc3_reduce_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, s, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
+    rc = launch_pdl(fc3_reduce_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, fs, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
                     gW3 + (size_t)h->C3 * kC, nonfinite);
     if (rc) return rc;
   }
@@ -685,10 +710,18 @@ static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfini
     if (rc) return rc;
     if (h->use_wgrad2) {
       h->wgrad2.args.nonfinite = nonfinite;
-      return gemm2_launch(h->wgrad2, s);
+      rc = gemm2_launch(h->wgrad2, s);
+    } else {
+      h->wgrad.args.nonfinite = nonfinite;
+      rc = gemm_launch(h->wgrad, s);
     }
-    h->wgrad.args.nonfinite = nonfinite;
-    return gemm_launch(h->wgrad, s);
+    if (rc) return rc;
+    if (h->fc3_pending) {  // join the fc3 gradient kernels forked in launch_tail
+      ACEZ_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+      ACEZ_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+      h->fc3_pending = false;
+    }
+    return ACEZ_OK;
   }
   if (!h->overlap_wgrad) {
     for (int l = L - 1; l >= 1; --l) {
@@ -790,6 +823,9 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   {
     const char* e = getenv("ACEZ_WGRAD_2CTA");
     h->use_wgrad2 = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    const char* f = getenv("ACEZ_FC3_OVERLAP");   // only with the fused chain (the join sits in its branch of the backward)
+    h->fc3_overlap = (f != nullptr && atoi(f) != 0 && h->use_chain) ? 1 : 0;
+    h->fc3_pending = false;
   }
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;

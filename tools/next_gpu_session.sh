@@ -48,6 +48,12 @@ stamp "breakdown tail occ2 rc=$?"; cat gpurun_out/next_breakdown_occ2.log >> $S
 ACEZ_TEST_EXTRA=1 timeout 300 python -m pytest tests/test_stress_gpu.py -m gpu -q > gpurun_out/next_stress.log 2>&1
 stamp "stress tests rc=$?"; tail -n 4 gpurun_out/next_stress.log >> $S
 
+# 3b2. fc3 gradient kernels on a side stream under the dgrad chain
+ACEZ_FC3_OVERLAP=1 timeout 150 python -m pytest tests/test_head_gpu.py tests/test_head_chain_gpu.py -m gpu -x -q > gpurun_out/next_fc3ov_tests.log 2>&1
+stamp "fc3 overlap tests rc=$?"; tail -n 2 gpurun_out/next_fc3ov_tests.log >> $S
+ACEZ_FC3_OVERLAP=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_fc3ov.log 2>&1
+stamp "breakdown fc3 overlap rc=$?"; cat gpurun_out/next_breakdown_fc3ov.log >> $S
+
 # 3c. optimiser state (34 MB) pinned in L2
 ACEZ_L2_PERSIST=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_l2_tests.log 2>&1
 stamp "L2 persistence tests rc=$?"; tail -n 2 gpurun_out/next_l2_tests.log >> $S
