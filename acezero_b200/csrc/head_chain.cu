@@ -644,6 +644,14 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
     if (rc) return rc;
   }
   {
+    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)kC, (uint64_t)L};
+    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)kC * kC * 2};
+    uint32_t box[3] = {64, (uint32_t)(mode == CHAIN_FWD ? CN / 2 : 64), 1};
+    rc = make_tensor_map(&C->tmW4, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, W16, dims, strides, box, nullptr,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
     uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, (uint64_t)out_slots};
     uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)out_zstride * 2};
     uint32_t box[3] = {64, (uint32_t)CM, 1};
@@ -727,6 +735,11 @@ int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
     const char* e = getenv("ACEZ_CHAIN_V3");  // not yet validated on hardware (round 2): see the kernel header
     return e != nullptr && atoi(e) != 0;
   }();
+  static const bool v4 = [] {
+    const char* e = getenv("ACEZ_CHAIN_V4");  // not yet validated on hardware (round 2): head_chain4.cu
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (v4) return chain4_launch(C, stream);
   if (xchg_st) {
     if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, true, false>(C, stream);
     return chain_launch_mode<CHAIN_DGRAD, true, false>(C, stream);

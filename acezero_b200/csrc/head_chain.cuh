@@ -49,6 +49,7 @@ struct ChainLaunch {
   CUtensorMap tmIn;   // first A tile: [rows, 512], box {64, 128, 1}
   CUtensorMap tmW;    // W16 [L][512][512]: FWD box {64, 256, 1} (K-major B), DGRAD box {64, 64, 1} (MN-major B)
   CUtensorMap tmOut;  // [slots][rows][512], box {64, 128, 1}
+  CUtensorMap tmW4;   // head_chain4.cu (experimental): FWD box {64, 128, 1} (this CTA's half of a weight k-block), DGRAD box {64, 64, 1}
   ChainArgs args;
   int mode;
 };
@@ -57,6 +58,7 @@ struct ChainLaunch {
 int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16, int L, __half* out_base,
                   long long out_zstride, int out_slots, int rows);
 int chain_launch(const ChainLaunch& C, cudaStream_t stream);
+int chain4_launch(const ChainLaunch& C, cudaStream_t stream);  // ACEZ_CHAIN_V4=1 (experimental, cta_group::2 on a cluster of 4)
 // profiling probe: copies the stamps of the most recent launch with ACEZ_CHAIN_DBG=1 to host memory
 int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas);
 

@@ -1,0 +1,447 @@
+// EXPERIMENTAL (ACEZ_CHAIN_V4=1; written without GPU time at the end of round 1, not yet run on hardware):
+// the fused layer chain of head_chain.cu on tcgen05 cta_group::2.
+//
+// Why: the cta_group::1 chain is bound by the shared-memory port (per layer and CTA 384 KB of UMMA operand reads + 256 KB
+// of weight fill + 4 x 64 KB of box traffic = 896 KB = 7 k cycles at 128 B/clk against 4.1 k cycles of UMMA issue). With
+// cta_group::2 two CTAs of an SM pair share every weight k-block (each stages HALF of it, the hardware feeds both tensor
+// cores from both halves): 128 KB of weight fill and 256 KB of operand reads per layer and CTA = 640 KB = 5 k cycles,
+// and the same 96 KB ring holds twice as many k-blocks in flight.
+//
+// Decomposition: a cluster of FOUR CTAs owns TWO 128-row tiles. rank = 2 c + r:
+//   r = row tile inside the cluster, c = channel half. Pair P_c = {2c, 2c+1} (an SM pair) runs
+//   tcgen05.mma.cta_group::2 with M = 256 (CTA r contributes its row tile's 128 x 512 A buffer), N = 256 (output channels
+//   [256 c, 256 c + 256) of the layer; CTA r stages weight rows [256 c + 128 r, +128) of every k-block). Accumulators:
+//   each CTA's TMEM holds ITS rows x the pair's 256 channels, double buffered. The epilogue, the box exchange (now with
+//   rank ^ 2: same row tile, other channel half), the TMA stores, the register-resident residual stream and the mask bit
+//   words are those of head_chain.cu (V3 epilogue without the half-box publication).
+// Roles: warp 0 TMA producer (both CTAs: own A tile, own half of every weight k-block, completing on the LEADER's barrier);
+//   warp 1 of the pair leader (r = 0) issues the UMMAs; warp 1 of the other CTA is a RELAY: the leader cannot wait on a
+//   remote mbarrier, so the partner forwards "my k-block j is in place" to the leader's partner_ready[j].
+// tcgen05.commit ... multicast::cluster (mask of the pair) releases weight stages / publishes accumulators to both CTAs.
+#include <stdlib.h>
+
+#include "head_chain.cuh"
+
+namespace acez {
+
+static constexpr int kC = 512;
+static constexpr int CM = 128, CN = 256, CK = 64;
+static constexpr int kKB = kC / CK;
+static constexpr int kBoxBytes = CM * CK * 2;        // 16 KB
+static constexpr int kABytes = kKB * kBoxBytes;      // 128 KB
+static constexpr int kBHalf = (CN / 2) * CK * 2;     // 16 KB: this CTA's half of a weight k-block
+static constexpr int kBStages = 6;
+static constexpr int kThreads4 = 320;
+static constexpr int kSmem4 = kABytes + kBStages * kBHalf + 1024 /*fp32 bias slice*/ + 384 /*barriers*/ + 1024 /*align*/;
+static_assert(kSmem4 <= 232448, "shared memory budget");
+static constexpr uint32_t kSw128 = 2;
+static constexpr uint32_t kPeerBit = 0xFEFFFFFFu;  // clears the pair bit of a shared::cluster address: the even CTA of the pair
+
+__device__ __forceinline__ uint32_t c4_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void c4_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t c4_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void c4_arrive_remote_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void c4_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool c4_try_wait(uint64_t* bar, uint32_t parity, int sem /*0 cta acquire, 1 cluster acquire, 2 cluster relaxed*/) {
+  uint32_t ok;
+  if (sem == 0) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } else if (sem == 1) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } else {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+  return ok != 0;
+}
+__device__ __noinline__ void c4_timeout(uint32_t tag, uint32_t parity) {
+  printf("acez: chain4 wait timeout: kind %u step %u index %u parity %u (block %d, cta rank %d, thread %d)\n", tag >> 16,
+         (tag >> 8) & 0xFF, tag & 0xFF, parity, blockIdx.x, (int)c4_ctarank(), threadIdx.x);
+  __trap();
+}
+// kinds: 1 a_ready, 2 b_full, 3 b_empty, 4 tmem_full, 5 peer_free, 7 partner_ready
+template <int SEM>
+__device__ __forceinline__ void c4_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  if (c4_try_wait(bar, parity, SEM)) return;
+  const long long t0 = clock64();
+  while (!c4_try_wait(bar, parity, SEM)) {
+    if (clock64() - t0 > 2000000000ll) c4_timeout(tag, parity);
+  }
+}
+__device__ __forceinline__ void c4_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void c4_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// weight load of a CTA of the pair: completes (bytes) on the pair LEADER's barrier of the same offset
+__device__ __forceinline__ void c4_tma_load_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBit), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void c4_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBit) : "memory");
+}
+__device__ __forceinline__ void c4_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void c4_commit_pair(uint64_t* bar, uint16_t pair_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(pair_mask)
+               : "memory");
+}
+__device__ __forceinline__ void c4_dsmem_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void c4_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// consumption order of the 8 k-blocks by arrival: own 0,1 | exchange partner's 0,1 | own 2,3 | partner's 2,3
+__device__ __forceinline__ int c4_order(int i, int c) {
+  const int b = ((i >> 2) << 1) | (i & 1);
+  return ((i & 2) ? (c ^ 1) : c) * 4 + b;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads4, 1)
+head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
+                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
+  constexpr bool kDgrad = (MODE == CHAIN_DGRAD);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kABytes;
+  float* sBiasF = reinterpret_cast<float*>(sB + kBStages * kBHalf);
+  uint64_t* a_ready = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBiasF) + 1024);
+  uint64_t* partner_ready = a_ready + kKB;   // leader only: the other CTA of the pair has k-block j in place
+  uint64_t* b_full = partner_ready + kKB;    // leader only (count 2)
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* tmem_full = b_empty + kBStages;
+  uint64_t* peer_free = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peer_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)c4_ctarank();
+  const int c = rank >> 1, r = rank & 1;
+  const bool leader = r == 0;
+  const int xpeer = rank ^ 2;               // exchange partner: same row tile, other channel half
+  const uint16_t pair_mask = (uint16_t)(0x3u << (2 * c));
+  const int m0 = ((int)(blockIdx.x >> 2) * 2 + r) * CM;
+  const int n_base = c * CN;                // the pair's output channels of every layer
+  const int nb_half = n_base + r * (CN / 2);
+  const int n_steps = args.n_steps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < kKB; ++i) {
+      mbar_init(&a_ready[i], 1);
+      mbar_init(&partner_ready[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], 2);   // leader: arrive.expect_tx (both halves) + the partner's arrive
+      mbar_init(&b_empty[i], 1);  // multicast commit
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(peer_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) c4_tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncwarp();
+  c4_cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (elect_one()) {
+      for (int i = 0; i < kKB; ++i) {
+        const int j = c4_order(i, c);
+        mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
+        tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const int wl = args.step[s].w_layer;
+        for (int i = 0; i < kKB; ++i) {
+          const int j = c4_order(i, c);
+          c4_wait<0>(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
+          if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * kBHalf);
+          else c4_arrive_leader(&b_full[stage]);
+          uint8_t* dst = sB + stage * kBHalf;
+          if (!kDgrad) {
+            c4_tma_load_pair(dst, &tmW, &b_full[stage], j * CK, nb_half, wl);  // 128 weight rows x 64 input channels
+          } else {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) c4_tma_load_pair(dst + t * 8192, &tmW, &b_full[stage], nb_half + 64 * t, j * CK, wl);
+          }
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t xpeer_free = c4_mapa(smem_u32(peer_free), (uint32_t)xpeer);
+    if (leader) {
+      // ------------------------------ UMMA issuer (pair leader) ------------------------------
+      constexpr uint32_t idesc = make_idesc_f16(2 * CM, CN, false, kDgrad);
+      constexpr uint32_t b_lbo = kDgrad ? 8192u : 0u;
+      constexpr uint32_t b_kstep = kDgrad ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
+        for (int i = 0; i < kKB; ++i) {
+          const int j = c4_order(i, c);
+          c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+          if ((i & 2) && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+          c4_wait<2>(&partner_ready[j], (uint32_t)(s & 1), (7u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+          c4_wait<0>(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
+            const uint32_t b_addr = smem_u32(sB + stage * kBHalf);
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 0, 1024, kSw128);
+              const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024, kSw128);
+              c4_umma(d_tmem, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) {
+            c4_commit_pair(&b_empty[stage], pair_mask);
+            if (i == kKB - 1) c4_commit_pair(&tmem_full[s & 1], pair_mask);
+          }
+          __syncwarp();
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
+        }
+        c4_wait<0>(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8) | 1u);
+        if (lane == 0) c4_arrive_remote_relaxed(xpeer_free);
+        __syncwarp();
+      }
+    } else {
+      // ------------------------------ relay (the other CTA of the pair) ------------------------------
+      for (int s = 0; s < n_steps; ++s) {
+        for (int i = 0; i < kKB; ++i) {
+          const int j = c4_order(i, c);
+          c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
+          if (lane == 0) {
+            if ((i & 2) && s + 1 < n_steps) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+            // my k-block j of step s is in place IN MY OWN shared memory (generic-proxy writes were fenced by their writers,
+            // async copies completed on the barrier) and it is my own tensor core that will read it: the signal to the
+            // leader, which issues the UMMAs for both CTAs, carries no data - relaxed, no fence (a release at cluster scope
+            // costs a MEMBAR.ALL.GPU per k-block here; measured ~600 cycles per handshake in the 2-CTA chain)
+            c4_arrive_remote_relaxed(c4_mapa(smem_u32(&partner_ready[j]), (uint32_t)(rank & ~1)));
+          }
+          __syncwarp();
+        }
+        c4_wait<0>(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8) | 1u);
+        if (lane == 0) c4_arrive_remote_relaxed(xpeer_free);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (as head_chain.cu V3, exchange partner = rank ^ 2) ------------------------------
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int rr = quarter * 32 + lane;
+    const int row = m0 + rr;
+    const bool row_ok = row < args.rows;
+    const int etid = threadIdx.x - 64;
+    const bool issuer = (lane == 0) && (quarter == 2 - 2 * grp);
+    const uint32_t swz = (uint32_t)(rr & 7);
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t badbits = 0;
+    uint32_t res[2][32];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+      for (int t = 0; t < 32; ++t) res[sl][t] = 0u;
+    if (!kDgrad && (args.flags & kChainFlagResInit)) {
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int j = c * 4 + grp + 2 * sl;
+        c4_wait<0>(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
+        const uint8_t* src = sA + j * kBoxBytes + rr * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 t = *reinterpret_cast<const uint4*>(src + ((((uint32_t)q) ^ swz) << 4));
+          res[sl][4 * q] = t.x; res[sl][4 * q + 1] = t.y; res[sl][4 * q + 2] = t.z; res[sl][4 * q + 3] = t.w;
+        }
+      }
+    }
+    for (int s = 0; s < n_steps; ++s) {
+      const ChainStep& st = args.step[s];
+      const int tbuf = s & 1;
+      const bool last = (s == n_steps - 1);
+      if (!kDgrad) {
+        if (s > 0) asm volatile("bar.sync 3, 256;" ::: "memory");
+        sBiasF[etid] = __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
+      }
+      c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
+      tcgen05_fence_after();
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
+      const bool want_mask = !kDgrad && st.mask_out != nullptr;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int box = grp + 2 * sl;
+        const int j = c * 4 + box;
+        const int col0 = n_base + box * 64;
+        uint2 mw = make_uint2(0u, 0u);
+        if (kDgrad && row_ok) mw = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + j * 8));
+        if (issuer) {
+          if (sl == 0) c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+          c4_store_wait_read1();
+        }
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        uint8_t* dst = sA + j * kBoxBytes + rr * 128;
+        uint32_t bits_lo = 0u, bits_hi = 0u;
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t vv[32];
+          tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + box * 64 + hf * 32), vv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int q = hf * 4 + q4;
+            uint4 o;
+            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+            float4 bf0 = make_float4(0.f, 0.f, 0.f, 0.f), bf1 = bf0;
+            if (!kDgrad) {
+              bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
+              bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
+            }
+            const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int col = q * 8 + 2 * t;
+              const int vc = col - hf * 32;
+              uint32_t& rs = res[sl][4 * q + t];
+              if (!kDgrad) {
+                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]) + bq[2 * t], __uint_as_float(vv[vc + 1]) + bq[2 * t + 1]);
+                if (relu) h = __hmax2(h, zero2);
+                if (want_mask) {
+                  const uint32_t m = __hgt2_mask(h, zero2);
+                  const uint32_t two = (m & 1u) | ((m >> 15) & 2u);
+                  if (col < 32) bits_lo |= two << col;
+                  else bits_hi |= two << (col - 32);
+                }
+                if (res_add) {
+                  h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);
+                  rs = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                ob[t] = *reinterpret_cast<const uint32_t*>(&h);
+              } else {
+                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
+                if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                if (res_save) rs = hb;
+                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;
+                const uint32_t w = (col < 32) ? (mw.x >> col) : (mw.y >> (col - 32));
+                const uint32_t m = ((w & 1u) ? 0x0000FFFFu : 0u) | ((w & 2u) ? 0xFFFF0000u : 0u);
+                ob[t] = hb & m;
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+          }
+        }
+        tcgen05_fence_before();
+        if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
+        fence_proxy_async();
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (issuer) {
+          const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+          if (!last) {
+            mbar_arrive(&a_ready[j]);
+            c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
+          }
+          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all();
+    if (kDgrad && args.nonfinite != nullptr) {
+      if (__any_sync(0xffffffffu, badbits != 0) && lane == 0) atomicOr(args.nonfinite, 1);
+    }
+  }
+
+  __syncwarp();
+  tcgen05_fence_before();
+  c4_cluster_sync();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    c4_tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int MODE>
+static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
+  auto kern = head_chain4_kernel<MODE>;
+  static bool configured = false;
+  if (!configured) {
+    ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4));
+    configured = true;
+  }
+  const int tiles = (C.args.rows + CM - 1) / CM;
+  const int clusters = (tiles + 1) / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(4 * clusters);
+  cfg.blockDim = dim3(kThreads4);
+  cfg.dynamicSmemBytes = kSmem4;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, C.tmW4, C.tmOut, C.args));
+  return ACEZ_OK;
+}
+
+int chain4_launch(const ChainLaunch& C, cudaStream_t stream) {
+  ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain4_launch: %d steps", C.args.n_steps);
+  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD>(C, stream);
+  return chain4_launch_mode<CHAIN_DGRAD>(C, stream);
+}
+
+}  // namespace acez

@@ -151,3 +151,10 @@ def test_chain_protocol_model_check():
         for seed in range(24):
             for n in (1, 2, 3, 8):
                 sim.Sim(n, seed).run()
+    # the cluster-of-4 / cta_group::2 variant (csrc/head_chain4.cu)
+    spec4 = importlib.util.spec_from_file_location("sim_chain4_protocol", ROOT / "tools" / "sim_chain4_protocol.py")
+    sim4 = importlib.util.module_from_spec(spec4)
+    spec4.loader.exec_module(sim4)
+    for seed in range(16):
+        for n in (1, 2, 3, 8):
+            sim4.Sim(n, seed).run()

@@ -38,6 +38,17 @@ stamp "wgrad 2-CTA tests rc=$?"; tail -n 3 gpurun_out/next_wgrad2_tests.log >> $
 ACEZ_WGRAD_2CTA=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_wgrad2.log 2>&1
 stamp "breakdown wgrad 2-CTA (256x128 tiles) rc=$?"; cat gpurun_out/next_breakdown_wgrad2.log >> $S
 
+# 2c. layer chain on cta_group::2 / cluster of 4 (only meaningful if the 2-CTA probe passed)
+ACEZ_CHAIN_V4=1 timeout 200 python -m pytest tests/test_head_chain_gpu.py tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_v4_tests.log 2>&1
+rc_v4=$?
+stamp "chain V4 tests rc=$rc_v4"; tail -n 6 gpurun_out/next_v4_tests.log >> $S
+if [ $rc_v4 -ne 0 ]; then
+  ACEZ_CHAIN_V4=1 timeout 100 python tools/diag_chain.py 384 > gpurun_out/next_v4_diag.log 2>&1
+  stamp "chain V4 diag rc=$?"; tail -n 24 gpurun_out/next_v4_diag.log >> $S
+fi
+ACEZ_CHAIN_V4=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_v4.log 2>&1
+stamp "breakdown chain V4 rc=$?"; cat gpurun_out/next_breakdown_v4.log >> $S
+
 # 3. tail kernel at 2 CTAs / SM
 ACEZ_TAIL_OCC2=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_occ2_tests.log 2>&1
 stamp "tail occ2 tests rc=$?"; tail -n 2 gpurun_out/next_occ2_tests.log >> $S
