@@ -14,6 +14,8 @@
 //   block-wide reduction of the 6x6 normal equations in double.
 // Arithmetic: projections in double (OpenCV's projectPoints computes in double and stores float pixels);
 // no cheirality test (z ? 1/z : 1), as in OpenCV. Not HBM-bound, no tensor cores: FP64/FP32 FMA + SFU + smem.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace acez {
@@ -256,120 +258,11 @@ __device__ __forceinline__ const float* stage_sc(const DsacArgs& a, int img, flo
 
 // ---------------------------------------------------------------- kernel 1: sample + score
 __global__ void __launch_bounds__(kDsacThreads) dsac_sample_score_kernel(const DsacArgs a) {
-  extern __shared__ float smem_sc[];
-  const int img = blockIdx.y;
-  const int cells = a.h * a.w;
-  const float* sc = stage_sc(a, img, smem_sc, cells);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps = kDsacThreads / 32;
-  const double f = a.focal[img], cx = a.ppx[img], cy = a.ppy[img];
-  const float thr = a.p.inlier_threshold, max_reproj = a.p.max_reproj;
-  const int sub = a.p.subsample, half = a.p.subsample / 2;
-  const float beta = 5.f / thr;  // dsacstar_util.h:324
-
-  for (int hyp = blockIdx.x * warps + warp; hyp < a.p.hyps; hyp += gridDim.x * warps) {
-    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
-    int ok = 0, tries_used = 0;
-    const int max_tries = a.injected ? 1 : (a.p.max_tries < 1 ? 1 : a.p.max_tries);
-    for (int base = 0; base < max_tries; base += 32) {
-      const int tr = base + lane;
-      int my_ok = 0;
-      double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tm[3] = {0, 0, 0};  // failed PnP -> zero rvec/tvec (dsacstar_util.h:114-116)
-      if (tr < max_tries) {
-        double Pw[4][3];
-        float px[4], py[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int x, y;
-          if (a.injected) {
-            const int* ip = a.injected + (((size_t)img * a.p.hyps + hyp) * 4 + j) * 2;
-            x = min(max(ip[0], 0), a.w - 1);
-            y = min(max(ip[1], 0), a.h - 1);
-          } else {
-            draw_cell(a.p.seed, img + a.p.image_index_base, hyp, tr, j, a.w, a.h, x, y);
-          }
-          const int c = y * a.w + x;
-          Pw[j][0] = sc[c]; Pw[j][1] = sc[cells + c]; Pw[j][2] = sc[2 * cells + c];
-          px[j] = (float)(x * sub + half);  // dsacstar_util.h:69-71
-          py[j] = (float)(y * sub + half);
-        }
-        double fb[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const double bx = ((double)px[j] - cx) / f, by = ((double)py[j] - cy) / f;
-          const double in = 1.0 / sqrt(bx * bx + by * by + 1.0);
-          fb[j][0] = bx * in; fb[j][1] = by * in; fb[j][2] = in;
-        }
-        double Rs[4][9], ts[4][3];
-        const int ns = p3p_grunert(Pw, fb, Rs, ts);
-        // cv::solvePnP(P3P): the 4th point picks among the <= 4 solutions (smallest reprojection error)
-        int best = -1;
-        double best_e = 0;
-        for (int s = 0; s < ns; ++s) {
-          float u, v;
-          project_pt(Rs[s], ts[s], Pw[3][0], Pw[3][1], Pw[3][2], f, cx, cy, u, v);
-          const double du = (double)u - px[3], dv = (double)v - py[3];
-          const double e = du * du + dv * dv;
-          if (isfinite(e) && (best < 0 || e < best_e)) { best = s; best_e = e; }
-        }
-        if (best >= 0) {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Rm[i] = Rs[best][i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) tm[i] = ts[best][i];
-          // all 4 sampled points must reproject within the inlier threshold (dsacstar_util.h:198-219)
-          my_ok = 1;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float u, v;
-            project_pt(Rm, tm, Pw[j][0], Pw[j][1], Pw[j][2], f, cx, cy, u, v);
-            const float dx = px[j] - u, dy = py[j] - v;
-            const double e = sqrt((double)dx * dx + (double)dy * dy);
-            if (!(e < (double)thr)) my_ok = 0;
-          }
-        }
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, my_ok);
-      int src;
-      if (m != 0) { src = __ffs(m) - 1; ok = 1; tries_used = base + src + 1; }
-      else if (base + 32 >= max_tries) { src = max_tries - 1 - base; tries_used = max_tries; }  // keep the last try
-      else continue;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = __shfl_sync(0xffffffffu, Rm[i], src);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) t[i] = __shfl_sync(0xffffffffu, tm[i], src);
-      break;
-    }
-
-    // soft inlier score over all cells (dsacstar_util.h:316-343, 356-446)
-    float acc = 0.f;
-    for (int c = lane; c < cells; c += 32) {
-      const int x = c % a.w, y = c / a.w;
-      float u, v;
-      project_pt(R, t, sc[c], sc[cells + c], sc[2 * cells + c], f, cx, cy, u, v);
-      const float e = repro_err((float)(x * sub + half), (float)(y * sub + half), u, v, max_reproj);
-      acc += 1.f / (1.f + __expf(beta * (e - thr)));  // 1 - sigmoid(beta (e - thr))
-    }
-    double score = warp_sum((double)acc) * ((double)a.p.inlier_alpha / (double)a.w / (double)a.h);
-    if (lane == 0) {
-      HypRec& rec = a.ws[(size_t)img * a.p.hyps + hyp];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) rec.R[i] = R[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) rec.t[i] = t[i];
-      rec.score = score;
-      rec.tries = tries_used;
-      rec.ok = ok;
-      const size_t o = (size_t)img * a.p.hyps + hyp;
-      if (a.dbg.hyp_scores) a.dbg.hyp_scores[o] = (float)score;
-      if (a.dbg.hyp_tries) a.dbg.hyp_tries[o] = tries_used;
-      if (a.dbg.hyp_poses) {
-        double rv[3];
-        rodrigues_inv(R, rv);
-        for (int i = 0; i < 3; ++i) { a.dbg.hyp_poses[o * 6 + i] = (float)rv[i]; a.dbg.hyp_poses[o * 6 + 3 + i] = (float)t[i]; }
-      }
-    }
-  }
+#include "dsac_sample_body.inc"
+}
+// ACEZ_DSAC_OCC=1 (experimental): 80 registers (128 otherwise, ~250 B of spills): three CTAs per SM instead of two.
+__global__ void __launch_bounds__(kDsacThreads, 3) dsac_sample_score_kernel_occ3(const DsacArgs a) {
+#include "dsac_sample_body.inc"
 }
 
 // ---------------------------------------------------------------- kernel 2: select + refine
@@ -442,211 +335,11 @@ __device__ void block_sum(double (&v)[CNT], double* s_part /*[warps][CNT]*/, dou
 }
 
 __global__ void __launch_bounds__(kDsacThreads) dsac_refine_kernel(const DsacArgs a) {
-  extern __shared__ float smem_sc[];
-  __shared__ double s_part[(kDsacThreads / 32) * 28];
-  __shared__ double s_out[28];
-  __shared__ double s_pose[6];   // current rvec, tvec
-  __shared__ double s_new[6];
-  __shared__ int s_flag;
-  __shared__ int s_best;
-  __shared__ double s_bestscore[kDsacThreads / 32];
-  __shared__ int s_bestidx[kDsacThreads / 32];
-
-  const int img = blockIdx.x;
-  const int cells = a.h * a.w;
-  const float* sc = stage_sc(a, img, smem_sc, cells);
-  uint8_t* flag_new = reinterpret_cast<uint8_t*>(smem_sc + (a.stage_smem ? 3 * cells : 0));
-  uint8_t* flag_acc = flag_new + cells;  // only used through counts; kept for clarity of the accepted inlier map
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double f = a.focal[img], cx = a.ppx[img], cy = a.ppy[img];
-  const float thr = a.p.inlier_threshold, max_reproj = a.p.max_reproj;
-  const int sub = a.p.subsample, half = a.p.subsample / 2;
-  const HypRec* recs = a.ws + (size_t)img * a.p.hyps;
-
-  // ---- argmax of the scores, first maximum wins (dsacstar_util.h:727-752 with training = false) ----
-  double bs = -1.0;
-  int bi = 0x7fffffff;
-  for (int hidx = tid; hidx < a.p.hyps; hidx += kDsacThreads) {
-    const double s = recs[hidx].score;
-    if (s == s && (bi == 0x7fffffff || s > bs)) { bs = s; bi = hidx; }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oi != 0x7fffffff && (bi == 0x7fffffff || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; }
-  }
-  if (lane == 0) { s_bestscore[warp] = bs; s_bestidx[warp] = bi; }
-  __syncthreads();
-  if (tid == 0) {
-    double b = s_bestscore[0];
-    int i0 = s_bestidx[0];
-    for (int w = 1; w < kDsacThreads / 32; ++w) {
-      const double os = s_bestscore[w];
-      const int oi = s_bestidx[w];
-      if (oi != 0x7fffffff && (i0 == 0x7fffffff || os > b || (os == b && oi < i0))) { b = os; i0 = oi; }
-    }
-    if (i0 == 0x7fffffff) i0 = 0;  // all scores NaN: the reference's draw() returns index 0
-    s_best = i0;
-    double rv[3];
-    rodrigues_inv(recs[i0].R, rv);
-    for (int k = 0; k < 3; ++k) { s_pose[k] = rv[k]; s_pose[3 + k] = recs[i0].t[k]; }
-    if (a.dbg.best) a.dbg.best[img] = i0;
-  }
-  __syncthreads();
-
-  int best_inliers = 4;   // dsacstar_util.h:537
-  int accepted_inliers = 0, rounds = 0;
-  for (int step = 0; step < a.p.max_refine_steps; ++step) {
-    // ---- inlier set of the current pose ----
-    double pose[6];
-    for (int k = 0; k < 6; ++k) pose[k] = s_pose[k];
-    double R[9];
-    rodrigues(pose, R);
-    double cnt[1] = {0};
-    for (int c = tid; c < cells; c += kDsacThreads) {
-      const int x = c % a.w, y = c / a.w;
-      float u, v;
-      project_pt(R, pose + 3, sc[c], sc[cells + c], sc[2 * cells + c], f, cx, cy, u, v);
-      const float e = repro_err((float)(x * sub + half), (float)(y * sub + half), u, v, max_reproj);
-      const uint8_t in = e < thr;
-      flag_new[c] = in;
-      cnt[0] += in;
-    }
-    block_sum<1>(cnt, s_part, s_out);
-    const int n_in = (int)(s_out[0] + 0.5);
-    if (n_in <= best_inliers) break;  // converged (dsacstar_util.h:561-563)
-    best_inliers = n_in;
-
-    // ---- Levenberg-Marquardt on the inliers (OpenCV CvLevMarq semantics) ----
-    // state: param = pose; prevParam; lambdaLg10 = -3; iters = 0
-    double param[6], prev[6];
-    for (int k = 0; k < 6; ++k) param[k] = pose[k];
-    int lambda_lg10 = -3, iters = 0;
-    double prev_err_norm = 0;
-    bool fail = false;
-    for (;;) {
-      // CALC_J: J^T J, J^T err, |err|^2 at param
-      double Rp[9], dR[3][9];
-      rodrigues(param, Rp);
-      rodrigues_jac(param, Rp, dR);
-      double acc[28];
-#pragma unroll
-      for (int k = 0; k < 28; ++k) acc[k] = 0;
-      for (int c = tid; c < cells; c += kDsacThreads) {
-        if (!flag_new[c]) continue;
-        const double X = sc[c], Y = sc[cells + c], Z = sc[2 * cells + c];
-        const int x = c % a.w, y = c / a.w;
-        const double xc = Rp[0] * X + Rp[1] * Y + Rp[2] * Z + param[3];
-        const double yc = Rp[3] * X + Rp[4] * Y + Rp[5] * Z + param[4];
-        const double zc = Rp[6] * X + Rp[7] * Y + Rp[8] * Z + param[5];
-        const double iz = zc ? 1.0 / zc : 1.0;
-        const double ex = xc * iz * f + cx - (double)(x * sub + half);
-        const double ey = yc * iz * f + cy - (double)(y * sub + half);
-        double Ju[6], Jv[6];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const double dx = dR[i][0] * X + dR[i][1] * Y + dR[i][2] * Z;
-          const double dy = dR[i][3] * X + dR[i][4] * Y + dR[i][5] * Z;
-          const double dz = dR[i][6] * X + dR[i][7] * Y + dR[i][8] * Z;
-          Ju[i] = f * iz * (dx - xc * iz * dz);
-          Jv[i] = f * iz * (dy - yc * iz * dz);
-        }
-        Ju[3] = f * iz; Ju[4] = 0;      Ju[5] = -f * xc * iz * iz;
-        Jv[3] = 0;      Jv[4] = f * iz; Jv[5] = -f * yc * iz * iz;
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = i; j < 6; ++j) acc[k++] += Ju[i] * Ju[j] + Jv[i] * Jv[j];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) acc[21 + i] += Ju[i] * ex + Jv[i] * ey;
-        acc[27] += ex * ex + ey * ey;
-      }
-      block_sum<28>(acc, s_part, s_out);
-      double JtJ[6][6], JtE[6];
-      {
-        int k = 0;
-        for (int i = 0; i < 6; ++i)
-          for (int j = i; j < 6; ++j) { JtJ[i][j] = s_out[k]; JtJ[j][i] = s_out[k]; ++k; }
-        for (int i = 0; i < 6; ++i) JtE[i] = s_out[21 + i];
-      }
-      const double err_at_param = sqrt(s_out[27]);
-      if (iters == 0) prev_err_norm = err_at_param;
-      for (int k = 0; k < 6; ++k) prev[k] = param[k];
-      // step(); CHECK_ERR with lambda escalation
-      double err_norm = 0;
-      for (;;) {
-        if (tid == 0) {
-          double A[6][6], bb[6], dx[6];
-          const double lambda = exp((double)lambda_lg10 * 2.302585092994046);
-          for (int i = 0; i < 6; ++i) {
-            for (int j = 0; j < 6; ++j) A[i][j] = JtJ[i][j];
-            A[i][i] *= 1.0 + lambda;
-            bb[i] = JtE[i];
-          }
-          const bool okk = solve6(A, bb, dx);
-          s_flag = okk ? 1 : 0;
-          for (int k = 0; k < 6; ++k) s_new[k] = okk ? prev[k] - dx[k] : prev[k];
-        }
-        __syncthreads();
-        if (!s_flag) { fail = true; }
-        for (int k = 0; k < 6; ++k) param[k] = s_new[k];
-        if (fail) break;
-        // error at the new parameters
-        double Rn[9];
-        rodrigues(param, Rn);
-        double e2[1] = {0};
-        for (int c = tid; c < cells; c += kDsacThreads) {
-          if (!flag_new[c]) continue;
-          const double X = sc[c], Y = sc[cells + c], Z = sc[2 * cells + c];
-          const int x = c % a.w, y = c / a.w;
-          const double xc = Rn[0] * X + Rn[1] * Y + Rn[2] * Z + param[3];
-          const double yc = Rn[3] * X + Rn[4] * Y + Rn[5] * Z + param[4];
-          const double zc = Rn[6] * X + Rn[7] * Y + Rn[8] * Z + param[5];
-          const double iz = zc ? 1.0 / zc : 1.0;
-          const double ex = xc * iz * f + cx - (double)(x * sub + half);
-          const double ey = yc * iz * f + cy - (double)(y * sub + half);
-          e2[0] += ex * ex + ey * ey;
-        }
-        block_sum<1>(e2, s_part, s_out);
-        err_norm = sqrt(s_out[0]);
-        if (err_norm > prev_err_norm && ++lambda_lg10 <= 16) continue;  // retry with a larger damping
-        break;
-      }
-      if (fail) break;
-      lambda_lg10 = max(lambda_lg10 - 1, -16);
-      double dn = 0, pn = 0;
-      for (int k = 0; k < 6; ++k) { dn += (param[k] - prev[k]) * (param[k] - prev[k]); pn += prev[k] * prev[k]; }
-      ++iters;
-      if (iters >= 20 || sqrt(dn) < 1.1920929e-07 * sqrt(pn) || !isfinite(err_norm)) break;
-      prev_err_norm = err_norm;
-    }
-    bool finite = true;
-    for (int k = 0; k < 6; ++k) finite &= isfinite(param[k]);
-    if (fail || !finite) break;  // "abort if PnP fails" (dsacstar_util.h:570-581)
-    __syncthreads();
-    if (tid == 0)
-      for (int k = 0; k < 6; ++k) s_pose[k] = param[k];
-    for (int c = tid; c < cells; c += kDsacThreads) flag_acc[c] = flag_new[c];
-    accepted_inliers = n_in;
-    ++rounds;
-    __syncthreads();
-  }
-
-  // ---- camera->world 4x4 = inverse of [R|t] (dsacstar_util.h:759-770, dsacstar.cpp:177-182) ----
-  if (tid == 0) {
-    double pose[6], R[9];
-    for (int k = 0; k < 6; ++k) pose[k] = s_pose[k];
-    rodrigues(pose, R);
-    float* o = a.out_pose + (size_t)img * 16;
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j) o[i * 4 + j] = (float)R[j * 3 + i];
-      o[i * 4 + 3] = (float)(-(R[0 * 3 + i] * pose[3] + R[1 * 3 + i] * pose[4] + R[2 * 3 + i] * pose[5]));
-    }
-    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
-    a.out_inliers[img] = accepted_inliers;
-    if (a.dbg.refine_rounds) a.dbg.refine_rounds[img] = rounds;
-  }
+#include "dsac_refine_body.inc"
+}
+// ACEZ_DSAC_OCC=1 (experimental): 128 registers (235 otherwise, ~700 B of spills): two CTAs per SM instead of one.
+__global__ void __launch_bounds__(kDsacThreads, 2) dsac_refine_kernel_occ2(const DsacArgs a) {
+#include "dsac_refine_body.inc"
 }
 
 }  // namespace acez
@@ -698,6 +391,23 @@ extern "C" int acez_dsac_forward_rgb_batch(const float* sc, int n, int h, int w,
   const int want = (2 * sm_count() + n - 1) / n;
   if (chunks > want) chunks = want < 1 ? 1 : want;
   dim3 grid1(chunks, n);
+  static const bool occ = [] {
+    const char* e = getenv("ACEZ_DSAC_OCC");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (occ) {
+    static bool configured_occ = false;
+    if (!configured_occ) {
+      ACEZ_CUDA(cudaFuncSetAttribute(dsac_sample_score_kernel_occ3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      ACEZ_CUDA(cudaFuncSetAttribute(dsac_refine_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      configured_occ = true;
+    }
+    dsac_sample_score_kernel_occ3<<<grid1, kDsacThreads, smem1, s>>>(a);
+    ACEZ_CUDA(cudaGetLastError());
+    dsac_refine_kernel_occ2<<<n, kDsacThreads, smem2, s>>>(a);
+    ACEZ_CUDA(cudaGetLastError());
+    return ACEZ_OK;
+  }
   dsac_sample_score_kernel<<<grid1, kDsacThreads, smem1, s>>>(a);
   ACEZ_CUDA(cudaGetLastError());
   dsac_refine_kernel<<<n, kDsacThreads, smem2, s>>>(a);

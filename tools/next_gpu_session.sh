@@ -65,6 +65,14 @@ stamp "fc3 overlap tests rc=$?"; tail -n 2 gpurun_out/next_fc3ov_tests.log >> $S
 ACEZ_FC3_OVERLAP=1 timeout 100 python tools/probe_step_breakdown.py > gpurun_out/next_breakdown_fc3ov.log 2>&1
 stamp "breakdown fc3 overlap rc=$?"; cat gpurun_out/next_breakdown_fc3ov.log >> $S
 
+# 3b3. DSAC* kernels at higher occupancy (80 / 128 registers)
+ACEZ_DSAC_OCC=1 timeout 200 python -m pytest tests/test_dsac_gpu.py -m gpu -x -q > gpurun_out/next_dsac_occ_tests.log 2>&1
+stamp "DSAC occupancy variant tests rc=$?"; tail -n 2 gpurun_out/next_dsac_occ_tests.log >> $S
+for v in 0 1; do
+  ACEZ_DSAC_OCC=$v timeout 100 python tools/probe_dsac_time.py > gpurun_out/next_dsac_occ$v.log 2>&1
+  stamp "DSAC probe occ=$v rc=$?"; tail -n 6 gpurun_out/next_dsac_occ$v.log >> $S
+done
+
 # 3c. optimiser state (34 MB) pinned in L2
 ACEZ_L2_PERSIST=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_l2_tests.log 2>&1
 stamp "L2 persistence tests rc=$?"; tail -n 2 gpurun_out/next_l2_tests.log >> $S
