@@ -52,14 +52,14 @@ class HeadEngine:
         if self._l2_persist:
             # experimental: ONE allocation for params | grads (+4) | exp_avg | exp_avg_sq so that a single L2 persistence
             # window covers the optimiser state (set by `enable_l2_persistence` on the stream the step runs on)
-            n, pad = self.n_params, (-self.n_params) % 64
+            n, pad = self.n_params, (-self.n_params) % 64 + 64   # >= 4 spare floats behind every section
             self._opt_pool = torch.zeros(4 * (n + pad) + 64, device=self.device, dtype=torch.float32)
             off = [i * (n + pad) for i in range(4)]
             self.params = self._opt_pool[off[0]:off[0] + n]
             self.grads_full = self._opt_pool[off[1]:off[1] + n + 4]
             self.grads = self.grads_full[:n]
             self.exp_avg = self._opt_pool[off[2]:off[2] + n]
-            self.exp_avg_sq = self._opt_pool[off[3] + 64:off[3] + 64 + n]   # (+64: clear of the 4 spare gradient slots)
+            self.exp_avg_sq = self._opt_pool[off[3]:off[3] + n]
         else:
             self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
             # 4 spare floats behind the gradient: data-parallel runs carry the GradScaler flag through the SAME all-reduce
