@@ -192,6 +192,9 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
   const bool relaxed_free = (args.flags & 1) != 0;
   const bool abl_xchg = (args.flags & 2) != 0, abl_store = (args.flags & 4) != 0, abl_w = (args.flags & 8) != 0;
   const bool abl_opnd = (args.flags & 16) != 0, abl_box = (args.flags & 32) != 0;
+  // V3 sub-switches (to attribute its gain): 128 = own boxes published whole (no halves), 256 = own-first k-block order
+  const bool v3_halves = V3 && (args.flags & 128) == 0;
+  const bool v3_arrival = V3 && (args.flags & 256) == 0;
   long long* dbg = args.dbg != nullptr ? args.dbg + (size_t)blockIdx.x * kChainDbgSlots : nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -223,7 +226,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       for (int i = 0; i < kKB; ++i) {
-        const int j = V3 ? chunk_order_v3(i, rank) : chunk_order(i, rank);
+        const int j = v3_arrival ? chunk_order_v3(i, rank) : chunk_order(i, rank);
         mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
       }
@@ -232,7 +235,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       for (int s = 0; s < n_steps; ++s) {
         const int wl = args.step[s].w_layer;
         for (int i = 0; i < kKB; ++i) {
-          const int j = V3 ? chunk_order_v3(i, rank) : chunk_order(i, rank);
+          const int j = v3_arrival ? chunk_order_v3(i, rank) : chunk_order(i, rank);
           chain_wait(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           if (abl_w) { mbar_arrive(&b_full[stage]); if (++stage == kBStages) { stage = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&b_full[stage], kBStage);
@@ -261,13 +264,13 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
       const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
       if constexpr (V3) {
         for (int i = 0; i < kKB; ++i) {
-          const int j = chunk_order_v3(i, rank);
-          const bool is_peer = (i & 2) != 0;
-          const int b = ((i >> 2) << 1) | (i & 1);  // box index inside its owner's half
-          const bool halves = !is_peer && s > 0;     // own boxes written by the epilogue arrive in two 32-column halves
+          const int j = v3_arrival ? chunk_order_v3(i, rank) : chunk_order(i, rank);
+          const bool is_peer = v3_arrival ? (i & 2) != 0 : i >= 4;
+          const int b = j & 3;                        // box index inside its owner's half
+          const bool halves = v3_halves && !is_peer && s > 0;  // own boxes written by the epilogue arrive in two 32-column halves
           if (halves) chain_wait(&a_half[b], (uint32_t)((s - 1) & 1), (6u << 16) | ((uint32_t)s << 8) | (uint32_t)b);
           else chain_wait(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
-          if (dbg && lane == 0 && (i == 0 || i == 2 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 2 ? 1 : 2))] = clock64();
+          if (dbg && lane == 0 && (i == 0 || i == (v3_arrival ? 2 : 4) || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 7 ? 2 : 1))] = clock64();
           // a peer box: arm the next phase (the peer's copy of step s lands with complete_tx; order is irrelevant)
           if (is_peer && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
           chain_wait(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
@@ -476,7 +479,7 @@ head_chain_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constan
             }
             *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
           }
-          if (hf == 0 && !last) {
+          if (hf == 0 && !last && v3_halves) {
             // first 32 columns of the box (k-steps 0, 1 of the next layer's k-block j) are in place: let the UMMAs start
             tcgen05_fence_before();
             fence_proxy_async();
@@ -670,6 +673,8 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
     C->args.flags = (e == nullptr || atoi(e) != 0) ? 1 : 0;
     const char* a = getenv("ACEZ_CHAIN_ABLATE");  // timing ablations (wrong results), see head_chain.cuh
     if (a != nullptr) C->args.flags |= atoi(a) & 62;
+    const char* v = getenv("ACEZ_CHAIN_V3_OPTS");  // V3 sub-switches: 1 = no half-box publication, 2 = own-first k-block order
+    if (v != nullptr) C->args.flags |= (atoi(v) & 3) << 7;
   }
   return ACEZ_OK;
 }

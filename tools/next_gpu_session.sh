@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next session: validates every opt-in experiment written without GPU time at the end of round 1.
-#   gpurun --timeout 900 -- 'bash tools/next_gpu_session.sh'          (about 5-6 minutes of run time, one GPU)
+#   gpurun --timeout 900 -- 'bash tools/next_gpu_session.sh'          (about 12-15 minutes of run time, one GPU)
 # Everything lands in gpurun_out/next_*.{log,txt}; the summary is printed at the end. Ordered by value.
 set +e
 mkdir -p gpurun_out
@@ -25,6 +25,10 @@ if [ $rc_v3 -ne 0 ]; then
 fi
 ACEZ_CHAIN_V3=1 ACEZ_PROBE_COMBOS="1:0" timeout 100 python tools/probe_chain_time.py > gpurun_out/next_v3_probe.log 2>&1
 stamp "chain V3 probe rc=$?"; cat gpurun_out/next_v3_probe.log >> $S
+for o in 1 2 3; do   # attribute the V3 gain: 1 = no half-box publication, 2 = own-first k-block order, 3 = both off (diet only)
+  ACEZ_CHAIN_V3=1 ACEZ_CHAIN_V3_OPTS=$o ACEZ_PROBE_COMBOS="1:0" timeout 100 python tools/probe_chain_time.py > gpurun_out/next_v3_probe_o$o.log 2>&1
+  stamp "chain V3 probe, V3_OPTS=$o rc=$?"; head -n 2 gpurun_out/next_v3_probe_o$o.log >> $S
+done
 ACEZ_PROBE_COMBOS="1:0" timeout 100 python tools/probe_chain_time.py > gpurun_out/next_v2_probe.log 2>&1
 stamp "chain v2 probe (same box) rc=$?"; head -n 3 gpurun_out/next_v2_probe.log >> $S
 
