@@ -77,6 +77,10 @@ for v in 0 1; do
   stamp "DSAC probe occ=$v rc=$?"; tail -n 6 gpurun_out/next_dsac_occ$v.log >> $S
 done
 
+# 3b4. buffer-fill rate (encoder + sampling + scatter), the number DESIGN.md section 7 lists as missing
+timeout 200 python tools/bench_buffer_fill.py 64 4 > gpurun_out/next_buffer_fill.log 2>&1
+stamp "buffer fill rc=$?"; tail -n 2 gpurun_out/next_buffer_fill.log >> $S
+
 # 3c. optimiser state (34 MB) pinned in L2
 ACEZ_L2_PERSIST=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_l2_tests.log 2>&1
 stamp "L2 persistence tests rc=$?"; tail -n 2 gpurun_out/next_l2_tests.log >> $S
