@@ -80,6 +80,10 @@ done
 # 3b4. buffer-fill rate (encoder + sampling + scatter), the number DESIGN.md section 7 lists as missing
 timeout 200 python tools/bench_buffer_fill.py 64 4 > gpurun_out/next_buffer_fill.log 2>&1
 stamp "buffer fill rc=$?"; tail -n 2 gpurun_out/next_buffer_fill.log >> $S
+ACEZ_FILL_BATCH=8 timeout 200 python -m pytest tests/test_stage_gpu.py -m gpu -x -q > gpurun_out/next_fill_batch_tests.log 2>&1
+stamp "batched buffer fill: stage tests (bit-exact indices, mapping + registration) rc=$?"; tail -n 2 gpurun_out/next_fill_batch_tests.log >> $S
+ACEZ_FILL_BATCH=8 timeout 200 python tools/bench_buffer_fill.py 64 4 > gpurun_out/next_buffer_fill_b8.log 2>&1
+stamp "buffer fill, batches of 8 rc=$?"; tail -n 2 gpurun_out/next_buffer_fill_b8.log >> $S
 
 # 3c. optimiser state (34 MB) pinned in L2
 ACEZ_L2_PERSIST=1 timeout 150 python -m pytest tests/test_head_gpu.py -m gpu -x -q > gpurun_out/next_l2_tests.log 2>&1
