@@ -1011,8 +1011,10 @@ extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = 8 * sm_count();
-  if (use_scaler == 1) {  // 2 = the caller's flag already covers every gradient (acez_head_train_fwd_bwd does)
-    rc = launch_pdl(grad_check_kernel, dim3(grid), dim3(256), 0, s, false, grads, n, found_inf_dev);
+  if (use_scaler == 1 || use_scaler == 3) {  // 2 = the caller's flag already covers every gradient (acez_head_train_fwd_bwd does)
+    // 3 (data parallel, experimental): one more element behind the gradient is checked too - the slot in which the ranks'
+    // local GradScaler flags travelled through the all-reduce (+inf when any rank overflowed)
+    rc = launch_pdl(grad_check_kernel, dim3(grid), dim3(256), 0, s, false, grads, n + (use_scaler == 3 ? 1 : 0), found_inf_dev);
     if (rc) return rc;
   }
   rc = launch_pdl(adamw_kernel, dim3(grid), dim3(256), 0, s, false, params, grads, exp_avg, exp_avg_sq, n, hyper_dev,

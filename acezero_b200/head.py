@@ -244,11 +244,13 @@ class HeadEngine:
         self.hyper.copy_(h, non_blocking=True)
         ev.record()
 
-    def adamw_step(self, use_scaler=True, flag_complete=True, stream=None):
-        """flag_complete: found_inf already covers all gradients (true after train_fwd_bwd)."""
+    def adamw_step(self, use_scaler=True, flag_complete=True, stream=None, check_flag_slot=False):
+        """flag_complete: found_inf already covers all gradients (true after train_fwd_bwd).
+        check_flag_slot (data parallel, experimental): the check pass also covers grads_full[n_params], the slot the ranks'
+        local flags travelled in (+inf when set), so no separate unpack kernels are needed."""
         rc = self.lib.acez_adamw_step(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.exp_avg),
                                       _lib.ptr(self.exp_avg_sq), self.n_params, _lib.ptr(self.hyper),
                                       _lib.ptr(self.scaler_state), _lib.ptr(self.found_inf),
-                                      (2 if flag_complete else 1) if use_scaler else 0, self.plan,
+                                      (2 if flag_complete else (3 if check_flag_slot else 1)) if use_scaler else 0, self.plan,
                                       _lib.stream_ptr(stream))
         _lib.check(rc, "acez_adamw_step")

@@ -229,6 +229,7 @@ int acez_buffer_fill(const void* feat_rows, const int64_t* sample_idx, int n_sam
  *   found_inf_dev    int: OR-ed with the grads' non-finite / fp16-overflow check; must already hold the activation-
  *                    gradient overflow flag of acez_head_train_fwd_bwd (same pointer). Not cleared by this call.
  *   use_scaler       0: plain AdamW (use_half False): no check, no unscale, no skip; 1: check grads here;
+ *                    3: like 1, and grads[n] (one spare element behind the gradient: the data-parallel flag slot) is checked too
  *                    2: found_inf_dev is already complete (acez_head_train_fwd_bwd folds the check of every gradient
  *                    into the kernels that produce it), no extra pass over the gradients
  *   scaler_state_dev[3] is a completion counter used by the kernel (keep it 0).

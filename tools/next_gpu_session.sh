@@ -100,5 +100,6 @@ timeout 150 python bench.py --steps 300 --warmup 5 --no-cpu-baseline > gpurun_ou
 stamp "bench default rc=$?"; cut -c1-400 gpurun_out/next_bench_default.json >> $S
 stamp done
 cat $S
-# Data parallel (costs 2x): gpurun --gpus 2 --timeout 600 -- 'for g in 0 1; do ACEZ_DP_ONE_GRAPH=$g python -m torch.distributed.run --nnodes=1 \
-#   --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 --warmup 5 > gpurun_out/next_dp2_onegraph$g.json; done'
+# Data parallel (costs 2x): gpurun --gpus 2 --timeout 600 -- 'for g in "0 0" "1 0" "1 1"; do set -- $g; ACEZ_DP_ONE_GRAPH=$1 ACEZ_DP_FUSED_FLAG=$2 \
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 \
+#   --warmup 5 > gpurun_out/next_dp2_graph$1_flag$2.json; done; python tools/check_dp.py'   (tools/check_dp.py: 1-GPU vs 2-GPU trajectories)
