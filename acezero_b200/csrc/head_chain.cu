@@ -646,14 +646,8 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)kC, (uint64_t)L};
-    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)kC * kC * 2};
-    uint32_t box[3] = {64, (uint32_t)(mode == CHAIN_FWD ? CN / 2 : 64), 1};
-    rc = make_tensor_map(&C->tmW4, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, W16, dims, strides, box, nullptr,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-  }
+  C->w16 = W16;
+  C->n_layers = L;
   {
     uint64_t dims[3] = {(uint64_t)kC, (uint64_t)rows, (uint64_t)out_slots};
     uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)out_zstride * 2};

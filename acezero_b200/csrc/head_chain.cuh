@@ -49,7 +49,8 @@ struct ChainLaunch {
   CUtensorMap tmIn;   // first A tile: [rows, 512], box {64, 128, 1}
   CUtensorMap tmW;    // W16 [L][512][512]: FWD box {64, 256, 1} (K-major B), DGRAD box {64, 64, 1} (MN-major B)
   CUtensorMap tmOut;  // [slots][rows][512], box {64, 128, 1}
-  CUtensorMap tmW4;   // head_chain4.cu (experimental): FWD box {64, 128, 1} (this CTA's half of a weight k-block), DGRAD box {64, 64, 1}
+  const __half* w16;  // the weight array and layer count tmW was built from (head_chain4.cu encodes its own map lazily, so
+  int n_layers;       // that the default path executes no code of the experimental one)
   ChainArgs args;
   int mode;
 };

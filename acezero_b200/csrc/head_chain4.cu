@@ -420,6 +420,15 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4));
     configured = true;
   }
+  // weight map of this variant: FWD box {64, 128, 1} (this CTA's half of a K-major weight k-block), DGRAD box {64, 64, 1}
+  CUtensorMap tmW4;
+  {
+    uint64_t dims[3] = {(uint64_t)kC, (uint64_t)kC, (uint64_t)C.n_layers};
+    uint64_t strides[2] = {(uint64_t)kC * 2, (uint64_t)kC * kC * 2};
+    uint32_t box[3] = {64, (uint32_t)(MODE == CHAIN_FWD ? CN / 2 : 64), 1};
+    int rc = make_tensor_map(&tmW4, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, C.w16, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
   const int tiles = (C.args.rows + CM - 1) / CM;
   const int clusters = (tiles + 1) / 2;
   cudaLaunchConfig_t cfg{};
@@ -434,7 +443,7 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, C.tmW4, C.tmOut, C.args));
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, tmW4, C.tmOut, C.args));
   return ACEZ_OK;
 }
 
