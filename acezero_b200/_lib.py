@@ -64,7 +64,7 @@ class DsacParams(C.Structure):
     _fields_ = [
         ("hyps", C.c_int), ("inlier_threshold", C.c_float), ("inlier_alpha", C.c_float), ("max_reproj", C.c_float),
         ("subsample", C.c_int), ("seed", C.c_uint64), ("max_tries", C.c_int), ("max_refine_steps", C.c_int),
-        ("image_index_base", C.c_int),
+        ("image_index_base", C.c_int), ("image_index", C.c_void_p),
     ]
 
 

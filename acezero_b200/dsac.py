@@ -24,9 +24,12 @@ def _as_dev_f32(v, n, device):
 
 def forward_rgb_batch(scene_coordinates, focal, ppx, ppy, hyps=64, inlier_threshold=10.0, inlier_alpha=100.0,
                       max_reproj=100.0, subsample=8, seed=0, max_tries=1000000, injected_idx=None,
-                      image_index_base=0, max_refine_steps=MAX_REF_STEPS, debug=False, stream=None):
+                      image_index_base=0, max_refine_steps=MAX_REF_STEPS, debug=False, stream=None, image_index=None):
     """scene_coordinates: CUDA float32 [n,3,h,w]. Returns (poses [n,4,4] float32 cam->world, inliers [n] int32)
-    on the device (+ a dict of per-hypothesis intermediates when debug=True). No host synchronisation."""
+    on the device (+ a dict of per-hypothesis intermediates when debug=True). No host synchronisation.
+
+    The sampling RNG of image i is keyed by `image_index[i]` (sequence / tensor of n ints, any order — e.g. the dataset
+    indices of a shuffled micro-batch) or, without it, by `image_index_base + i`."""
     lib = _lib.load()
     sc = scene_coordinates
     if not (torch.is_tensor(sc) and sc.is_cuda and sc.dim() == 4 and sc.shape[1] == 3):
@@ -41,8 +44,15 @@ def forward_rgb_batch(scene_coordinates, focal, ppx, ppy, hyps=64, inlier_thresh
     inliers = torch.empty((n,), device=dev, dtype=torch.int32)
     ws_bytes = lib.acez_dsac_workspace_bytes(n, h, w, hyps)
     ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    idx_t = None
+    if image_index is not None:
+        idx_t = image_index if torch.is_tensor(image_index) else torch.as_tensor(list(image_index), dtype=torch.int32)
+        idx_t = idx_t.to(device=dev, dtype=torch.int32, non_blocking=True).reshape(-1).contiguous()
+        if idx_t.numel() != n:
+            raise ValueError(f"image_index must have {n} entries")
     p = _lib.DsacParams(hyps, inlier_threshold, inlier_alpha, max_reproj, subsample, int(seed) & 0xFFFFFFFFFFFFFFFF,
-                        int(min(max_tries, 2**31 - 1)), max_refine_steps, image_index_base)
+                        int(min(max_tries, 2**31 - 1)), max_refine_steps, image_index_base,
+                        idx_t.data_ptr() if idx_t is not None else None)
     inj = None
     if injected_idx is not None:
         inj = torch.as_tensor(injected_idx, dtype=torch.int32).to(dev).contiguous()
@@ -70,25 +80,33 @@ def forward_rgb_batch(scene_coordinates, focal, ppx, ppy, hyps=64, inlier_thresh
     return poses, inliers
 
 
-_call_counter = 0
+def content_key(sc):
+    """31-bit RNG key that is a pure function of a scene-coordinate map's bits (device tensor [n], no host sync)."""
+    n = sc.shape[0]
+    return (sc.contiguous().view(torch.int32).reshape(n, -1).sum(dim=1, dtype=torch.int64) & 0x7FFFFFFF).to(torch.int32)
 
 
 def forward_rgb(sceneCoordinates, outPose, ransacHypotheses, inlierThreshold, focalLength, ppointX, ppointY,
-                inlierAlpha, maxReproj, subSampling, randomSeed, max_hypotheses_tries):
+                inlierAlpha, maxReproj, subSampling, randomSeed, max_hypotheses_tries, image_index=None):
     """Drop-in for the reference's `dsacstar.forward_rgb` (all-positional call at register_mapping.py:229-242).
 
     sceneCoordinates: [1,3,H,W] float32, CPU (as the reference passes it) or CUDA; outPose: [4,4] float32 written in
-    place (camera->world); returns the inlier count as a Python int. Silent on stdout. The reference applies its
-    seed only on the first call of a process (thread_rand.cpp:17) and then continues one RNG stream; here every call
-    is keyed by (randomSeed, number of previous calls) so successive frames still draw different samples.
+    place (camera->world); returns the inlier count as a Python int. Silent on stdout.
+
+    The reference applies its seed only on the first call of a process (thread_rand.cpp:17) and then continues one RNG
+    stream, so its result depends on the call history. Here the result is a pure function of the arguments: the
+    sampling RNG is keyed by (randomSeed, image key), the key being `image_index` when the caller passes it (extension,
+    keyword only) and otherwise a checksum of the scene-coordinate bits — the same image and seed give the same pose
+    in any call order, in any process, on any number of GPUs.
     """
-    global _call_counter
     if sceneCoordinates.dim() != 4 or sceneCoordinates.shape[0] != 1:
         raise RuntimeError("sceneCoordinates must be 1x3xHxW (only batch size 1 is supported by this entry point)")
     sc = sceneCoordinates if sceneCoordinates.is_cuda else sceneCoordinates.cuda(non_blocking=True)
+    if sc.dtype != torch.float32:
+        raise RuntimeError(f"expected scalar type Float but found {sc.dtype}")
+    key = content_key(sc) if image_index is None else [int(image_index)]
     poses, inl = forward_rgb_batch(sc, float(focalLength), float(ppointX), float(ppointY), int(ransacHypotheses),
                                    float(inlierThreshold), float(inlierAlpha), float(maxReproj), int(subSampling),
-                                   int(randomSeed), int(max_hypotheses_tries), image_index_base=_call_counter)
-    _call_counter += 1
+                                   int(randomSeed), int(max_hypotheses_tries), image_index=key)
     outPose.copy_(poses[0].to(outPose.device))
     return int(inl.item())

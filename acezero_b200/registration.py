@@ -27,23 +27,14 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
         f = K[:, 0, 0].contiguous()
         with torch.no_grad():
             sc = network(imgs).float().contiguous()                   # [n,3,h,w] stays on the device
-        # one launch for the whole micro-batch when indices are consecutive-keyed: key image j by its dataset index
+        # ONE DSAC* launch pair per micro-batch in any image order (the loader of register_mapping.py:147 shuffles):
+        # the RNG of image j is keyed by its dataset index through the per-image key array of the C ABI
         idx = [int(p[3]) for p in pending]
-        if all(idx[j] == idx[0] + j for j in range(len(idx))):
-            poses, inl = dsac.forward_rgb_batch(sc, f, K[:, 0, 2].contiguous(), K[:, 1, 2].contiguous(), hypotheses,
-                                                threshold, inlier_alpha, max_pixel_error, network.OUTPUT_SUBSAMPLE,
-                                                base_seed, max_tries, image_index_base=idx[0])
-        else:
-            ps, ns = [], []
-            for j in range(len(idx)):
-                pj, nj = dsac.forward_rgb_batch(sc[j:j + 1], f[j:j + 1], K[j:j + 1, 0, 2].contiguous(),
-                                                K[j:j + 1, 1, 2].contiguous(), hypotheses, threshold, inlier_alpha,
-                                                max_pixel_error, network.OUTPUT_SUBSAMPLE, base_seed, max_tries,
-                                                image_index_base=idx[j])
-                ps.append(pj); ns.append(nj)
-            poses, inl = torch.cat(ps), torch.cat(ns)
+        poses, inl = dsac.forward_rgb_batch(sc, f, K[:, 0, 2].contiguous(), K[:, 1, 2].contiguous(), hypotheses,
+                                            threshold, inlier_alpha, max_pixel_error, network.OUTPUT_SUBSAMPLE,
+                                            base_seed, max_tries, image_index=idx)
         for j, p in enumerate(pending):
-            results.append({"file": p[2], "index": int(p[3]), "pose": poses[j], "inliers": inl[j], "focal": float(f[j])})
+            results.append({"file": p[2], "index": int(p[3]), "pose": poses[j], "inliers": inl[j], "focal": p[4]})
         pending.clear()
 
     count = 0
@@ -55,7 +46,10 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
                 continue
             Kb = K[b]
             assert torch.allclose(Kb[0, 0], Kb[1, 1]), "a single focal length is supported (register_mapping.py:219)"
-            item = (image[b:b + 1], Kb.to(device), filenames[b] if not isinstance(filenames, str) else filenames, i)
+            # focal from the CPU copy of K (no device read-back per image)
+            focal = float(Kb[0, 0])
+            item = (image[b:b + 1], Kb.to(device, non_blocking=True),
+                    filenames[b] if not isinstance(filenames, str) else filenames, i, focal)
             if pending and (pending[0][0].shape != item[0].shape or len(pending) >= micro_batch):
                 flush()
             pending.append(item)

@@ -245,9 +245,10 @@ int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
  *                        focalLength, ppointX, ppointY, inlierAlpha, maxReproj, subSampling, randomSeed,
  *                        max_hypotheses_tries) -> int inliers          (dsacstar/dsacstar.cpp:66-186, 898-899)
  * batched over n images, device pointers, per-image intrinsics.
- *   - sampling RNG: counter-based, keyed (seed, image index + image_index_base, hypothesis, try, draw) — results do
- *     not depend on batch composition or GPU count (the reference's mt19937-per-OMP-thread stream is not
- *     reproducible across machines);
+ *   - sampling RNG: counter-based, keyed (seed, image key, hypothesis, try, draw) with image key = image_index[i] when
+ *     that array is given (any order: a shuffled micro-batch of register_mapping.py:147 is ONE launch), else
+ *     image_index_base + i — results do not depend on batch composition or GPU count (the reference's
+ *     mt19937-per-OMP-thread stream is not reproducible across machines);
  *   - injected_idx (nullable) int32 [n, hyps, 4, 2] = (x, y) cell of each of the 4 correspondences: overrides the
  *     RNG and disables retries (parity tests feed the oracle's minimal sets);
  *   - out_pose: camera->world 4x4 row-major float (dsacstar.cpp:177-182); out_inliers: size of the inlier set the
@@ -262,7 +263,8 @@ typedef struct acez_dsac_params {
   uint64_t seed;
   int max_tries;
   int max_refine_steps;   /* reference MAX_REF_STEPS = 100 (dsacstar.cpp:47) */
-  int image_index_base;   /* added to the in-batch image index for RNG keying */
+  int image_index_base;   /* added to the in-batch image index for RNG keying (used when image_index is NULL) */
+  const int* image_index; /* nullable, device int32 [n]: RNG key of image i (dataset index), overrides image_index_base + i */
 } acez_dsac_params;
 
 typedef struct acez_dsac_debug { /* all nullable; device pointers */

@@ -12,11 +12,12 @@ from oracle import dsacstar_ref as D
 pytestmark = pytest.mark.gpu
 
 
-def _run(sc, f, px, py, hyps, seed, max_tries, injected=None, image_index_base=0):
+def _run(sc, f, px, py, hyps, seed, max_tries, injected=None, image_index_base=0, image_index=None):
     from acezero_b200 import dsac
     t = torch.from_numpy(np.ascontiguousarray(sc)).cuda()
     poses, inl, dbg = dsac.forward_rgb_batch(t, f, px, py, hyps, 10.0, 100.0, 100.0, 8, seed, max_tries,
-                                             injected_idx=injected, image_index_base=image_index_base, debug=True)
+                                             injected_idx=injected, image_index_base=image_index_base, debug=True,
+                                             image_index=image_index)
     torch.cuda.synchronize()
     return poses.cpu().numpy(), inl.cpu().numpy(), {k: v.cpu().numpy() for k, v in dbg.items()}
 
@@ -73,6 +74,35 @@ def test_batch_independence_and_image_keying():
     for i in (0, 3, 4):
         p1, i1, _ = _run(scs[i], 525.0, 320.0, 240.0, 64, 99, 16, image_index_base=i)
         assert np.array_equal(p1[0], poses[i]) and i1[0] == inl[i]
+
+
+def test_shuffled_micro_batch_is_one_launch_with_per_image_keys():
+    """The per-image key array of the C ABI (acez_dsac_params.image_index): a micro-batch in ANY image order (the loader
+    of register_mapping.py:147 shuffles) gives, image by image, the result of the in-order batch."""
+    scs = [D.synth_scene(s)[0] for s in (41, 42, 43, 44, 45, 46)]
+    poses, inl, dbg = _run(np.concatenate(scs, 0), 525.0, 320.0, 240.0, 64, 99, 16)
+    order = [4, 0, 5, 2, 1, 3]
+    keys = [100 + o for o in order]
+    p2, i2, d2 = _run(np.concatenate([scs[o] for o in order], 0), 525.0, 320.0, 240.0, 64, 99, 16, image_index=keys)
+    p3, i3, d3 = _run(np.concatenate(scs, 0), 525.0, 320.0, 240.0, 64, 99, 16, image_index_base=100)
+    for j, o in enumerate(order):
+        assert np.array_equal(p2[j], p3[o]) and i2[j] == i3[o]
+        assert np.array_equal(d2["hyp_tries"][j], d3["hyp_tries"][o])
+    # keys matter: base 0 and base 100 draw different minimal sets
+    assert not np.array_equal(dbg["hyp_tries"], d3["hyp_tries"])
+
+
+def test_positional_entry_point_is_a_pure_function_of_its_arguments():
+    """dsacstar.forward_rgb: same image + same seed => same pose, whatever was solved before in this process (the RNG is
+    keyed by (seed, checksum of the scene-coordinate bits), not by a call counter)."""
+    import dsacstar
+    a, b = D.synth_scene(51)[0], D.synth_scene(52)[0]
+    o1, o2, o3 = torch.zeros((4, 4)), torch.zeros((4, 4)), torch.zeros((4, 4))
+    n1 = dsacstar.forward_rgb(torch.from_numpy(a), o1, 64, 10, 525.0, 320.0, 240.0, 100, 100, 8, 2089, 16)
+    dsacstar.forward_rgb(torch.from_numpy(b), o2, 64, 10, 525.0, 320.0, 240.0, 100, 100, 8, 2089, 16)
+    n3 = dsacstar.forward_rgb(torch.from_numpy(a), o3, 64, 10, 525.0, 320.0, 240.0, 100, 100, 8, 2089, 16)
+    assert n1 == n3 and torch.equal(o1, o3)
+    assert not torch.equal(o1, o2)
 
 
 def test_reference_positional_entry_point():

@@ -1,8 +1,5 @@
 """Stress / scale cases of BASELINE.json configs[4] (10k frames, 1M-patch buffer, RANSAC sweep 64..4096 hypotheses) at
-sizes the oracles still finish in seconds. Opt-in (ACEZ_TEST_EXTRA=1): written at the end of round 1 without GPU time
-left, so they join the default `-m gpu` suite only after their first run on a GPU box."""
-import os
-
+sizes the oracles still finish in seconds."""
 import numpy as np
 import pytest
 import torch
@@ -10,8 +7,7 @@ import torch
 from oracle import ace_ref
 from oracle import dsacstar_ref as D
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ACEZ_TEST_EXTRA", "0") != "1", reason="extra stress cases (set ACEZ_TEST_EXTRA=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("hyps", [512, 4096])
