@@ -6,7 +6,10 @@ integer contract (image order, patch indices, epoch permutations), same output f
 
   create_training_buffer : encoder = tcgen05 implicit-GEMM plan, NHWC rows; `torch.multinomial` with the reference's CUDA
                            generator (bit-exact indices); one fused fill kernel per image instead of ~12 small kernels;
-                           the mask test runs on the CPU copy of the mask (no GPU sync per image)
+                           the mask test runs on the CPU copy of the mask (no GPU sync per image). With G ranks
+                           (torchrun, see acezero_b200/launch.py) rank r encodes every G-th image of the reference's loader
+                           order, every rank replays the sampling generator for all images (indices stay bit-exact) and
+                           the rows are all-gathered into the same replicated buffer a single GPU would build
   run_epoch/training_step: `acezero_b200.trainer.TrainLoop` — one CUDA graph per iteration, no host sync; with
                            `--pose_refinement naive|mlp` / `--refine_calibration` the refiners stay PyTorch-autograd
                            models fed by the kernel's dL/dP, dL/dK (eager launches)
@@ -24,9 +27,19 @@ from torch.utils.data import DataLoader, sampler
 from ace_network import Regressor
 from acezero_b200 import _lib
 from acezero_b200 import posefile
+from acezero_b200.encoder import out_hw as encoder_out_hw
+from acezero_b200.parallel import rows_capacity_per_rank
 from acezero_b200.trainer import TrainLoop, BUFFER_KEYS
 
 _logger = logging.getLogger(__name__)
+
+
+def _permute_rows_gpu(src, index, out):
+    """out[i, :] = src[index[i], :] for 2-D byte views on the GPU (one launch of the library's row-gather kernel)."""
+    lib = _lib.load()
+    rc = lib.acez_gather_rows(_lib.ptr(src), _lib.ptr(index), int(index.numel()), int(src.shape[1]), _lib.ptr(out),
+                              _lib.stream_ptr())
+    _lib.check(rc, "acez_gather_rows")
 
 
 def set_seed(seed):
@@ -37,10 +50,16 @@ def set_seed(seed):
 
 
 class TrainerACE:
-    def __init__(self, options, dataset=None):
+    def __init__(self, options, dataset=None, rank=0, world_size=1):
         self.log_file = None
         self.options = options
-        self.device = torch.device('cuda')
+        # one process per GPU: the launcher (acezero_b200.launch.select_device) has selected this rank's device
+        self.rank, self.world = int(rank), int(world_size)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        if not options.use_half:
+            _logger.warning("--use_half False: the sm_100a head computes with fp16 operands / fp32 accumulation in either "
+                            "mode; dynamic loss scaling with the overflow check stays on (an unscaled fp16 backward "
+                            "underflows and has no skip-on-inf)")
         if getattr(options, "training_buffer_cpu", False):
             _logger.warning("--training_buffer_cpu is ignored: the patch buffer stays in HBM (<= 9.8 GB of 180 GB)")
         if getattr(options, "render_visualization", False):
@@ -119,12 +138,14 @@ class TrainerACE:
         _logger.info(f"Filled training buffer in {creating_buffer_time:.1f}s.")
 
         base_file_name, _ = os.path.splitext(self.options.output_map_file)
-        self.log_file = open(base_file_name + '.txt', 'w')
+        # rank 0 owns the output files; every rank still reads the statistics (the read is a collective)
+        self.log_file = open(base_file_name + '.txt', 'w') if self.rank == 0 else None
 
         self.pose_refiner.create_pose_buffer()            # reference :231 (after the buffer: same RNG order)
         head = self.regressor.heads.engine(training=True, max_rows=self.options.batch_size)
         self.loop = TrainLoop(head, self.options, self.training_buffer, use_depth=self.use_depth,
-                              pose_refiner=self.pose_refiner, K_optimizer=self.K_optimizer)
+                              pose_refiner=self.pose_refiner, K_optimizer=self.K_optimizer, rank=self.rank,
+                              world_size=self.world)
         t0 = time.time()
         while self.loop.run_epoch(on_iteration=self._log_iteration):
             pass
@@ -133,9 +154,10 @@ class TrainerACE:
         self.iteration, self.epoch = self.loop.iteration, self.loop.epoch
         self.regressor.heads.export_engine_weights()
 
-        self.save_model()
-        self.save_poses()
-        self.log_file.close()
+        if self.rank == 0:
+            self.save_model()
+            self.save_poses()
+            self.log_file.close()
         _logger.info(f'Done without errors. Creating buffer time: {creating_buffer_time:.1f} seconds. '
                      f'Training time: {training_time:.1f} seconds. '
                      f'Total time: {time.time() - self.training_start:.1f} seconds.')
@@ -145,17 +167,22 @@ class TrainerACE:
         st = loop.last_stats
         loss, inl = float(st[0]), float(st[1]) / loop.b_global
         if float(st[3]) != 0 or not np.isfinite(loss):
-            _logger.error("Aborting because of NaN loss")  # reference :615-617
+            # st[3] is latched on the device: a non-finite loss of ANY iteration since the last read (reference :615-617
+            # checks every step; here the check costs no per-step host sync and still cannot miss one)
+            _logger.error("Aborting because of NaN loss")
             raise SystemExit(1)
+        if self.rank != 0:
+            return
         t = time.time() - self.training_start
-        _logger.info(f'Iteration: {loop.iteration:6d}|{loop.schedule.max_iterations:6d} / Epoch {loop.epoch:03d}, '
+        it = loop.iteration - 1   # the iteration these statistics belong to (the reference logs before incrementing, :642-651)
+        _logger.info(f'Iteration: {it:6d}|{loop.schedule.max_iterations:6d} / Epoch {loop.epoch:03d}, '
                      f'Loss: {loss:.1f}, Batch inliers ({self.options.learning_rate_cooldown_trigger_px_threshold}px): '
                      f'{inl * 100:.1f}%, Time: {t:.0f}s')
         orig, cur = self.pose_refiner.get_all_original_poses(), self.pose_refiner.get_all_current_poses()
         dist = torch.linalg.norm(cur[:, :, 3] - orig[:, :, 3], dim=1)
         _logger.info(f'Poses moved by: Avg={dist.mean() * 100:.1f}cm, Min={dist.min() * 100:.1f}cm, '
                      f'Max={dist.max() * 100:.1f}cm')
-        line = f"{loop.iteration} {t} {loss} {inl} {dist.mean()} {dist.min()} {dist.max()}"
+        line = f"{it} {t} {loss} {inl} {dist.mean()} {dist.min()} {dist.max()}"
         if self.K_optimizer is not None:
             focal = float(self.K_optimizer.get_focal_length())
             _logger.info(f"Current Focal Length: {focal:.1f}")
@@ -182,8 +209,75 @@ class TrainerACE:
                             timeout=60 if self.num_data_loader_workers > 0 else 0)
         _logger.info("Starting creation of the training buffer.")
         size = min(o.max_dataset_passes * len(self.dataset) * o.samples_per_image, o.max_training_buffer_size)
+        rank, world = self.rank, self.world
+        # data parallel: this rank fills a LOCAL staging buffer with the rows of its own images (every world-th non-empty
+        # image of the loader order); single GPU: local == the final buffer
+        local_cap = size if world == 1 else rows_capacity_per_rank(size, o.samples_per_image, world)
         d = self.device
-        buf = {
+        buf = self._alloc_buffer(local_cap)
+        lib = _lib.load()
+        enc = self.regressor.encoder
+        self.sample_log = []  # (image index, sampled cells) — kept for the bit-exactness tests
+        keep_log = bool(getattr(o, "keep_sample_log", False))
+        buffer_idx, passes, image_counter = 0, 0, 0
+        records = []                 # (owner rank, first global row, rows, first local row) of every image in the buffer
+        local_rows = [0] * world
+        n_encoded = 0
+        with torch.no_grad():
+            while buffer_idx < o.max_training_buffer_size and passes < o.max_dataset_passes:
+                passes += 1
+                for image, mask, pose_inv, aug_pose_inv, K, Kinv, crds, _, idx in loader:
+                    B = image.shape[0]
+                    assert B == 1, "the buffer is filled image by image (batch_size=1 sampler, reference :298-300)"
+                    H, W = encoder_out_hw(image.shape[2], image.shape[3])
+                    # mask at output resolution (reference :373-378); decided on the CPU copy: no GPU sync
+                    m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
+                    if m.sum() == 0:
+                        continue
+                    weights = m.float().view(-1).to(d, non_blocking=True)
+                    n_sel = min(o.samples_per_image * B, o.max_training_buffer_size - buffer_idx)
+                    # EVERY rank draws the indices of EVERY image: the CUDA generator advances exactly as in a single-GPU run
+                    sample_idxs = torch.multinomial(weights, n_sel, replacement=True,
+                                                    generator=self.sampling_generator)     # reference :423-426
+                    if keep_log:
+                        self.sample_log.append((int(idx), sample_idxs.cpu()))
+                    owner = image_counter % world
+                    image_counter += 1
+                    if owner == rank:
+                        feats = enc.forward_nhwc(image.to(d, non_blocking=True))      # [1,h,w,512] fp16
+                        assert feats.shape[1] == H and feats.shape[2] == W
+                        mats = torch.cat([aug_pose_inv[0, :3].reshape(-1), pose_inv[0].reshape(-1), K[0].reshape(-1),
+                                          Kinv[0].reshape(-1)]).float().pin_memory().to(d, non_blocking=True)
+                        crds_d = crds[0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
+                        rc = lib.acez_buffer_fill(_lib.ptr(feats), _lib.ptr(sample_idxs), n_sel, W, H * W,
+                                                  Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats), _lib.ptr(crds_d), int(idx),
+                                                  local_rows[rank], _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
+                                                  _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
+                                                  _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
+                                                  _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
+                        _lib.check(rc, "acez_buffer_fill")
+                        n_encoded += 1
+                    records.append((owner, buffer_idx, n_sel, local_rows[owner]))
+                    local_rows[owner] += n_sel
+                    buffer_idx += n_sel
+                    if buffer_idx >= o.max_training_buffer_size:
+                        break
+        self.training_buffer_size = min(buffer_idx, o.max_training_buffer_size)
+        self.images_encoded = n_encoded
+        if world == 1:
+            self.training_buffer = {k: v[:self.training_buffer_size] for k, v in buf.items()}
+        else:
+            from acezero_b200.parallel import allgather_buffer_rows
+            self.training_buffer = allgather_buffer_rows(buf, records, local_rows, self.training_buffer_size, world,
+                                                         permute_rows=_permute_rows_gpu)
+        gb = sum(v.element_size() * v.nelement() for v in self.training_buffer.values()) / 1024 ** 3
+        _logger.info(f"Created buffer of {gb:.2f}GB with {passes} passes over the training data"
+                     + (f" (rank {rank} of {world} encoded {n_encoded} of {image_counter} images)." if world > 1 else "."))
+
+    def _alloc_buffer(self, size):
+        """The 8 arrays of the reference's buffer dict (ace_trainer.py:330-340), `size` rows."""
+        d = self.device
+        return {
             'features': torch.empty((size, self.regressor.feature_dim), dtype=torch.float16, device=d),
             'target_px': torch.empty((size, 2), dtype=torch.float32, device=d),
             'aug_poses_inv': torch.empty((size, 3, 4), dtype=torch.float32, device=d),
@@ -193,46 +287,6 @@ class TrainerACE:
             'target_crds': torch.empty((size, 3), dtype=torch.float32, device=d),
             'pose_idx': torch.empty((size, 1), dtype=torch.int16, device=d),
         }
-        lib = _lib.load()
-        enc = self.regressor.encoder
-        self.sample_log = []  # (image index, sampled cells) — kept for the bit-exactness tests
-        keep_log = bool(getattr(o, "keep_sample_log", False))
-        buffer_idx, passes = 0, 0
-        with torch.no_grad():
-            while buffer_idx < o.max_training_buffer_size and passes < o.max_dataset_passes:
-                passes += 1
-                for image, mask, pose_inv, aug_pose_inv, K, Kinv, crds, _, idx in loader:
-                    B = image.shape[0]
-                    assert B == 1, "the buffer is filled image by image (batch_size=1 sampler, reference :298-300)"
-                    feats = enc.forward_nhwc(image.to(d, non_blocking=True))      # [1,h,w,512] fp16
-                    _, H, W, C = feats.shape
-                    # mask at output resolution (reference :373-378); decided on the CPU copy: no GPU sync
-                    m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
-                    if m.sum() == 0:
-                        continue
-                    weights = m.float().view(-1).to(d, non_blocking=True)
-                    n_sel = min(o.samples_per_image * B, o.max_training_buffer_size - buffer_idx)
-                    sample_idxs = torch.multinomial(weights, n_sel, replacement=True,
-                                                    generator=self.sampling_generator)     # reference :423-426
-                    if keep_log:
-                        self.sample_log.append((int(idx), sample_idxs.cpu()))
-                    mats = torch.cat([aug_pose_inv[0, :3].reshape(-1), pose_inv[0].reshape(-1), K[0].reshape(-1),
-                                      Kinv[0].reshape(-1)]).float().pin_memory().to(d, non_blocking=True)
-                    crds_d = crds[0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
-                    rc = lib.acez_buffer_fill(_lib.ptr(feats), _lib.ptr(sample_idxs), n_sel, W, H * W,
-                                              Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats), _lib.ptr(crds_d), int(idx),
-                                              buffer_idx, _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
-                                              _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
-                                              _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
-                                              _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
-                    _lib.check(rc, "acez_buffer_fill")
-                    buffer_idx += n_sel
-                    if buffer_idx >= o.max_training_buffer_size:
-                        break
-        self.training_buffer_size = min(buffer_idx, o.max_training_buffer_size)
-        self.training_buffer = {k: v[:self.training_buffer_size] for k, v in buf.items()}
-        gb = sum(v.element_size() * v.nelement() for v in self.training_buffer.values()) / 1024 ** 3
-        _logger.info(f"Created buffer of {gb:.2f}GB with {passes} passes over the training data.")
 
     def _create_training_buffer_batched(self, max_batch):
         """Experimental (ACEZ_FILL_BATCH=n, not yet run on hardware): the same buffer, same generators and call order (=> the

@@ -135,7 +135,10 @@ class TrainLoop:
         if self.b_global % world_size != 0:
             raise ValueError("batch_size must be divisible by the number of ranks")
         self.b = self.b_global // world_size
-        self.use_scaler = bool(options.use_half)
+        # The head kernels compute with fp16 operands in either mode, so dynamic loss scaling + the skip-on-overflow check stay
+        # on for `--use_half False` too (the reference trains in fp32 there, ace_trainer.py:517, ace_schedule.py:70; an
+        # unscaled fp16 backward underflows, and without the check one overflow would write NaN into the weights)
+        self.use_scaler = True
         self.schedule = Schedule(options)
         self.iteration = 0
         self.epoch = 0
@@ -157,8 +160,6 @@ class TrainLoop:
         self.set_buffer(buffer)
         if head.max_rows < self.b or not head.training:
             raise ValueError("head engine must be created with training=True and max_rows >= per-rank batch")
-        if not self.use_scaler:
-            head.scaler_state[0] = 1.0
         # static per-iteration tensors (graph-stable addresses)
         d = self.device
         self.idx_dev = torch.zeros(self.b, dtype=torch.int64, device=d)

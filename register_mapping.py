@@ -49,15 +49,27 @@ def build_parser():
     p.add_argument("--synthetic_seed", type=int, default=2089)
     p.add_argument("--synthetic_offset", type=int, default=0, help="first trajectory index of the synthetic frames")
     p.add_argument("--encoder_seed", type=int, default=None)
+    p.add_argument("--gpus", type=int, default=0,
+                   help="extension: GPUs (ranks) for this stage; 0 = $ACEZ_GPUS or 1 (acezero_b200/launch.py)")
+    p.add_argument("--micro_batch", type=int, default=16, help="extension: images per DSAC* launch pair")
     return p
 
 
 def main(argv=None):
     logging.basicConfig(level=logging.INFO)
+    import sys
+    argv = list(sys.argv[1:] if argv is None else argv)
     opt = build_parser().parse_args(argv)
     if opt.render_visualization:
         raise NotImplementedError("the visualiser is out of scope (SURVEY §2.1 row 13)")
+    from acezero_b200 import launch
+    # the fast registration check of a seed trial (ace_zero_util.py:242-259: --max_estimates 1000) stays on one leased GPU
+    small_job = opt.max_estimates > 0
+    launch.maybe_self_launch(Path(__file__).resolve(), argv, launch.requested_gpus(opt.gpus), small_job=small_job)
     import torch
+    rank, world = launch.select_device(small_job=small_job)
+    if rank != 0:
+        logging.getLogger().setLevel(logging.WARNING)
     from torch.utils.data import DataLoader
     from ace_network import Regressor
     from acezero_b200 import posefile
@@ -66,13 +78,13 @@ def main(argv=None):
     torch.manual_seed(opt.base_seed)
     np.random.seed(opt.base_seed)
     random.seed(opt.base_seed)
-    device = torch.device("cuda")
+    device = torch.device("cuda", torch.cuda.current_device())
 
     if opt.synthetic > 0:
         from acezero_b200.synthetic import SyntheticDataset
         testset = SyntheticDataset(opt.synthetic, seed=opt.synthetic_seed,
                                    focal=opt.use_external_focal_length if opt.use_external_focal_length > 0 else 525.0,
-                                   device="cuda", indices=range(opt.synthetic_offset, opt.synthetic_offset + opt.synthetic))
+                                   device=str(device), indices=range(opt.synthetic_offset, opt.synthetic_offset + opt.synthetic))
         workers = 0
     else:
         try:
@@ -99,7 +111,17 @@ def main(argv=None):
     pose_log_file = Path(opt.network).parent / f"poses_{opt.session}.txt"
     _logger.info(f"Saving per-frame poses and errors to: {pose_log_file}")
     results, stats = register(network, loader, opt.hypotheses, opt.threshold, opt.inlieralpha, opt.maxpixelerror,
-                              opt.base_seed, opt.hypotheses_max_tries, opt.max_estimates, device=device)
+                              opt.base_seed, opt.hypotheses_max_tries, opt.max_estimates, micro_batch=opt.micro_batch,
+                              rank=rank, world_size=world, device=device)
+    if world > 1:
+        # image i was solved by rank i % world (per-image RNG key: the poses do not depend on the number of ranks);
+        # rank 0 collects the (pose, inlier count) rows and writes the file
+        from acezero_b200.parallel import gather_registration
+        results = gather_registration(results, world)
+        launch.shutdown_distributed()
+        if rank != 0:
+            return
+    launch.release_gpu()
     with open(pose_log_file, "w", 1) as pose_log:
         for r in results:
             _logger.info(f"Frame: {r['file']}, Confidence: {r['inliers']}")

@@ -113,3 +113,110 @@ def test_schedule_matches_torch_schedulers():
         buf.append(inl); buf = buf[-100:]
         it += 1
     assert max_it < 400
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sharded buffer creation: row map + all-gather of the ranks' staging rows
+# ------------------------------------------------------------------------------------------------------------------
+def _records(world, n_images, rows_per_image, total_rows, ragged_at=None):
+    """The bookkeeping TrainerACE.create_training_buffer keeps on every rank: images dealt round-robin in loader order."""
+    records, local_rows, g = [], [0] * world, 0
+    for k in range(n_images):
+        n = rows_per_image if k != ragged_at else rows_per_image // 3       # e.g. a partly masked-out image
+        n = min(n, total_rows - g)
+        if n <= 0:
+            break
+        owner = k % world
+        records.append((owner, g, n, local_rows[owner]))
+        local_rows[owner] += n
+        g += n
+    return records, local_rows, g
+
+
+def _permute_rows_cpu(src, index, out):
+    out.copy_(src.index_select(0, index))
+
+
+def _buffer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from acezero_b200 import parallel
+    records, local_rows, total = _records(world, 11, 8, 80, ragged_at=4)
+    # the single-GPU buffer: row g holds (g, 2g) / int16 g
+    full = {"features": torch.arange(total, dtype=torch.float16).view(-1, 1).repeat(1, 4),
+            "target_px": torch.stack([torch.arange(total, dtype=torch.float32), 2 * torch.arange(total, dtype=torch.float32)], 1),
+            "pose_idx": torch.arange(total, dtype=torch.int16).view(-1, 1)}
+    cap = parallel.rows_capacity_per_rank(80, 8, world)
+    local = {k: torch.zeros((cap,) + tuple(v.shape[1:]), dtype=v.dtype) for k, v in full.items()}
+    for owner, g0, n, l0 in records:
+        if owner == rank:
+            for k in full:
+                local[k][l0:l0 + n] = full[k][g0:g0 + n]
+    merged = parallel.allgather_buffer_rows(local, records, local_rows, total, world, permute_rows=_permute_rows_cpu)
+    out[rank] = all(torch.equal(merged[k], full[k]) for k in full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_buffer_rows_allgather_to_the_single_gpu_buffer():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_buffer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] and out[1]
+
+
+def test_row_map_covers_every_row_once():
+    from acezero_b200 import parallel
+    records, local_rows, total = _records(4, 37, 1024, 36000, ragged_at=9)
+    stride = max(local_rows)
+    src = parallel.build_row_map(records, 4, stride, total)
+    assert len(np.unique(src)) == total                       # a permutation: every staged row is used exactly once
+    owner = src // stride
+    assert (owner[:1024] == 0).all() and (owner[1024:2048] == 1).all()
+    with pytest.raises(ValueError):
+        parallel.build_row_map(records[:-1], 4, stride, total)
+    assert parallel.rows_capacity_per_rank(36000, 1024, 4) >= stride
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stage-executable placement (acezero_b200/launch.py)
+# ------------------------------------------------------------------------------------------------------------------
+def test_launch_policy(tmp_path, monkeypatch):
+    from acezero_b200 import launch
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("ACEZ_GPUS", raising=False)
+    assert launch.requested_gpus(0) == 1 and launch.requested_gpus(4) == 4
+    monkeypatch.setenv("ACEZ_GPUS", "8")
+    assert launch.requested_gpus(0) == 8 and launch.requested_gpus(2) == 2
+    assert launch.world() == (0, 1, 0) and not launch.in_worker()
+    cmd = launch.torchrun_command("train_ace.py", ["a", "b.pt", "--iterations", 5], 8, port=29999)
+    assert cmd[1:4] == ["-m", "torch.distributed.run", "--nnodes=1"] and "--nproc-per-node=8" in cmd
+    assert cmd[cmd.index("--master-addr") + 1] == "127.0.0.1" and cmd[-5:] == ["train_ace.py", "a", "b.pt", "--iterations", "5"]
+    # single GPU, a worker of a group, or a small job (seed trial): the caller does the work itself (no exec)
+    launch.maybe_self_launch("train_ace.py", [], 1)
+    launch.maybe_self_launch("train_ace.py", [], 8, small_job=True)
+    monkeypatch.setenv("RANK", "3"); monkeypatch.setenv("WORLD_SIZE", "8"); monkeypatch.setenv("LOCAL_RANK", "3")
+    launch.maybe_self_launch("train_ace.py", [], 8)
+    assert launch.world() == (3, 8, 3)
+
+
+def _lease_worker(lock_dir, q, hold):
+    from acezero_b200 import launch
+    q.put(launch.lease_gpu(4, lock_dir=lock_dir, blocking_fallback=False))
+    hold.wait(20)
+
+
+def test_parallel_seed_workers_lease_distinct_gpus(tmp_path):
+    """Four concurrent single-GPU stage processes (ace_zero.py --seed_parallel_workers 4) on a 4-GPU box: one GPU each."""
+    ctx = mp.get_context("spawn")
+    q, hold = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_lease_worker, args=(str(tmp_path), q, hold)) for _ in range(4)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=60) for _ in procs)
+    hold.set()
+    for p in procs:
+        p.join(30)
+    assert got == [0, 1, 2, 3]

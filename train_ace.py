@@ -55,6 +55,9 @@ def build_parser():
     p.add_argument("--synthetic_seed", type=int, default=2089)
     p.add_argument("--encoder_seed", type=int, default=None,
                    help="extension: deterministic random encoder weights instead of --encoder_path")
+    p.add_argument("--gpus", type=int, default=0,
+                   help="extension: GPUs (ranks) for this stage; 0 = $ACEZ_GPUS or 1. More than one: the executable "
+                        "re-launches itself under torchrun (acezero_b200/launch.py)")
     return p
 
 
@@ -70,9 +73,22 @@ def validate(o):
 
 def main(argv=None):
     logging.basicConfig(level=logging.INFO)
+    import sys
+    argv = list(sys.argv[1:] if argv is None else argv)
     o = build_parser().parse_args(argv)
     validate(o)
+    from acezero_b200 import launch
+    # seed trials (ace_zero.py:184-196: one mapping image, several seeds in parallel) stay on one leased GPU each;
+    # full mapping stages shard over ACEZ_GPUS / --gpus ranks
+    small_job = o.use_pose_seed >= 0
+    n_gpus = launch.requested_gpus(o.gpus)
+    if o.batch_size % max(n_gpus, 1) != 0:
+        raise ValueError(f"batch_size {o.batch_size} is not divisible by {n_gpus} GPUs")
+    launch.maybe_self_launch(Path(__file__).resolve(), argv, n_gpus, small_job=small_job)
     import torch
+    rank, world = launch.select_device(small_job=small_job)
+    if rank != 0:
+        logging.getLogger().setLevel(logging.WARNING)
     from ace_trainer import TrainerACE
     dataset = None
     o.encoder_state_dict = None
@@ -83,10 +99,13 @@ def main(argv=None):
         from acezero_b200.synthetic import SyntheticDataset
         dataset = SyntheticDataset(o.synthetic, seed=o.synthetic_seed,
                                    focal=o.use_external_focal_length or 525.0,
-                                   device="cuda" if torch.cuda.is_available() else "cpu")
+                                   device=f"cuda:{torch.cuda.current_device()}" if torch.cuda.is_available() else "cpu")
         o.num_data_workers = 0
-    trainer = TrainerACE(o, dataset=dataset)
+    trainer = TrainerACE(o, dataset=dataset, rank=rank, world_size=world)
     trainer.train()
+    if world > 1:
+        launch.shutdown_distributed()
+    launch.release_gpu()
 
 
 if __name__ == "__main__":
