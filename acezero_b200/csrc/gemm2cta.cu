@@ -128,6 +128,8 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   t2_cluster_sync();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();               // the set-up above overlapped the predecessor's tail; its writes are visible from here on
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
@@ -258,7 +260,7 @@ static int encode2(CUtensorMap* tm, const __half* base, int mn_major, int rows_m
 }
 
 template <bool A_MN, bool B_MN, int BN>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& a, int batch, cudaStream_t stream) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& a, int batch, cudaStream_t stream, bool pdl) {
   auto kern = gemm2cta_kernel<A_MN, B_MN, BN>;
   constexpr int T2_SMEM = T2Cfg<BN>::kSmem;
   static bool configured = false;
@@ -272,26 +274,28 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Ar
   cfg.blockDim = dim3(T2_THREADS);
   cfg.dynamicSmemBytes = T2_SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
   return ACEZ_OK;
 }
 
-int gemm2_launch(const Gemm2Launch& L, cudaStream_t s) {
+int gemm2_launch(const Gemm2Launch& L, cudaStream_t s, bool pdl) {
   ACEZ_REQUIRE(L.a_mn == L.b_mn, "gemm2cta: operands must both be K-major or both MN-major");
   ACEZ_REQUIRE(L.bn == 128 || L.bn == 256, "gemm2cta: bn must be 128 or 256");
   if (L.bn == 128) {
-    if (L.a_mn) return launch2<true, true, 128>(L.tmA, L.tmB, L.args, L.batch, s);
-    return launch2<false, false, 128>(L.tmA, L.tmB, L.args, L.batch, s);
+    if (L.a_mn) return launch2<true, true, 128>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+    return launch2<false, false, 128>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
   }
-  if (L.a_mn) return launch2<true, true, 256>(L.tmA, L.tmB, L.args, L.batch, s);
-  return launch2<false, false, 256>(L.tmA, L.tmB, L.args, L.batch, s);
+  if (L.a_mn) return launch2<true, true, 256>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+  return launch2<false, false, 256>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
 }
 
 }  // namespace acez

@@ -24,6 +24,7 @@ struct Gemm2Launch {
   int a_mn, b_mn;        // 0 = K-major, 1 = MN-major (both equal)
 };
 
-int gemm2_launch(const Gemm2Launch& L, cudaStream_t stream);
+// pdl: programmatic dependent launch (only when the stream predecessor is a kernel)
+int gemm2_launch(const Gemm2Launch& L, cudaStream_t stream, bool pdl = false);
 
 }  // namespace acez

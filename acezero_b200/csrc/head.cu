@@ -706,11 +706,11 @@ static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfini
   const int L = h->L;
   if (h->use_chain && L >= 2) {
     h->chain_bwd.args.nonfinite = nonfinite;
-    int rc = chain_launch(h->chain_bwd, s);
+    int rc = chain_launch(h->chain_bwd, s, /*pdl=*/!h->fc3_pending);  // predecessor: fc3_reduce_kernel (or the side-stream fork)
     if (rc) return rc;
     if (h->use_wgrad2) {
       h->wgrad2.args.nonfinite = nonfinite;
-      rc = gemm2_launch(h->wgrad2, s);
+      rc = gemm2_launch(h->wgrad2, s, /*pdl=*/true);
     } else {
       h->wgrad.args.nonfinite = nonfinite;
       rc = gemm_launch(h->wgrad, s);

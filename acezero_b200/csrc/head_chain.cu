@@ -724,7 +724,7 @@ static int chain_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
   return ACEZ_OK;
 }
 
-int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
+int chain_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
   ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain_launch: %d steps", C.args.n_steps);
   static const bool xchg_st = [] {
     const char* e = getenv("ACEZ_CHAIN_XCHG");
@@ -738,7 +738,7 @@ int chain_launch(const ChainLaunch& C, cudaStream_t stream) {
     const char* e = getenv("ACEZ_CHAIN_V4");  // not yet validated on hardware (round 2): head_chain4.cu
     return e != nullptr && atoi(e) != 0;
   }();
-  if (v4) return chain4_launch(C, stream);
+  if (v4) return chain4_launch(C, stream, pdl);
   if (xchg_st) {
     if (C.mode == CHAIN_FWD) return chain_launch_mode<CHAIN_FWD, true, false>(C, stream);
     return chain_launch_mode<CHAIN_DGRAD, true, false>(C, stream);

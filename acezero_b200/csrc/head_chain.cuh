@@ -58,8 +58,9 @@ struct ChainLaunch {
 // in: the first A operand [rows,512]; out_base/out_zstride(elements)/out_slots: where new tiles are stored.
 int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16, int L, __half* out_base,
                   long long out_zstride, int out_slots, int rows);
-int chain_launch(const ChainLaunch& C, cudaStream_t stream);
-int chain4_launch(const ChainLaunch& C, cudaStream_t stream);  // ACEZ_CHAIN_V4=1 (experimental, cta_group::2 on a cluster of 4)
+// pdl: launch with the programmatic-dependent-launch attribute (only when the stream predecessor is a kernel)
+int chain_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl = false);
+int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl);  // cta_group::2 on a cluster of 4 (head_chain4.cu)
 // profiling probe: copies the stamps of the most recent launch with ACEZ_CHAIN_DBG=1 to host memory
 int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas);
 

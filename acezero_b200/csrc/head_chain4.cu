@@ -31,7 +31,6 @@ static constexpr int kBoxBytes = CM * CK * 2;        // 16 KB
 static constexpr int kABytes = kKB * kBoxBytes;      // 128 KB
 static constexpr int kBHalf = (CN / 2) * CK * 2;     // 16 KB: this CTA's half of a weight k-block
 static constexpr int kBStages = 6;
-static constexpr int kThreads4 = 320;
 static constexpr int kSmem4 = kABytes + kBStages * kBHalf + 1024 /*fp32 bias slice*/ + 384 /*barriers*/ + 1024 /*align*/;
 static_assert(kSmem4 <= 232448, "shared memory budget");
 static constexpr uint32_t kSw128 = 2;
@@ -125,17 +124,34 @@ __device__ __forceinline__ void c4_dsmem_copy(uint32_t dst_cluster, uint32_t src
 }
 __device__ __forceinline__ void c4_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// consumption order of the 8 k-blocks by arrival: own 0,1 | exchange partner's 0,1 | own 2,3 | partner's 2,3
+// consumption order of the 8 k-blocks by arrival. Two epilogue groups publish own boxes 0,1 first and 2,3 one box time
+// later: own 0,1 | exchange partner's 0,1 | own 2,3 | partner's 2,3. Four groups publish all own boxes together: own 0..3 |
+// partner's 0..3.
+template <int G>
 __device__ __forceinline__ int c4_order(int i, int c) {
+  if (G == 4) return (i < 4 ? c : (c ^ 1)) * 4 + (i & 3);
   const int b = ((i >> 2) << 1) | (i & 1);
   return ((i & 2) ? (c ^ 1) : c) * 4 + b;
 }
+template <int G>
+__device__ __forceinline__ bool c4_is_partner_box(int i) { return G == 4 ? i >= 4 : (i & 2) != 0; }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads4, 1)
+// prmt.b32 with the sign-replicate bit (8) in the selector nibbles: byte <- 0xFF / 0x00 from the msb of the selected byte
+__device__ __forceinline__ uint32_t c4_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// G = number of epilogue groups (each = 4 warps, one per TMEM lane quarter): 2 -> a group drains two 64-column boxes per
+// step in sequence (the round-1 epilogue), 4 -> one box per group, all four boxes of a step in parallel.
+template <int MODE, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
   constexpr bool kDgrad = (MODE == CHAIN_DGRAD);
+  constexpr int NB = 4 / G;            // boxes per epilogue group and step
+  constexpr int kEpiThreads = 128 * G;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -183,12 +199,16 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   c4_cluster_sync();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // programmatic dependent launch: everything above overlapped the predecessor's tail; its global writes are visible from
+  // here on. (A plain launch returns from the wait at once.) The successor may be scheduled as soon as SMs free up.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       for (int i = 0; i < kKB; ++i) {
-        const int j = c4_order(i, c);
+        const int j = c4_order<G>(i, c);
         mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
       }
@@ -197,7 +217,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       for (int s = 0; s < n_steps; ++s) {
         const int wl = args.step[s].w_layer;
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order(i, c);
+          const int j = c4_order<G>(i, c);
           c4_wait<0>(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * kBHalf);
           else c4_arrive_leader(&b_full[stage]);
@@ -224,9 +244,9 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       for (int s = 0; s < n_steps; ++s) {
         const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order(i, c);
+          const int j = c4_order<G>(i, c);
           c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
-          if ((i & 2) && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+          if (c4_is_partner_box<G>(i) && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
           c4_wait<2>(&partner_ready[j], (uint32_t)(s & 1), (7u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
           c4_wait<0>(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           tcgen05_fence_after();
@@ -256,10 +276,10 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       // ------------------------------ relay (the other CTA of the pair) ------------------------------
       for (int s = 0; s < n_steps; ++s) {
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order(i, c);
+          const int j = c4_order<G>(i, c);
           c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
           if (lane == 0) {
-            if ((i & 2) && s + 1 < n_steps) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+            if (c4_is_partner_box<G>(i) && s + 1 < n_steps) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
             // my k-block j of step s is in place IN MY OWN shared memory (generic-proxy writes were fenced by their writers,
             // async copies completed on the barrier) and it is my own tensor core that will read it: the signal to the
             // leader, which issues the UMMAs for both CTAs, carries no data - relaxed, no fence (a release at cluster scope
@@ -274,26 +294,30 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       }
     }
   } else {
-    // ------------------------------ epilogue (as head_chain.cu V3, exchange partner = rank ^ 2) ------------------------------
+    // ------------------------------ epilogue (exchange partner = rank ^ 2) ------------------------------
     const int quarter = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;                 // 0 .. G-1
     const int rr = quarter * 32 + lane;
     const int row = m0 + rr;
     const bool row_ok = row < args.rows;
     const int etid = threadIdx.x - 64;
-    const bool issuer = (lane == 0) && (quarter == 2 - 2 * grp);
+    // one issuing thread per group, on different warps / SM sub-partitions
+    const bool issuer = (lane == 0) && (quarter == (G == 2 ? 2 - 2 * grp : grp));
     const uint32_t swz = (uint32_t)(rr & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    auto bar_group = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
+    auto bar_all = [&]() { asm volatile("bar.sync 6, %0;" ::"n"(kEpiThreads) : "memory"); };
     uint32_t badbits = 0;
-    uint32_t res[2][32];
+    // residual stream (forward) / skip-path gradient (dgrad) of this thread's row and boxes: stays in registers
+    uint32_t res[NB][32];
 #pragma unroll
-    for (int sl = 0; sl < 2; ++sl)
+    for (int sl = 0; sl < NB; ++sl)
 #pragma unroll
       for (int t = 0; t < 32; ++t) res[sl][t] = 0u;
     if (!kDgrad && (args.flags & kChainFlagResInit)) {
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int j = c * 4 + grp + 2 * sl;
+      for (int sl = 0; sl < NB; ++sl) {
+        const int j = c * 4 + grp + G * sl;
         c4_wait<0>(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
         const uint8_t* src = sA + j * kBoxBytes + rr * 128;
 #pragma unroll
@@ -308,27 +332,32 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       const int tbuf = s & 1;
       const bool last = (s == n_steps - 1);
       if (!kDgrad) {
-        if (s > 0) asm volatile("bar.sync 3, 256;" ::: "memory");
-        sBiasF[etid] = __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
+        // fp32 copy of the fp16-rounded bias slice (autocast casts the bias to fp16 before the conv adds it); every
+        // epilogue warp must have finished the previous step's boxes before it is overwritten
+        if (s > 0) bar_all();
+        if (etid < CN) sBiasF[etid] = __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
       }
       c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
       tcgen05_fence_after();
-      asm volatile("bar.sync 3, 256;" ::: "memory");
+      bar_all();
       const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
       const bool want_mask = !kDgrad && st.mask_out != nullptr;
 #pragma unroll
-      for (int sl = 0; sl < 2; ++sl) {
-        const int box = grp + 2 * sl;
+      for (int sl = 0; sl < NB; ++sl) {
+        const int box = grp + G * sl;
         const int j = c * 4 + box;
         const int col0 = n_base + box * 64;
         uint2 mw = make_uint2(0u, 0u);
         if (kDgrad && row_ok) mw = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + j * 8));
         if (issuer) {
+          // peer_free phase s: the exchange partner's MMAs of step s have retired, i.e. it has consumed the boxes copied to it
+          // during step s-1 (those copies no longer read the boxes rewritten below) and its A buffer may be overwritten
           if (sl == 0) c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
-          c4_store_wait_read1();
+          // the TMA store that last read this box's memory has finished reading (one bulk group per box)
+          if (NB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        bar_group();
         uint8_t* dst = sA + j * kBoxBytes + rr * 128;
         uint32_t bits_lo = 0u, bits_hi = 0u;
         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
@@ -342,50 +371,62 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
             const int q = hf * 4 + q4;
             uint4 o;
             uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
-            float4 bf0 = make_float4(0.f, 0.f, 0.f, 0.f), bf1 = bf0;
             if (!kDgrad) {
-              bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
-              bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
-            }
-            const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+              const float4 bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
+              const float4 bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
+              const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+              uint32_t mm[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int col = q * 8 + 2 * t;
-              const int vc = col - hf * 32;
-              uint32_t& rs = res[sl][4 * q + t];
-              if (!kDgrad) {
+              for (int t = 0; t < 4; ++t) {
+                const int vc = q4 * 8 + 2 * t;
+                // single rounding of (acc + bias) to fp16; ReLU on the rounded value gives the same result as before it
                 __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]) + bq[2 * t], __uint_as_float(vv[vc + 1]) + bq[2 * t + 1]);
                 if (relu) h = __hmax2(h, zero2);
-                if (want_mask) {
-                  const uint32_t m = __hgt2_mask(h, zero2);
-                  const uint32_t two = (m & 1u) | ((m >> 15) & 2u);
-                  if (col < 32) bits_lo |= two << col;
-                  else bits_hi |= two << (col - 32);
-                }
+                mm[t] = __hgt2_mask(h, zero2);   // 0xFFFF per half that is > 0 (pre-residual x: the backward's ReLU mask)
+                uint32_t& rs = res[sl][4 * q + t];
                 if (res_add) {
-                  h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);
+                  h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);  // residual sum in fp16, as the reference's `res + x`
                   rs = *reinterpret_cast<const uint32_t*>(&h);
                 }
                 ob[t] = *reinterpret_cast<const uint32_t*>(&h);
-              } else {
+              }
+              if (want_mask) {
+                // 8 columns -> 8 bits (bit k = column 8 q + k): gather one byte per half, fold with a multiply
+                const uint32_t P = __byte_perm(mm[0], mm[1], 0x6420);
+                const uint32_t Q = __byte_perm(mm[2], mm[3], 0x6420);
+                const uint32_t byte = (((P & 0x08040201u) * 0x01010101u) >> 24) | (((Q & 0x80402010u) * 0x01010101u) >> 24);
+                if (q < 4) bits_lo |= byte << (8 * q);
+                else bits_hi |= byte << (8 * (q - 4));
+              }
+            } else {
+              // ReLU mask of the activation this gradient flows into: bit k of byte q = column 8 q + k. Spread the byte's
+              // bits to the sign bits of 8 bytes (multiply), then prmt with sign replication makes 0xFFFF / 0 per half.
+              const uint32_t b = ((q < 4) ? (mw.x >> (8 * q)) : (mw.y >> (8 * (q - 4)))) & 0xFFu;
+              const uint32_t w_lo = (b & 0xFu) * 0x10204080u;
+              const uint32_t w_hi = (b >> 4) * 0x10204080u;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const int vc = q4 * 8 + 2 * t;
+                uint32_t& rs = res[sl][4 * q + t];
+                // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
                 __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
                 if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
                 const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-                if (res_save) rs = hb;
-                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;
-                const uint32_t w = (col < 32) ? (mw.x >> col) : (mw.y >> (col - 32));
-                const uint32_t m = ((w & 1u) ? 0x0000FFFFu : 0u) | ((w & 2u) ? 0xFFFF0000u : 0u);
+                if (res_save) rs = hb;   // the unmasked sum is the skip-path gradient of the block below
+                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+                const uint32_t m = c4_prmt((t < 2) ? w_lo : w_hi, 0u, (t & 1) ? 0xBBAAu : 0x9988u);
                 ob[t] = hb & m;
               }
             }
             *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
           }
         }
+        // this TMEM buffer is rewritten by the MMAs of step s+2, which are released (transitively) by the barrier arrivals
+        // below: order the completed tcgen05.ld before them
         tcgen05_fence_before();
         if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
-        fence_proxy_async();
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        fence_proxy_async();   // the box is complete in shared memory: publish it to the tensor core / copy engines
+        bar_group();
         if (issuer) {
           const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
           if (!last) {
@@ -393,7 +434,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
             c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
           }
           if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
-          tma_store_commit();
+          tma_store_commit();   // always one group per box (keeps the wait_group.read accounting exact)
         }
       }
     }
@@ -412,9 +453,9 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   }
 }
 
-template <int MODE>
-static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
-  auto kern = head_chain4_kernel<MODE>;
+template <int MODE, int G>
+static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
+  auto kern = head_chain4_kernel<MODE, G>;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4));
@@ -433,24 +474,34 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream) {
   const int clusters = (tiles + 1) / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(4 * clusters);
-  cfg.blockDim = dim3(kThreads4);
+  cfg.blockDim = dim3(64 + 128 * G);
   cfg.dynamicSmemBytes = kSmem4;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 4;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, tmW4, C.tmOut, C.args));
   return ACEZ_OK;
 }
 
-int chain4_launch(const ChainLaunch& C, cudaStream_t stream) {
+int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
   ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain4_launch: %d steps", C.args.n_steps);
-  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD>(C, stream);
-  return chain4_launch_mode<CHAIN_DGRAD>(C, stream);
+  static const int groups = [] {
+    const char* e = getenv("ACEZ_CHAIN_EPI_GROUPS");   // 4 (default): one 64-column box per epilogue group; 2: the round-1 epilogue
+    return (e != nullptr && atoi(e) == 2) ? 2 : 4;
+  }();
+  if (groups == 2) {
+    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2>(C, stream, pdl);
+    return chain4_launch_mode<CHAIN_DGRAD, 2>(C, stream, pdl);
+  }
+  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 4>(C, stream, pdl);
+  return chain4_launch_mode<CHAIN_DGRAD, 4>(C, stream, pdl);
 }
 
 }  // namespace acez

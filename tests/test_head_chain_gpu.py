@@ -95,8 +95,10 @@ def test_chain_train_step_matches_layer_path_and_oracle(monkeypatch, nb, rows):
     assert abs(out[1][0][1] - out[0][0][1]) <= 2 and abs(out[1][0][2] - out[0][0][2]) <= 2
     for k, gref in out[0][1].items():
         rel = (out[1][1][k].reshape(-1) - gref.reshape(-1)).norm() / (gref.norm() + 1e-12)
-        # fp16 ulp flips of activations / activation gradients, summed over as few as 300 rows (observed up to 1.2e-2)
-        assert rel < 2.5e-2, f"{k}: chain vs layer path rel L2 {rel:.3e}"
+        # fp16 ulp flips of activations / activation gradients (the chain sums the 8 k-blocks in box-arrival order, the
+        # per-layer kernels in index order), amplified through ReLU-mask flips and summed over as few as 300 rows: observed
+        # 1.2e-2 with the own-boxes-first order, 3.0e-2 with the arrival order. The binding check is (b), against the oracle.
+        assert rel < 5e-2, f"{k}: chain vs layer path rel L2 {rel:.3e}"
     # (b) chain vs oracle autograd
     tr = ace_ref.TrainerRef(sd, nb, True, opts, lambda i: 1e-3, emulate_half=True)
     tr.iteration = it
