@@ -191,10 +191,17 @@ class TrainerACE:
 
     # ------------------------------------------------------------------------------------------------------------
     def create_training_buffer(self):
-        """reference ace_trainer.py:293-452."""
-        if os.environ.get("ACEZ_FILL_BATCH", "0") not in ("", "0"):
-            return self._create_training_buffer_batched(int(os.environ["ACEZ_FILL_BATCH"]))
+        """reference ace_trainer.py:293-452.
+
+        Same loader, generators and call order as the reference (=> the same images in the same order and bit-exact patch
+        indices); what differs is the execution: consecutive loader items of equal image size share ONE encoder launch
+        (the reference encodes at batch 1, :366-367; `ACEZ_FILL_BATCH`, default 8, 1 = per image), images go host->device
+        asynchronously from the loader's pinned tensors straight into the batch slot, the per-image matrices of a group
+        travel as one pinned row block, an all-true mask costs no resize / copy, and one fused kernel per image scatters
+        the sampled rows into all 8 buffer arrays. No host synchronisation per image.
+        """
         o = self.options
+        max_batch = max(1, int(os.environ.get("ACEZ_FILL_BATCH", "8") or 8))
         batch_sampler = sampler.BatchSampler(sampler.RandomSampler(self.dataset, generator=self.batch_generator),
                                              batch_size=1, drop_last=False)
 
@@ -223,6 +230,54 @@ class TrainerACE:
         records = []                 # (owner rank, first global row, rows, first local row) of every image in the buffer
         local_rows = [0] * world
         n_encoded = 0
+        ones_cache = {}
+        # pinned staging of the per-image matrices (aug_inv 12 | pose_inv 16 | K 9 | Kinv 9), one block per group; a block
+        # is reused only after the copy that read it has completed
+        n_stage = 4
+        mats_host = [torch.zeros((max_batch, 46), dtype=torch.float32).pin_memory() for _ in range(n_stage)]
+        mats_np = [m.numpy() for m in mats_host]
+        mats_dev = [torch.zeros((max_batch, 46), dtype=torch.float32, device=d) for _ in range(n_stage)]
+        stage_events = [None] * n_stage
+        stage_next = [0]
+        group = []                   # owned loader items waiting for the shared encoder launch
+
+        def flush():
+            nonlocal n_encoded
+            if not group:
+                return
+            n = len(group)
+            H_img, W_img = group[0]["image"].shape[2], group[0]["image"].shape[3]
+            images = torch.empty((n, 1, H_img, W_img), dtype=group[0]["image"].dtype, device=d)
+            sl = stage_next[0]
+            stage_next[0] = (sl + 1) % n_stage
+            if stage_events[sl] is not None:
+                stage_events[sl].synchronize()
+            else:
+                stage_events[sl] = torch.cuda.Event()
+            for k, g in enumerate(group):
+                images[k].copy_(g["image"][0], non_blocking=True)             # pinned (loader) -> device, asynchronous
+                row = mats_np[sl][k]
+                row[0:12] = g["aug_pose_inv"][0, :3].reshape(-1).numpy()
+                row[12:28] = g["pose_inv"][0].reshape(-1).numpy()
+                row[28:37] = g["K"][0].reshape(-1).numpy()
+                row[37:46] = g["Kinv"][0].reshape(-1).numpy()
+            mats_dev[sl][:n].copy_(mats_host[sl][:n], non_blocking=True)
+            stage_events[sl].record()
+            feats = enc.forward_nhwc(images)                                  # [n,h,w,512] fp16: ONE launch sequence
+            _, H, W, C = feats.shape
+            for k, g in enumerate(group):
+                assert (H, W) == g["hw"]
+                crds_d = g["crds"][0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
+                rc = lib.acez_buffer_fill(_lib.ptr(feats[k]), _lib.ptr(g["sample_idxs"]), g["n_sel"], W, H * W,
+                                          Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats_dev[sl][k]), _lib.ptr(crds_d), g["idx"],
+                                          g["local_row0"], _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
+                                          _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
+                                          _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
+                                          _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
+                _lib.check(rc, "acez_buffer_fill")
+            n_encoded += n
+            group.clear()
+
         with torch.no_grad():
             while buffer_idx < o.max_training_buffer_size and passes < o.max_dataset_passes:
                 passes += 1
@@ -230,11 +285,17 @@ class TrainerACE:
                     B = image.shape[0]
                     assert B == 1, "the buffer is filled image by image (batch_size=1 sampler, reference :298-300)"
                     H, W = encoder_out_hw(image.shape[2], image.shape[3])
-                    # mask at output resolution (reference :373-378); decided on the CPU copy: no GPU sync
-                    m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
-                    if m.sum() == 0:
-                        continue
-                    weights = m.float().view(-1).to(d, non_blocking=True)
+                    # mask at output resolution (reference :373-378), decided on the CPU copy: no GPU sync. An all-true mask
+                    # (no rotation augmentation) stays all-true under NEAREST resizing: no resize, no host->device copy
+                    if bool(mask.all()):
+                        if (H, W) not in ones_cache:
+                            ones_cache[(H, W)] = torch.ones(H * W, dtype=torch.float32, device=d)
+                        weights = ones_cache[(H, W)]
+                    else:
+                        m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
+                        if m.sum() == 0:
+                            continue
+                        weights = m.float().view(-1).to(d, non_blocking=True)
                     n_sel = min(o.samples_per_image * B, o.max_training_buffer_size - buffer_idx)
                     # EVERY rank draws the indices of EVERY image: the CUDA generator advances exactly as in a single-GPU run
                     sample_idxs = torch.multinomial(weights, n_sel, replacement=True,
@@ -244,24 +305,17 @@ class TrainerACE:
                     owner = image_counter % world
                     image_counter += 1
                     if owner == rank:
-                        feats = enc.forward_nhwc(image.to(d, non_blocking=True))      # [1,h,w,512] fp16
-                        assert feats.shape[1] == H and feats.shape[2] == W
-                        mats = torch.cat([aug_pose_inv[0, :3].reshape(-1), pose_inv[0].reshape(-1), K[0].reshape(-1),
-                                          Kinv[0].reshape(-1)]).float().pin_memory().to(d, non_blocking=True)
-                        crds_d = crds[0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
-                        rc = lib.acez_buffer_fill(_lib.ptr(feats), _lib.ptr(sample_idxs), n_sel, W, H * W,
-                                                  Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats), _lib.ptr(crds_d), int(idx),
-                                                  local_rows[rank], _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
-                                                  _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
-                                                  _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
-                                                  _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
-                        _lib.check(rc, "acez_buffer_fill")
-                        n_encoded += 1
+                        if group and (group[0]["image"].shape != image.shape or len(group) == max_batch):
+                            flush()
+                        group.append({"image": image, "pose_inv": pose_inv, "aug_pose_inv": aug_pose_inv, "K": K, "Kinv": Kinv,
+                                      "crds": crds, "idx": int(idx), "sample_idxs": sample_idxs, "n_sel": n_sel,
+                                      "local_row0": local_rows[rank], "hw": (H, W)})
                     records.append((owner, buffer_idx, n_sel, local_rows[owner]))
                     local_rows[owner] += n_sel
                     buffer_idx += n_sel
                     if buffer_idx >= o.max_training_buffer_size:
                         break
+                flush()
         self.training_buffer_size = min(buffer_idx, o.max_training_buffer_size)
         self.images_encoded = n_encoded
         if world == 1:
@@ -287,115 +341,6 @@ class TrainerACE:
             'target_crds': torch.empty((size, 3), dtype=torch.float32, device=d),
             'pose_idx': torch.empty((size, 1), dtype=torch.int16, device=d),
         }
-
-    def _create_training_buffer_batched(self, max_batch):
-        """Experimental (ACEZ_FILL_BATCH=n, not yet run on hardware): the same buffer, same generators and call order (=> the
-        same bit-exact patch indices), but consecutive loader items of equal image size share ONE encoder launch (the
-        reference encodes at batch 1, ace_trainer.py:366-367), the per-image matrices travel through a pinned ring and an
-        all-true mask costs no host->device copy. Round 1 measured the encoder at 0.11 ms per 480x640 image at batch 8; the
-        per-image Python / copy overhead of the default path dominates buffer creation."""
-        o = self.options
-        batch_sampler = sampler.BatchSampler(sampler.RandomSampler(self.dataset, generator=self.batch_generator),
-                                             batch_size=1, drop_last=False)
-
-        def seed_worker(worker_id):
-            worker_seed = torch.initial_seed() % 2 ** 32
-            np.random.seed(worker_seed)
-            random.seed(worker_seed)
-
-        loader = DataLoader(dataset=self.dataset, sampler=batch_sampler, batch_size=None, worker_init_fn=seed_worker,
-                            generator=self.loader_generator, pin_memory=True, num_workers=self.num_data_loader_workers,
-                            persistent_workers=self.num_data_loader_workers > 0,
-                            timeout=60 if self.num_data_loader_workers > 0 else 0)
-        size = min(o.max_dataset_passes * len(self.dataset) * o.samples_per_image, o.max_training_buffer_size)
-        d = self.device
-        buf = {
-            'features': torch.empty((size, self.regressor.feature_dim), dtype=torch.float16, device=d),
-            'target_px': torch.empty((size, 2), dtype=torch.float32, device=d),
-            'aug_poses_inv': torch.empty((size, 3, 4), dtype=torch.float32, device=d),
-            'poses_inv': torch.empty((size, 4, 4), dtype=torch.float32, device=d),
-            'intrinsics': torch.empty((size, 3, 3), dtype=torch.float32, device=d),
-            'intrinsics_inv': torch.empty((size, 3, 3), dtype=torch.float32, device=d),
-            'target_crds': torch.empty((size, 3), dtype=torch.float32, device=d),
-            'pose_idx': torch.empty((size, 1), dtype=torch.int16, device=d),
-        }
-        lib = _lib.load()
-        enc = self.regressor.encoder
-        self.sample_log = []
-        keep_log = bool(getattr(o, "keep_sample_log", False))
-        ring = 4 * max_batch
-        mats_host = torch.zeros((ring, 46), dtype=torch.float32).pin_memory()   # 12 + 16 + 9 + 9 floats per image
-        mats_dev = torch.zeros((ring, 46), dtype=torch.float32, device=d)
-        ring_events = [None] * ring
-        slot = [0]
-        ones_cache = {}
-        state = {"buffer_idx": 0}
-
-        def flush(group):
-            """group: list of loader items with identical image shape."""
-            if not group:
-                return
-            images = torch.cat([g[0] for g in group], 0).to(d, non_blocking=True)
-            feats = enc.forward_nhwc(images)                                  # [n,h,w,512] fp16, one launch
-            _, H, W, C = feats.shape
-            for k, (image, mask, pose_inv, aug_pose_inv, K, Kinv, crds, _, idx) in enumerate(group):
-                if state["buffer_idx"] >= o.max_training_buffer_size:
-                    return
-                m = TF.resize(mask, [H, W], interpolation=TF.InterpolationMode.NEAREST).bool()
-                n_valid = int(m.sum())
-                if n_valid == 0:
-                    continue
-                if n_valid == H * W:                                          # all cells valid: no copy
-                    if (H, W) not in ones_cache:
-                        ones_cache[(H, W)] = torch.ones(H * W, dtype=torch.float32, device=d)
-                    weights = ones_cache[(H, W)]
-                else:
-                    weights = m.float().view(-1).pin_memory().to(d, non_blocking=True)
-                n_sel = min(o.samples_per_image, o.max_training_buffer_size - state["buffer_idx"])
-                sample_idxs = torch.multinomial(weights, n_sel, replacement=True,
-                                                generator=self.sampling_generator)     # reference :423-426
-                if keep_log:
-                    self.sample_log.append((int(idx), sample_idxs.cpu()))
-                sl = slot[0]
-                slot[0] = (sl + 1) % ring
-                if ring_events[sl] is not None:
-                    ring_events[sl].synchronize()                              # the copy that last read this row is done
-                else:
-                    ring_events[sl] = torch.cuda.Event()
-                row = mats_host[sl]
-                row[0:12] = aug_pose_inv[0, :3].reshape(-1)
-                row[12:28] = pose_inv[0].reshape(-1)
-                row[28:37] = K[0].reshape(-1)
-                row[37:46] = Kinv[0].reshape(-1)
-                mats_dev[sl].copy_(row, non_blocking=True)
-                ring_events[sl].record()
-                crds_d = crds[0].float().contiguous().to(d, non_blocking=True) if self.use_depth else None
-                rc = lib.acez_buffer_fill(_lib.ptr(feats[k]), _lib.ptr(sample_idxs), n_sel, W, H * W,
-                                          Regressor.OUTPUT_SUBSAMPLE, _lib.ptr(mats_dev[sl]), _lib.ptr(crds_d), int(idx),
-                                          state["buffer_idx"], _lib.ptr(buf['features']), _lib.ptr(buf['target_px']),
-                                          _lib.ptr(buf['aug_poses_inv']), _lib.ptr(buf['poses_inv']),
-                                          _lib.ptr(buf['intrinsics']), _lib.ptr(buf['intrinsics_inv']),
-                                          _lib.ptr(buf['target_crds']), _lib.ptr(buf['pose_idx']), _lib.stream_ptr())
-                _lib.check(rc, "acez_buffer_fill")
-                state["buffer_idx"] += n_sel
-
-        passes = 0
-        with torch.no_grad():
-            while state["buffer_idx"] < o.max_training_buffer_size and passes < o.max_dataset_passes:
-                passes += 1
-                group = []
-                for item in loader:
-                    assert item[0].shape[0] == 1, "the buffer is filled image by image (batch_size=1 sampler, reference :298-300)"
-                    if group and (item[0].shape != group[0][0].shape or len(group) == max_batch):
-                        flush(group)
-                        group = []
-                    group.append(item)
-                    if state["buffer_idx"] >= o.max_training_buffer_size:
-                        break
-                flush(group)
-        torch.cuda.synchronize()
-        self.training_buffer_size = min(state["buffer_idx"], o.max_training_buffer_size)
-        self.training_buffer = {k: v[:self.training_buffer_size] for k, v in buf.items()}
 
     # ------------------------------------------------------------------------------------------------------------
     def save_model(self):

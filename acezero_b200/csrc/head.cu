@@ -65,8 +65,6 @@ struct acez_head_plan {
   cudaEvent_t ev_join;
   bool side_ready;
   int overlap_wgrad;
-  int fc3_overlap;     // ACEZ_FC3_OVERLAP=1 (experimental): the fc3 weight-gradient kernels run on the side stream, under the dgrad chain
-  bool fc3_pending;    // a join with the side stream is due at the end of the backward
 };
 
 namespace acez {
@@ -184,9 +182,15 @@ __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __r
 }
 
 // ----------------------------------------------------------------------------------------------
-// tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1]); one warp per row, lane owns columns
-// [16*lane, 16*lane+16) with its slice of the fc3 weights held in registers. The gradient w.r.t. the 4 fc3 outputs is
-// written to G3 [rows,4]; fc3_wgrad_kernel turns it into dW3 / db3.
+// tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1]) + per-block partial of the fc3 weight gradient.
+// One block = 32 rows, three phases:
+//   A  warp w, rows 4w..4w+3: the 4 fc3 dot products of a row (lane owns columns [16 lane, 16 lane + 16), its slice of the fc3
+//      weights in registers, the 4 rows' activations stay in registers for phase C) -> shared memory
+//   B  ONE THREAD PER ROW (warp 0): de-homogenisation, pose compose, reprojection loss and its analytic backward, back through
+//      the de-homogenisation -> g[4]. The per-row chain (divisions, exp / log / tanh) is latency bound; 32 rows advance in
+//      parallel instead of one per warp with all lanes redundant (round 1: 20 us for 5120 rows)
+//   C  warp w, rows 4w..4w+3: dX = g W3 with the ReLU mask -> DZ[L-1] (1 KB per row, coalesced) and the warp's partial of
+//      dW3 = sum_rows g x^T; block partial -> FC3PART[block] (summed by fc3_reduce_kernel)
 // ----------------------------------------------------------------------------------------------
 struct TailArgs {
   int rows, C3, use_homogeneous, training;
@@ -203,80 +207,285 @@ struct TailArgs {
   float* d_P; float* d_Kdiag;
   const float* d_sc_in; // training == 2: gradient w.r.t. the scene coordinates supplied by the caller (autograd)
   __half* dz;           // DZ[L-1] [rows,512]
-  float* g3;            // [rows,4] gradient w.r.t. the fc3 outputs (fp16-rounded values)
-  float* stats;         // [4]: written (not accumulated) by the last block to finish
+  float* fc3_part;      // nullable: [gridDim.x][4*512+4] per-block partials of dW3 / db3
+  float* stats;         // [4]: written (not accumulated) by the last block to finish; [3] is a latch (OR with its old value)
   int* nonfinite;       // written (not OR-ed) by the last block: later kernels of the iteration OR into it
   float* blk_part;      // [gridDim.x][8] per-block partial sums
   unsigned int* blk_count;  // self-resetting completion counter
 };
 
 static constexpr int kTailThreads = 256;
+static constexpr int kTailRows = 32;                                   // rows per block
+static constexpr int kTailAccBytes = (kTailThreads / 32) * 4 * kC * 4;  // dynamic smem of the fc3-gradient variant: 64 KB
 
 __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
-#include "head_tail_body.inc"
-}
-// ACEZ_TAIL_OCC2=1 (experimental, round 2): the same body capped at 128 registers (184 otherwise; a few hundred bytes of
-// spills) so that two CTAs = 16 warps fit per SM and the whole grid is resident in one wave (round-1 profile: 12.7 % of the
-// warp slots active, two waves of 148 CTAs).
-__global__ void __launch_bounds__(kTailThreads, 2) head_tail_kernel_occ2(const TailArgs a) {
-#include "head_tail_body.inc"
-}
-
-// dW3[j][c] = sum_rows G3[row][j] * x8[row][c], db3[j] = sum_rows G3[row][j].
-// Stage 1: one block per 32-row slab; thread (cg, rs) owns 8 columns (one 16-byte load per row) of every 4th row, all
-// loads of a thread are independent; slab partials go to global. Stage 2: sum the slab partials (coalesced), write the
-// gradient, and fold the GradScaler overflow check for these values into the same pass.
-static constexpr int kFc3Threads = 256;
-static constexpr int kFc3Rows = 32;
-__global__ void __launch_bounds__(kFc3Threads) fc3_wgrad_partial_kernel(const __half* __restrict__ x,
-                                                                       const float* __restrict__ g3, int rows,
-                                                                       float* __restrict__ part /*[nblk][2052]*/) {
-  __shared__ float sAcc[4][64][33];
-  __shared__ float sB[4][4];
+  extern __shared__ float sAcc[];              // [8 warps][4][512] (only when a.fc3_part != nullptr)
+  __shared__ float sS[kTailRows][4];           // fc3 outputs (fp16-rounded, as the autocast conv produces them)
+  __shared__ float sG[kTailRows][4];           // gradient w.r.t. the fc3 outputs (fp16-rounded values)
+  __shared__ float sRed[3];
+  __shared__ int sLast;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * kTailRows;
   pdl_wait();
   pdl_launch_dependents();
-  const int t = threadIdx.x, cg = t & 63, rs = t >> 6;
-  const int r0 = blockIdx.x * kFc3Rows, r1 = min(rows, r0 + kFc3Rows);
-  float acc[4][8];
+
+  // ---- phase-B threads prefetch their row's geometry (212 B from 5 arrays) before the dot products ----
+  const int brow = r0 + tid;
+  const bool b_active = tid < kTailRows && brow < a.rows;
+  float geoA[12], geoT[16], Kr[9], Ki[9], tpx0 = 0.f, tpx1 = 0.f;
+  if (b_active && a.training == 1) {
+    if (a.Pin != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+      for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(&geoA[4 * k]) = *reinterpret_cast<const float4*>(a.Pin + 12 * (size_t)brow + 4 * k);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 3; ++k) *reinterpret_cast<float4*>(&geoA[4 * k]) = *reinterpret_cast<const float4*>(a.A + 12 * (size_t)brow + 4 * k);
 #pragma unroll
-  for (int i = 0; i < kFc3Rows / 4; ++i) {
-    const int r = r0 + rs + 4 * i;
-    if (r < r1) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(x + (size_t)r * kC + 8 * cg);
-      const float4 g = *reinterpret_cast<const float4*>(g3 + 4 * (size_t)r);
-      const __half2* xh = reinterpret_cast<const __half2*>(&xv);
-      const float gj[4] = {g.x, g.y, g.z, g.w};
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(&geoT[4 * k]) = *reinterpret_cast<const float4*>(a.T + 16 * (size_t)brow + 4 * k);
+    }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float2 f = __half22float2(xh[c]);
+    for (int k = 0; k < 9; ++k) { Kr[k] = a.K[9 * (size_t)brow + k]; Ki[k] = a.Kinv[9 * (size_t)brow + k]; }
+    const float2 tp = *reinterpret_cast<const float2*>(a.tpx + 2 * (size_t)brow);
+    tpx0 = tp.x; tpx1 = tp.y;
+  }
+
+  // ---- phase A: fc3 dot products ----
+  __half2 w[4][8];   // this lane's slice of the fc3 weights: 4 rows x 16 columns
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[j][2 * c] = fmaf(gj[j], f.x, acc[j][2 * c]);
-          acc[j][2 * c + 1] = fmaf(gj[j], f.y, acc[j][2 * c + 1]);
-        }
-      }
-      if (cg == 0) { accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w; }
+  for (int j = 0; j < 4; ++j) {
+    const uint4* wp = reinterpret_cast<const uint4*>(a.W3h + j * kC + lane * 16);
+    const uint4 t0 = wp[0], t1 = wp[1];
+    const __half2* h0 = reinterpret_cast<const __half2*>(&t0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&t1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w[j][k] = h0[k]; w[j][4 + k] = h1[k]; }
+  }
+  uint4 xr[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + 4 * warp + i;
+    if (row < a.rows) {
+      const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * kC + lane * 16);
+      xr[i][0] = xp[0]; xr[i][1] = xp[1];
+    } else {
+      xr[i][0] = make_uint4(0u, 0u, 0u, 0u); xr[i][1] = xr[i][0];
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int i = 0; i < 4; ++i) {
+    const __half2* xh = reinterpret_cast<const __half2*>(xr[i]);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sAcc[rs][cg][j * 8 + c] = acc[j][c];
-  if (cg == 0)
-    for (int j = 0; j < 4; ++j) sB[rs][j] = accb[j];
-  __syncthreads();
-  float* out = part + (size_t)blockIdx.x * (4 * kC + 4);
-  for (int idx = t; idx < 4 * kC; idx += kFc3Threads) {
-    const int j = idx / kC, col = idx % kC;
-    const int g = col >> 3, c = col & 7;
-    out[idx] = sAcc[0][g][j * 8 + c] + sAcc[1][g][j * 8 + c] + sAcc[2][g][j * 8 + c] + sAcc[3][g][j * 8 + c];
+    for (int k = 0; k < 8; ++k) {
+      const float2 xf = __half22float2(xh[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wf = __half22float2(w[j][k]);
+        d[j] = fmaf(xf.x, wf.x, d[j]);
+        d[j] = fmaf(xf.y, wf.y, d[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = warp_sum(d[j]);
+    if (lane < 4) {
+      const float dj = lane == 0 ? d[0] : (lane == 1 ? d[1] : (lane == 2 ? d[2] : d[3]));
+      const float bj = (lane < a.C3) ? __half2float(__float2half_rn(a.b3[lane])) : 0.f;
+      sS[4 * warp + i][lane] = __half2float(__float2half_rn(dj + bj));
+    }
   }
-  if (t < 4) out[4 * kC + t] = sB[0][t] + sB[1][t] + sB[2][t] + sB[3][t];
+  __syncthreads();
+
+  // ---- phase B: one thread per row ----
+  float loss_sum = 0.f, inl_sum = 0.f, valid_sum = 0.f;
+  bool bad = false, bad_g = false;
+  if (tid < kTailRows) {
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b_active) {
+      acez_loss_params lp = a.lp;
+      if (a.training && a.grad_scale_dev != nullptr) lp.grad_scale = *a.grad_scale_dev;
+      if (a.training && a.loss_weight_dev != nullptr) lp.loss_weight = *a.loss_weight_dev;
+      const float s0 = sS[tid][0], s1 = sS[tid][1], s2 = sS[tid][2], s3 = sS[tid][3];
+      const float sv[3] = {s0, s1, s2};
+      // homogeneous -> 3-D (ace_network.py:139-147), fp32
+      float X[3], h = 1.f, sig = 0.f;
+      bool h_pass = true;
+      if (a.use_homogeneous) {
+        const float bx = a.h_beta * s3;
+        float sp;
+        if (bx > 20.f) { sp = s3; sig = 1.f; }               // torch softplus threshold
+        else { sp = log1pf(expf(bx)) / a.h_beta; sig = 1.f / (1.f + expf(-bx)); }
+        h = sp + a.max_inv_scale;
+        h_pass = h <= a.min_inv_scale;                          // clamp_(max=) backward mask
+        h = fminf(h, a.min_inv_scale);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) X[i] = sv[i] / h + a.mean[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) X[i] = sv[i] + a.mean[i];
+      }
+      if (a.sc_out != nullptr) {
+        a.sc_out[(size_t)brow * 3 + 0] = X[0]; a.sc_out[(size_t)brow * 3 + 1] = X[1]; a.sc_out[(size_t)brow * 3 + 2] = X[2];
+      }
+      if (a.training) {
+        RowLoss o;
+        if (a.training == 2) {
+          // external gradient (torch.autograd through the Regressor module): skip the loss, take dL/dX from the caller
+#pragma unroll
+          for (int i = 0; i < 3; ++i) o.gX[i] = a.d_sc_in[3 * (size_t)brow + i];
+          o.loss = 0.f; o.valid = true; o.inlier = false; o.gK00 = o.gK11 = 0.f;
+          o.gc[0] = o.gc[1] = o.gc[2] = 0.f;
+        } else {
+          float P[12];
+          if (a.Pin != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) P[k] = geoA[k];
+          } else {
+            compose_pose(geoA, geoT, P);
+          }
+          repro_row(lp, X, P, Kr, Ki, tpx0, tpx1, (lp.use_depth && a.G) ? a.G + 3 * (size_t)brow : nullptr, o);
+          loss_sum = o.loss / (float)lp.divisor;
+          inl_sum = o.inlier ? 1.f : 0.f;
+          valid_sum = o.valid ? 1.f : 0.f;
+          bad = !isfinite(o.loss);
+          if (a.d_Kdiag != nullptr) { a.d_Kdiag[2 * (size_t)brow] = o.gK00; a.d_Kdiag[2 * (size_t)brow + 1] = o.gK11; }
+          if (a.d_P != nullptr) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              *reinterpret_cast<float4*>(a.d_P + 12 * (size_t)brow + 4 * r) = make_float4(o.gc[r] * X[0], o.gc[r] * X[1], o.gc[r] * X[2], o.gc[r]);
+          }
+        }
+        // back through the de-homogenisation to the 4 fc3 outputs; rounded to fp16 like autograd's cast
+        if (a.use_homogeneous) {
+          const float ih = 1.f / h;
+          float gh = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { g[i] = o.gX[i] * ih; gh -= o.gX[i] * sv[i] * ih * ih; }
+          g[3] = h_pass ? gh * sig : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) g[i] = o.gX[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          g[j] = __half2float(__float2half_rn(g[j]));
+          bad_g |= !isfinite(g[j]);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(&sG[tid][0]) = make_float4(g[0], g[1], g[2], g[3]);
+    if (a.training == 1) {   // warp 0 holds all 32 rows of the block
+      loss_sum = warp_sum(loss_sum); inl_sum = warp_sum(inl_sum); valid_sum = warp_sum(valid_sum);
+      if (tid == 0) { sRed[0] = loss_sum; sRed[1] = inl_sum; sRed[2] = valid_sum; }
+    }
+  }
+  if (!a.training) return;
+  __syncthreads();
+
+  // ---- phase C: dX8 = g W3 (fp16 result), masked by the ReLU of x8 -> DZ[L-1]; fc3 weight-gradient partial ----
+  float acc[4][16];
+  if (a.fc3_part != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[j][k] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + 4 * warp + i;
+    if (row >= a.rows) continue;
+    const float4 gv = *reinterpret_cast<const float4*>(&sG[4 * warp + i][0]);
+    const float g[4] = {gv.x, gv.y, gv.z, gv.w};
+    const __half2* xh = reinterpret_cast<const __half2*>(xr[i]);
+    uint4 outv[2];
+    __half2* oh = reinterpret_cast<__half2*>(outv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 xf = __half22float2(xh[k]);
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 wf = __half22float2(w[j][k]);
+        d0 = fmaf(g[j], wf.x, d0);
+        d1 = fmaf(g[j], wf.y, d1);
+        if (a.fc3_part != nullptr) {
+          acc[j][2 * k] = fmaf(g[j], xf.x, acc[j][2 * k]);
+          acc[j][2 * k + 1] = fmaf(g[j], xf.y, acc[j][2 * k + 1]);
+        }
+      }
+      __half2 hv = __floats2half2_rn(d0, d1);
+      const float2 hf = __half22float2(hv);
+      bad_g |= !(isfinite(hf.x) && isfinite(hf.y));
+      if (!(xf.x > 0.f)) hv.x = __float2half_rn(0.f);
+      if (!(xf.y > 0.f)) hv.y = __float2half_rn(0.f);
+      oh[k] = hv;
+    }
+    uint4* dzp = reinterpret_cast<uint4*>(a.dz + (size_t)row * kC + lane * 16);
+    dzp[0] = outv[0];
+    dzp[1] = outv[1];
+  }
+  if (a.fc3_part != nullptr) {
+    float* mine = sAcc + (size_t)warp * 4 * kC;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        *reinterpret_cast<float4*>(mine + j * kC + lane * 16 + 4 * k) = make_float4(acc[j][4 * k], acc[j][4 * k + 1], acc[j][4 * k + 2], acc[j][4 * k + 3]);
+  }
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);
+  const int any_bad_g = __syncthreads_or(bad_g ? 1 : 0);
+  if (a.fc3_part != nullptr) {
+    float* out = a.fc3_part + (size_t)blockIdx.x * (4 * kC + 4);
+    for (int idx = tid; idx < 4 * kC; idx += kTailThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kTailThreads / 32; ++wv) t += sAcc[(size_t)wv * 4 * kC + idx];
+      out[idx] = t;
+    }
+    if (tid < 4) {
+      float t = 0.f;
+      for (int r = 0; r < kTailRows; ++r) t += sG[r][tid];
+      out[4 * kC + tid] = t;
+    }
+  }
+  // per-block partials, then the last block to finish writes the totals (no pre-zeroing, deterministic order)
+  if (tid == 0) {
+    float* p = a.blk_part + 8 * (size_t)blockIdx.x;
+    p[0] = a.training == 1 ? sRed[0] : 0.f; p[1] = a.training == 1 ? sRed[1] : 0.f; p[2] = a.training == 1 ? sRed[2] : 0.f;
+    p[3] = any_bad ? 1.f : 0.f; p[4] = any_bad_g ? 1.f : 0.f;
+    __threadfence();
+    const unsigned int done = atomicAdd(a.blk_count, 1u);
+    sLast = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (sLast) {
+    __threadfence();
+    float accs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = tid; b < (int)gridDim.x; b += kTailThreads) {
+      const volatile float* p = a.blk_part + 8 * (size_t)b;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) accs[k] += p[k];
+    }
+    __shared__ float sTot[5][kTailThreads / 32];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float wsum = warp_sum(accs[k]);
+      if (lane == 0) sTot[k][warp] = wsum;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < 5; ++k)
+        for (int wv = 0; wv < kTailThreads / 32; ++wv) t[k] += sTot[k][wv];
+      if (a.stats != nullptr) {
+        // stats[3] latches: a non-finite loss of any iteration stays visible until the host clears it (the reference
+        // checks the loss every iteration, ace_trainer.py:615-617; here the host reads it only when it logs)
+        const float was = a.stats[3];
+        a.stats[0] = t[0]; a.stats[1] = t[1]; a.stats[2] = t[2]; a.stats[3] = (t[3] > 0.f || was > 0.f) ? 1.f : 0.f;
+      }
+      if (a.nonfinite != nullptr) *a.nonfinite = t[4] > 0.f ? 1 : 0;
+      *a.blk_count = 0u;  // ready for the next launch
+    }
+  }
 }
 
 __global__ void fc3_reduce_kernel(const float* __restrict__ part, int nblk, int C3, float* __restrict__ gW3,
@@ -632,19 +841,7 @@ static void fill_tail_common(const acez_head_plan* h, int rows, TailArgs& t) {
   t.b3 = h->params + (size_t)h->L * kLayerStride + (size_t)h->C3 * kC;
 }
 
-static int tail_grid(int rows) {
-  const int per_block = kTailThreads / 32;
-  int g = (rows + per_block - 1) / per_block;
-  // CTAs per SM (default 2; ACEZ_TAIL_BLOCKS_PER_SM to probe): fewer rows per warp shorten the serial per-row chain, more
-  // blocks lengthen the last-block reduction over the per-block partials (4096 slots)
-  static const int per_sm = [] {
-    const char* e = getenv("ACEZ_TAIL_BLOCKS_PER_SM");
-    const int v = e != nullptr ? atoi(e) : 2;
-    return v >= 1 && v <= 8 ? v : 2;
-  }();
-  const int cap = per_sm * sm_count() < 4096 ? per_sm * sm_count() : 4096;
-  return g < cap ? (g < 1 ? 1 : g) : cap;
-}
+static int tail_grid(int rows) { return (rows + kTailRows - 1) / kTailRows; }
 
 static int ensure_side_stream(acez_head_plan* h) {
   if (!h->side_ready) {
@@ -664,35 +861,22 @@ static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s,
     h->counters_zeroed = true;
     pdl = false;  // predecessor is a memset
   }
+  ACEZ_REQUIRE(tail_grid(rows) <= 4096, "head tail: %d rows exceed the per-block partial buffer (131072 rows)", rows);
   t.blk_part = h->BLKPART;
   t.blk_count = h->BLKCOUNT;
-  static const bool occ2 = [] {
-    const char* e = getenv("ACEZ_TAIL_OCC2");
-    return e != nullptr && atoi(e) != 0;
-  }();
-  int rc = occ2 ? launch_pdl(head_tail_kernel_occ2, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t)
-                : launch_pdl(head_tail_kernel, dim3(tail_grid(rows)), dim3(kTailThreads), 0, s, pdl, t);
+  t.fc3_part = with_fc3_grad ? h->FC3PART : nullptr;
+  static bool configured = false;
+  if (!configured) {
+    ACEZ_CUDA(cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailAccBytes));
+    configured = true;
+  }
+  int rc = launch_pdl(head_tail_kernel, dim3(tail_grid(rows)), dim3(kTailThreads), with_fc3_grad ? (size_t)kTailAccBytes : 0, s, pdl, t);
   if (rc) return rc;
   if (with_fc3_grad) {
-    const int nblk = (rows + kFc3Rows - 1) / kFc3Rows;
+    const int nblk = tail_grid(rows);
     float* gW3 = h->grads + (size_t)h->L * kLayerStride;
-    cudaStream_t fs = s;
-    bool first_pdl = true;
-    if (h->fc3_overlap) {
-      // fork: the two fc3 gradient kernels (10 us, 160 + 65 small CTAs) only need G3 and ACT[L] from the tail; they run on
-      // the SMs the 80-CTA dgrad chain leaves idle and are joined at the end of launch_backward_gemms
-      rc = ensure_side_stream(h);
-      if (rc) return rc;
-      ACEZ_CUDA(cudaEventRecord(h->ev_dz[0], s));
-      ACEZ_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_dz[0], 0));
-      fs = h->side_stream;
-      first_pdl = false;  // predecessor on that stream is an event wait, not a kernel
-      h->fc3_pending = true;
-    }
-    rc = launch_pdl(fc3_wgrad_partial_kernel, dim3(nblk), dim3(kFc3Threads), 0, fs, first_pdl, t.x, (const float*)h->G3, rows, h->FC3PART);
-    if (rc) return rc;
     const int total = 4 * kC + 4;
-    rc = launch_pdl(fc3_reduce_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, fs, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
+    rc = launch_pdl(fc3_reduce_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, s, true, (const float*)h->FC3PART, nblk, h->C3, gW3,
                     gW3 + (size_t)h->C3 * kC, nonfinite);
     if (rc) return rc;
   }
@@ -706,7 +890,7 @@ static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfini
   const int L = h->L;
   if (h->use_chain && L >= 2) {
     h->chain_bwd.args.nonfinite = nonfinite;
-    int rc = chain_launch(h->chain_bwd, s, /*pdl=*/!h->fc3_pending);  // predecessor: fc3_reduce_kernel (or the side-stream fork)
+    int rc = chain_launch(h->chain_bwd, s, /*pdl=*/true);  // predecessor: fc3_reduce_kernel
     if (rc) return rc;
     if (h->use_wgrad2) {
       h->wgrad2.args.nonfinite = nonfinite;
@@ -716,11 +900,6 @@ static int launch_backward_gemms(acez_head_plan* h, cudaStream_t s, int* nonfini
       rc = gemm_launch(h->wgrad, s);
     }
     if (rc) return rc;
-    if (h->fc3_pending) {  // join the fc3 gradient kernels forked in launch_tail
-      ACEZ_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
-      ACEZ_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-      h->fc3_pending = false;
-    }
     return ACEZ_OK;
   }
   if (!h->overlap_wgrad) {
@@ -821,11 +1000,10 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
     h->use_chain = ((e == nullptr || atoi(e) != 0) && h->L <= kChainMaxSteps) ? 1 : 0;
   }
   {
+    // batched weight gradient on cta_group::2 tiles (gemm2cta.cu, 256 x 128 per SM pair): validated in round 2, 35.4 vs 44.7 us
+    // for the 8 x 512 x 512 x 5120 launch; ACEZ_WGRAD_2CTA=0 selects the cta_group::1 kernel of gemm.cu
     const char* e = getenv("ACEZ_WGRAD_2CTA");
-    h->use_wgrad2 = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    const char* f = getenv("ACEZ_FC3_OVERLAP");   // only with the fused chain (the join sits in its branch of the backward)
-    h->fc3_overlap = (f != nullptr && atoi(f) != 0 && h->use_chain) ? 1 : 0;
-    h->fc3_pending = false;
+    h->use_wgrad2 = (e == nullptr || atoi(e) != 0) ? 1 : 0;
   }
   h->act_stride = (size_t)cfg->max_rows * kC;
   h->prepared_rows = -1;
@@ -918,7 +1096,6 @@ extern "C" int acez_head_train_fwd_bwd(acez_head_plan* h, int rows, const acez_l
   t.grad_scale_dev = b->grad_scale_dev;
   t.loss_weight_dev = b->loss_weight_dev;
   t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
-  t.g3 = h->G3;
   t.stats = stats;
   t.nonfinite = nonfinite;
   rc = launch_tail(h, t, rows, s, nonfinite, true, true);
@@ -942,7 +1119,6 @@ extern "C" int acez_head_backward(acez_head_plan* h, int rows, const float* d_sc
   t.lp.grad_scale = 1.f; t.lp.divisor = 1;
   t.d_sc_in = d_sc_b3;
   t.dz = h->DZ + (size_t)(L - 1) * h->act_stride;
-  t.g3 = h->G3;
   t.stats = nullptr;
   t.nonfinite = nonfinite;
   rc = launch_tail(h, t, rows, s, nonfinite, true, false);  // first kernel of this call

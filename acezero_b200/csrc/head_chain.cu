@@ -677,6 +677,18 @@ static long long* g_chain_dbg = nullptr;
 static int g_chain_dbg_ctas = 0;
 static constexpr int kChainDbgMaxCtas = 1024;
 
+long long* chain_debug_buffer(int ctas) {
+  static const bool want_dbg = [] {
+    const char* e = getenv("ACEZ_CHAIN_DBG");
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (!want_dbg || ctas > kChainDbgMaxCtas) return nullptr;
+  if (g_chain_dbg == nullptr && cudaMalloc(&g_chain_dbg, (size_t)kChainDbgMaxCtas * kChainDbgSlots * sizeof(long long)) != cudaSuccess)
+    return nullptr;
+  g_chain_dbg_ctas = ctas;
+  return g_chain_dbg;
+}
+
 int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas) {
   ACEZ_REQUIRE(host_out != nullptr && n_ctas != nullptr, "chain_debug_read: null argument");
   *n_ctas = 0;

@@ -61,6 +61,8 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
 // pdl: launch with the programmatic-dependent-launch attribute (only when the stream predecessor is a kernel)
 int chain_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl = false);
 int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl);  // cta_group::2 on a cluster of 4 (head_chain4.cu)
+// profiling probe: device buffer for the clock64 stamps of a launch with `ctas` CTAs (nullptr unless ACEZ_CHAIN_DBG=1)
+long long* chain_debug_buffer(int ctas);
 // profiling probe: copies the stamps of the most recent launch with ACEZ_CHAIN_DBG=1 to host memory
 int chain_debug_read(long long* host_out, size_t max_slots, int* n_ctas);
 

@@ -124,17 +124,16 @@ __device__ __forceinline__ void c4_dsmem_copy(uint32_t dst_cluster, uint32_t src
 }
 __device__ __forceinline__ void c4_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// consumption order of the 8 k-blocks by arrival. Two epilogue groups publish own boxes 0,1 first and 2,3 one box time
-// later: own 0,1 | exchange partner's 0,1 | own 2,3 | partner's 2,3. Four groups publish all own boxes together: own 0..3 |
-// partner's 0..3.
-template <int G>
-__device__ __forceinline__ int c4_order(int i, int c) {
-  if (G == 4) return (i < 4 ? c : (c ^ 1)) * 4 + (i & 3);
+// consumption order of the 8 k-blocks. Two epilogue groups publish own boxes 0,1 first and 2,3 one box time later, so the
+// ARRIVAL order is own 0,1 | exchange partner's 0,1 | own 2,3 | partner's 2,3. The alternative (own_first: own 0..3 | partner's
+// 0..3, the order of the cta_group::1 chain; four groups publish all own boxes together) sums the k-blocks in an order
+// closer to the index order of the per-layer kernels / the CPU oracle: same arithmetic, different fp32 summation order.
+__device__ __forceinline__ int c4_order(int i, int c, bool own_first) {
+  if (own_first) return (i < 4 ? c : (c ^ 1)) * 4 + (i & 3);
   const int b = ((i >> 2) << 1) | (i & 1);
   return ((i & 2) ? (c ^ 1) : c) * 4 + b;
 }
-template <int G>
-__device__ __forceinline__ bool c4_is_partner_box(int i) { return G == 4 ? i >= 4 : (i & 2) != 0; }
+__device__ __forceinline__ bool c4_is_partner_box(int i, bool own_first) { return own_first ? i >= 4 : (i & 2) != 0; }
 
 // prmt.b32 with the sign-replicate bit (8) in the selector nibbles: byte <- 0xFF / 0x00 from the msb of the selected byte
 __device__ __forceinline__ uint32_t c4_prmt(uint32_t a, uint32_t b, uint32_t sel) {
@@ -175,6 +174,8 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   const int n_base = c * CN;                // the pair's output channels of every layer
   const int nb_half = n_base + r * (CN / 2);
   const int n_steps = args.n_steps;
+  const bool own_first = (G == 4) || (args.flags & 256) != 0;   // k-block consumption order (ACEZ_CHAIN_ORDER=own)
+  long long* dbg = args.dbg != nullptr ? args.dbg + (size_t)blockIdx.x * kChainDbgSlots : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmIn);
@@ -203,12 +204,13 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   // here on. (A plain launch returns from the wait at once.) The successor may be scheduled as soon as SMs free up.
   pdl_wait();
   pdl_launch_dependents();
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       for (int i = 0; i < kKB; ++i) {
-        const int j = c4_order<G>(i, c);
+        const int j = c4_order(i, c, own_first);
         mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);
         tma_load_3d(sA + j * kBoxBytes, &tmIn, &a_ready[j], j * CK, m0, 0);
       }
@@ -217,7 +219,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       for (int s = 0; s < n_steps; ++s) {
         const int wl = args.step[s].w_layer;
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order<G>(i, c);
+          const int j = c4_order(i, c, own_first);
           c4_wait<0>(&b_empty[stage], phase ^ 1, (3u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * kBHalf);
           else c4_arrive_leader(&b_full[stage]);
@@ -244,12 +246,13 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       for (int s = 0; s < n_steps; ++s) {
         const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * CN);
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order<G>(i, c);
+          const int j = c4_order(i, c, own_first);
           c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
-          if (c4_is_partner_box<G>(i) && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+          if (c4_is_partner_box(i, own_first) && s + 1 < n_steps && lane == 0) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
           c4_wait<2>(&partner_ready[j], (uint32_t)(s & 1), (7u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
           c4_wait<0>(&b_full[stage], phase, (2u << 16) | ((uint32_t)s << 8) | (uint32_t)i);
           tcgen05_fence_after();
+          if (dbg && lane == 0 && (i == 0 || i == 2 || i == 7)) dbg[8 + 8 * s + (i == 0 ? 0 : (i == 7 ? 2 : 1))] = clock64();
           if (elect_one()) {
             const uint32_t a_addr = smem_u32(sA + j * kBoxBytes);
             const uint32_t b_addr = smem_u32(sB + stage * kBHalf);
@@ -269,17 +272,20 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
           if (++stage == kBStages) { stage = 0; phase ^= 1; }
         }
         c4_wait<0>(&tmem_full[s & 1], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8) | 1u);
-        if (lane == 0) c4_arrive_remote_relaxed(xpeer_free);
+        if (lane == 0) {
+          c4_arrive_remote_relaxed(xpeer_free);
+          if (dbg) dbg[8 + 8 * s + 3] = clock64();
+        }
         __syncwarp();
       }
     } else {
       // ------------------------------ relay (the other CTA of the pair) ------------------------------
       for (int s = 0; s < n_steps; ++s) {
         for (int i = 0; i < kKB; ++i) {
-          const int j = c4_order<G>(i, c);
+          const int j = c4_order(i, c, own_first);
           c4_wait<0>(&a_ready[j], (uint32_t)(s & 1), (1u << 16) | ((uint32_t)s << 8) | (uint32_t)j);
           if (lane == 0) {
-            if (c4_is_partner_box<G>(i) && s + 1 < n_steps) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
+            if (c4_is_partner_box(i, own_first) && s + 1 < n_steps) mbar_arrive_expect_tx(&a_ready[j], kBoxBytes);  // arm the next phase
             // my k-block j of step s is in place IN MY OWN shared memory (generic-proxy writes were fenced by their writers,
             // async copies completed on the barrier) and it is my own tensor core that will read it: the signal to the
             // leader, which issues the UMMAs for both CTAs, carries no data - relaxed, no fence (a release at cluster scope
@@ -337,104 +343,117 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         if (s > 0) bar_all();
         if (etid < CN) sBiasF[etid] = __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
       }
-      c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
-      tcgen05_fence_after();
-      bar_all();
-      const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
-      const bool want_mask = !kDgrad && st.mask_out != nullptr;
+      // ReLU-mask words of this thread's row for all its boxes (dgrad): in flight while the accumulator is still being computed
+      uint2 mw[NB];
 #pragma unroll
       for (int sl = 0; sl < NB; ++sl) {
+        mw[sl] = make_uint2(0u, 0u);
+        if (kDgrad && row_ok) mw[sl] = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + (c * 4 + grp + G * sl) * 8));
+      }
+      if (issuer) {
+        // peer_free phase s: the exchange partner's MMAs of step s have retired, i.e. it has consumed the boxes copied to it
+        // during step s-1 (those copies no longer read the boxes rewritten below) and its A buffer may be overwritten.
+        c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
+        // the TMA stores of the previous step (issued one whole step ago) have finished reading this group's boxes
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (dbg && grp == 0) dbg[8 + 8 * s + 5] = clock64();
+      }
+      c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
+      tcgen05_fence_after();
+      if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
+      bar_all();   // bias slice visible; the issuers' permissions (above) hold for every thread of their group
+      const int res_add = st.res_add, res_save = st.res_save, relu = st.relu;
+      const bool want_mask = !kDgrad && st.mask_out != nullptr;
+      const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+      // The group's boxes are drained in 32-column halves with the TMEM loads software-pipelined: while the registers of
+      // half p are processed, the load of half p+1 is in flight (TMEM reads are the floor of the epilogue: 128 KB of
+      // accumulators per layer and CTA)
+      uint32_t vv[2][32];
+      uint32_t bits_lo = 0u, bits_hi = 0u;
+      tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + grp * 64), vv[0]);
+#pragma unroll
+      for (int p = 0; p < 2 * NB; ++p) {
+        const int sl = p >> 1, hf = p & 1;
         const int box = grp + G * sl;
         const int j = c * 4 + box;
-        const int col0 = n_base + box * 64;
-        uint2 mw = make_uint2(0u, 0u);
-        if (kDgrad && row_ok) mw = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + j * 8));
-        if (issuer) {
-          // peer_free phase s: the exchange partner's MMAs of step s have retired, i.e. it has consumed the boxes copied to it
-          // during step s-1 (those copies no longer read the boxes rewritten below) and its A buffer may be overwritten
-          if (sl == 0) c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
-          // the TMA store that last read this box's memory has finished reading (one bulk group per box)
-          if (NB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        tmem_ld_wait_for(vv[p & 1]);
+        if (p + 1 < 2 * NB) {
+          const int nbox = grp + G * ((p + 1) >> 1);
+          tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + nbox * 64 + ((p + 1) & 1) * 32), vv[(p + 1) & 1]);
         }
-        bar_group();
         uint8_t* dst = sA + j * kBoxBytes + rr * 128;
-        uint32_t bits_lo = 0u, bits_hi = 0u;
-        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t vv[32];
-          tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + box * 64 + hf * 32), vv);
-          tmem_ld_wait();
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int q = hf * 4 + q4;
+          uint4 o;
+          uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+          if (!kDgrad) {
+            const float4 bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
+            const float4 bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
+            const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
+            uint32_t mm[4];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int q = hf * 4 + q4;
-            uint4 o;
-            uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
-            if (!kDgrad) {
-              const float4 bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
-              const float4 bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
-              const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
-              uint32_t mm[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int vc = q4 * 8 + 2 * t;
-                // single rounding of (acc + bias) to fp16; ReLU on the rounded value gives the same result as before it
-                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]) + bq[2 * t], __uint_as_float(vv[vc + 1]) + bq[2 * t + 1]);
-                if (relu) h = __hmax2(h, zero2);
-                mm[t] = __hgt2_mask(h, zero2);   // 0xFFFF per half that is > 0 (pre-residual x: the backward's ReLU mask)
-                uint32_t& rs = res[sl][4 * q + t];
-                if (res_add) {
-                  h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);  // residual sum in fp16, as the reference's `res + x`
-                  rs = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                ob[t] = *reinterpret_cast<const uint32_t*>(&h);
+            for (int t = 0; t < 4; ++t) {
+              const int vc = q4 * 8 + 2 * t;
+              // single rounding of (acc + bias) to fp16; ReLU on the rounded value gives the same result as before it
+              __half2 h = __floats2half2_rn(__uint_as_float(vv[p & 1][vc]) + bq[2 * t], __uint_as_float(vv[p & 1][vc + 1]) + bq[2 * t + 1]);
+              if (relu) h = __hmax2(h, zero2);
+              mm[t] = __hgt2_mask(h, zero2);   // 0xFFFF per half that is > 0 (pre-residual x: the backward's ReLU mask)
+              uint32_t& rs = res[sl][4 * q + t];
+              if (res_add) {
+                h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);  // residual sum in fp16, as the reference's `res + x`
+                rs = *reinterpret_cast<const uint32_t*>(&h);
               }
-              if (want_mask) {
-                // 8 columns -> 8 bits (bit k = column 8 q + k): gather one byte per half, fold with a multiply
-                const uint32_t P = __byte_perm(mm[0], mm[1], 0x6420);
-                const uint32_t Q = __byte_perm(mm[2], mm[3], 0x6420);
-                const uint32_t byte = (((P & 0x08040201u) * 0x01010101u) >> 24) | (((Q & 0x80402010u) * 0x01010101u) >> 24);
-                if (q < 4) bits_lo |= byte << (8 * q);
-                else bits_hi |= byte << (8 * (q - 4));
-              }
-            } else {
-              // ReLU mask of the activation this gradient flows into: bit k of byte q = column 8 q + k. Spread the byte's
-              // bits to the sign bits of 8 bytes (multiply), then prmt with sign replication makes 0xFFFF / 0 per half.
-              const uint32_t b = ((q < 4) ? (mw.x >> (8 * q)) : (mw.y >> (8 * (q - 4)))) & 0xFFu;
-              const uint32_t w_lo = (b & 0xFu) * 0x10204080u;
-              const uint32_t w_hi = (b >> 4) * 0x10204080u;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const int vc = q4 * 8 + 2 * t;
-                uint32_t& rs = res[sl][4 * q + t];
-                // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
-                __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
-                if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
-                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-                if (res_save) rs = hb;   // the unmasked sum is the skip-path gradient of the block below
-                badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
-                const uint32_t m = c4_prmt((t < 2) ? w_lo : w_hi, 0u, (t & 1) ? 0xBBAAu : 0x9988u);
-                ob[t] = hb & m;
-              }
+              ob[t] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+            if (want_mask) {
+              // 8 columns -> 8 bits (bit k = column 8 q + k): gather one byte per half, fold with a multiply
+              const uint32_t P = __byte_perm(mm[0], mm[1], 0x6420);
+              const uint32_t Q = __byte_perm(mm[2], mm[3], 0x6420);
+              const uint32_t byte = (((P & 0x08040201u) * 0x01010101u) >> 24) | (((Q & 0x80402010u) * 0x01010101u) >> 24);
+              if (q < 4) bits_lo |= byte << (8 * q);
+              else bits_hi |= byte << (8 * (q - 4));
+            }
+          } else {
+            // ReLU mask of the activation this gradient flows into: bit k of byte q = column 8 q + k. Spread the byte's
+            // bits to the sign bits of 8 bytes (multiply), then prmt with sign replication makes 0xFFFF / 0 per half.
+            const uint32_t b = ((q < 4) ? (mw[sl].x >> (8 * q)) : (mw[sl].y >> (8 * (q - 4)))) & 0xFFu;
+            const uint32_t w_lo = (b & 0xFu) * 0x10204080u;
+            const uint32_t w_hi = (b >> 4) * 0x10204080u;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int vc = q4 * 8 + 2 * t;
+              uint32_t& rs = res[sl][4 * q + t];
+              // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
+              __half2 h = __floats2half2_rn(__uint_as_float(vv[p & 1][vc]), __uint_as_float(vv[p & 1][vc + 1]));
+              if (res_add) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
+              const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+              if (res_save) rs = hb;   // the unmasked sum is the skip-path gradient of the block below
+              badbits |= ((hb & 0x7C007C00u) + 0x04000400u) & 0x80008000u;  // exponent all ones: inf / nan
+              const uint32_t m = c4_prmt((t < 2) ? w_lo : w_hi, 0u, (t & 1) ? 0xBBAAu : 0x9988u);
+              ob[t] = hb & m;
+            }
           }
+          *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
         }
-        // this TMEM buffer is rewritten by the MMAs of step s+2, which are released (transitively) by the barrier arrivals
-        // below: order the completed tcgen05.ld before them
-        tcgen05_fence_before();
-        if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
-        fence_proxy_async();   // the box is complete in shared memory: publish it to the tensor core / copy engines
-        bar_group();
-        if (issuer) {
-          const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
-          if (!last) {
-            mbar_arrive(&a_ready[j]);
-            c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
+        if (hf == 1) {
+          // box complete. Its TMEM columns are rewritten by the MMAs of step s+2, which are released (transitively) by the
+          // barrier arrivals below: order the completed tcgen05.ld before them
+          tcgen05_fence_before();
+          if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
+          bits_lo = 0u; bits_hi = 0u;
+          fence_proxy_async();   // publish the box to the tensor core / copy engines (async proxy)
+          bar_group();
+          if (issuer) {
+            const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+            if (!last) {
+              mbar_arrive(&a_ready[j]);
+              c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
+            }
+            if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, n_base + box * 64, m0, st.out_slot);
+            tma_store_commit();
+            if (dbg && grp == 0) dbg[8 + 8 * s + (sl == 0 ? 6 : 7)] = clock64();
           }
-          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, col0, m0, st.out_slot);
-          tma_store_commit();   // always one group per box (keeps the wait_group.read accounting exact)
         }
       }
     }
@@ -444,6 +463,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     }
   }
 
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   __syncwarp();
   tcgen05_fence_before();
   c4_cluster_sync();
@@ -486,7 +506,14 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pd
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
-  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, tmW4, C.tmOut, C.args));
+  ChainArgs args = C.args;
+  static const bool own_first = [] {
+    const char* e = getenv("ACEZ_CHAIN_ORDER");
+    return e != nullptr && e[0] == 'o';
+  }();
+  if (own_first) args.flags |= 256;
+  args.dbg = chain_debug_buffer(4 * clusters);   // nullptr unless ACEZ_CHAIN_DBG=1 (tools/probe_chain_time.py)
+  ACEZ_CUDA(cudaLaunchKernelEx(&cfg, kern, C.tmIn, tmW4, C.tmOut, args));
   return ACEZ_OK;
 }
 

@@ -130,3 +130,31 @@ class SyntheticDataset(Dataset):
         if isinstance(idx, list):
             return default_collate([self._single(i) for i in idx])
         return self._single(idx)
+
+
+class CachedDataset(Dataset):
+    """The items of another dataset rendered ONCE and served from host memory (benchmarks: the procedural renderer of
+    SyntheticDataset costs more than the encoder; real datasets decode on DataLoader workers). Same 9-tuples, same
+    accessor surface as CamLocDataset / SyntheticDataset."""
+
+    def __init__(self, base):
+        self.base = base
+        self.items = [base[i] for i in range(len(base))]
+        self.rgb_files = base.rgb_files
+        self.poses = base.poses
+        self.mean_cam_center = base.mean_cam_center
+
+    def __len__(self):
+        return len(self.items)
+
+    def set_external_focal_length(self, f):
+        self.base.set_external_focal_length(f)
+        self.items = [self.base[i] for i in range(len(self.base))]
+
+    def get_focal_length(self, idx):
+        return self.base.get_focal_length(idx)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, list):
+            return default_collate([self.items[i] for i in idx])
+        return self.items[idx]

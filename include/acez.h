@@ -196,7 +196,9 @@ typedef struct acez_train_batch {
 } acez_train_batch;
 
 /* One head forward + reprojection loss + full backward into `grads` (overwritten, scaled by grad_scale).
- * stats: [4] floats as in acez_repro_loss_fwd_bwd, overwritten by the call. nonfinite (int, device) is overwritten: 1 if
+ * stats: [4] floats as in acez_repro_loss_fwd_bwd; [0..2] are overwritten by the call, [3] (non-finite loss seen) is a LATCH:
+ * it is OR-ed with its previous value, so a caller that reads the statistics only every n-th iteration cannot miss a NaN
+ * (the reference checks every iteration, ace_trainer.py:615-617); the caller zeroes it. nonfinite (int, device) is overwritten: 1 if
  * any activation gradient or (fp16-rounded) weight gradient is inf/nan — the complete GradScaler found_inf of this
  * backward pass. Replaces ace_trainer.py:516-627. */
 int acez_head_train_fwd_bwd(acez_head_plan* plan, int rows, const acez_loss_params* lp, const acez_train_batch* batch,

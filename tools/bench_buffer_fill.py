@@ -14,25 +14,14 @@ import torch
 sys.path.insert(0, ".")
 import train_ace  # noqa: E402
 from ace_trainer import TrainerACE  # noqa: E402
-from acezero_b200.synthetic import SyntheticDataset  # noqa: E402
+from acezero_b200.synthetic import CachedDataset, SyntheticDataset  # noqa: E402
 from acezero_b200.weights import random_encoder_state  # noqa: E402
-
-
-class CachedDataset(SyntheticDataset):
-    """Renders every frame once; afterwards items come from host memory like decoded images would."""
-
-    def build_cache(self):
-        self._cache = [SyntheticDataset._single(self, i) for i in range(len(self))]
-
-    def _single(self, idx):
-        return self._cache[idx]
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     passes = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    ds = CachedDataset(n, H=480, W=640, focal=525.0, device="cuda")
-    ds.build_cache()
+    ds = CachedDataset(SyntheticDataset(n, H=480, W=640, focal=525.0, device="cuda"))
     with tempfile.TemporaryDirectory() as tmp:
         o = train_ace.build_parser().parse_args(["synthetic", str(Path(tmp) / "map.pt")])
         o.encoder_state_dict = random_encoder_state(77)
