@@ -149,6 +149,7 @@ class TrainerACE:
         t0 = time.time()
         while self.loop.run_epoch(on_iteration=self._log_iteration):
             pass
+        self.loop.finish()            # device schedule -> host: the final iteration count (cool-down may have shortened it)
         torch.cuda.synchronize()
         training_time = time.time() - t0
         self.iteration, self.epoch = self.loop.iteration, self.loop.epoch

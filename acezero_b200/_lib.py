@@ -68,6 +68,19 @@ class DsacParams(C.Structure):
     ]
 
 
+class ScheduleParams(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("iterations", C.c_int), ("lr_min", C.c_float), ("lr_max", C.c_float),
+        ("warmup_iterations", C.c_int), ("warmup_lr", C.c_float), ("cooldown_iterations", C.c_int),
+        ("cooldown_trigger", C.c_float), ("batch_global", C.c_int), ("loss_dyntanh", C.c_int),
+        ("loss_schedule_circle", C.c_int), ("soft_clamp", C.c_float), ("soft_clamp_min", C.c_float),
+    ]
+
+
+SCHED_STATE_FLOATS = 128
+SCHED_KINDS = {"constant": 0, "circle": 1, "1cyclepoly": 2}
+
+
 class DsacDebug(C.Structure):
     _fields_ = [
         ("hyp_poses", C.c_void_p), ("hyp_scores", C.c_void_p), ("best", C.c_void_p), ("hyp_tries", C.c_void_p),
@@ -83,7 +96,7 @@ EXPORTS = [
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
     "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_plan_fused_chain", "acez_debug_chain_clocks", "acez_head_forward", "acez_head_forward_train",
     "acez_head_backward", "acez_head_train_fwd_bwd",
-    "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
+    "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_schedule_init", "acez_schedule_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
     "acez_encoder_forward",
 ]
@@ -125,6 +138,8 @@ def load():
     lib.acez_gather_rows_multi.argtypes = [vp, vp, vp, i, vp, i, vp]
     lib.acez_buffer_fill.argtypes = [vp, vp, i, i, i, i, vp, vp, i, C.c_longlong] + [vp] * 8 + [vp]
     lib.acez_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, i, vp, vp]
+    lib.acez_schedule_init.argtypes = [C.POINTER(ScheduleParams), vp, vp]
+    lib.acez_schedule_step.argtypes = [C.POINTER(ScheduleParams), vp, vp, vp, vp]
     lib.acez_dsac_workspace_bytes.argtypes = [i, i, i, i]
     lib.acez_dsac_workspace_bytes.restype = C.c_size_t
     lib.acez_dsac_forward_rgb_batch.argtypes = [vp, i, i, i, vp, vp, vp, C.POINTER(DsacParams), vp, vp, vp,

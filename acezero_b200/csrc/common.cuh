@@ -63,6 +63,25 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- explicit shared-space accesses (a generic pointer into dynamic shared memory compiles to LD.E / ST.E: generic-address
+// instructions that resolve the address space at run time; measured on the chain epilogue: they dominate its issue stalls) ----
+__device__ __forceinline__ void sts_128(uint32_t smem_addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_128f(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t smem_addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_addr), "f"(v) : "memory");
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

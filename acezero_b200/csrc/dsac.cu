@@ -247,21 +247,16 @@ struct DsacArgs {
   int stage_smem;
 };
 
-// stage the image's scene coordinates (3 planes) into shared memory, or fall back to global pointers
-__device__ __forceinline__ const float* stage_sc(const DsacArgs& a, int img, float* smem, int cells) {
+// stage the image's scene coordinates (3 planes) into shared memory. The kernels index the `extern __shared__` array itself
+// afterwards (a pointer that may be global OR shared compiles to generic LD.E in the scoring loop)
+__device__ __forceinline__ void stage_sc(const DsacArgs& a, int img, float* smem, int cells) {
   const float* g = a.sc + (size_t)img * 3 * cells;
-  if (!a.stage_smem) return g;
-  for (int i = threadIdx.x; i < 3 * cells; i += blockDim.x) smem[i] = g[i];
+  for (int i = threadIdx.x; i < 3 * cells; i += blockDim.x) smem[i] = __ldg(g + i);
   __syncthreads();
-  return smem;
 }
 
 // ---------------------------------------------------------------- kernel 1: sample + score
 __global__ void __launch_bounds__(kDsacThreads) dsac_sample_score_kernel(const DsacArgs a) {
-#include "dsac_sample_body.inc"
-}
-// ACEZ_DSAC_OCC=1 (experimental): 80 registers (128 otherwise, ~250 B of spills): three CTAs per SM instead of two.
-__global__ void __launch_bounds__(kDsacThreads, 3) dsac_sample_score_kernel_occ3(const DsacArgs a) {
 #include "dsac_sample_body.inc"
 }
 
@@ -337,10 +332,6 @@ __device__ void block_sum(double (&v)[CNT], double* s_part /*[warps][CNT]*/, dou
 __global__ void __launch_bounds__(kDsacThreads) dsac_refine_kernel(const DsacArgs a) {
 #include "dsac_refine_body.inc"
 }
-// ACEZ_DSAC_OCC=1 (experimental): 128 registers (235 otherwise, ~700 B of spills): two CTAs per SM instead of one.
-__global__ void __launch_bounds__(kDsacThreads, 2) dsac_refine_kernel_occ2(const DsacArgs a) {
-#include "dsac_refine_body.inc"
-}
 
 }  // namespace acez
 
@@ -375,8 +366,9 @@ extern "C" int acez_dsac_forward_rgb_batch(const float* sc, int n, int h, int w,
   a.out_inliers = out_inliers;
   if (dbg) a.dbg = *dbg;
   const int cells = h * w;
-  a.stage_smem = cells <= kMaxSmemCells ? 1 : 0;
-  const size_t smem1 = a.stage_smem ? (size_t)cells * 12 : 0;
+  ACEZ_REQUIRE(cells <= kMaxSmemCells, "dsac: %d cells exceed the shared-memory staging budget (%d)", cells, kMaxSmemCells);
+  a.stage_smem = 1;
+  const size_t smem1 = (size_t)cells * 12;
   const size_t smem2 = smem1 + (size_t)cells * 2;
   static bool configured = false;
   if (!configured) {
@@ -391,23 +383,6 @@ extern "C" int acez_dsac_forward_rgb_batch(const float* sc, int n, int h, int w,
   const int want = (2 * sm_count() + n - 1) / n;
   if (chunks > want) chunks = want < 1 ? 1 : want;
   dim3 grid1(chunks, n);
-  static const bool occ = [] {
-    const char* e = getenv("ACEZ_DSAC_OCC");
-    return e != nullptr && atoi(e) != 0;
-  }();
-  if (occ) {
-    static bool configured_occ = false;
-    if (!configured_occ) {
-      ACEZ_CUDA(cudaFuncSetAttribute(dsac_sample_score_kernel_occ3, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      ACEZ_CUDA(cudaFuncSetAttribute(dsac_refine_kernel_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      configured_occ = true;
-    }
-    dsac_sample_score_kernel_occ3<<<grid1, kDsacThreads, smem1, s>>>(a);
-    ACEZ_CUDA(cudaGetLastError());
-    dsac_refine_kernel_occ2<<<n, kDsacThreads, smem2, s>>>(a);
-    ACEZ_CUDA(cudaGetLastError());
-    return ACEZ_OK;
-  }
   dsac_sample_score_kernel<<<grid1, kDsacThreads, smem1, s>>>(a);
   ACEZ_CUDA(cudaGetLastError());
   dsac_refine_kernel<<<n, kDsacThreads, smem2, s>>>(a);

@@ -211,6 +211,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // all pipeline stages are drained by now: their memory stages the output tiles for the TMA stores
     uint8_t* sOut = smem;
     uint8_t* sOut2 = smem + BM * BN * 2;
+    const uint32_t sOut_u32 = smem_u32(sOut), sOut2_u32 = smem_u32(sOut2), sOp_u32 = smem_u32(sOp), sBias_u32 = smem_u32(sBias);
     const uint32_t swz = (uint32_t)(r & 7);
     bool bad = false;
     if (EPI == EPI_WGRAD) {
@@ -250,17 +251,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 8; ++q) {
           const uint32_t off = row_off + ((((uint32_t)q) ^ swz) << 4);
           uint4 opv = make_uint4(0, 0, 0, 0);
-          if (args.ld_op) opv = *reinterpret_cast<const uint4*>(sOp + off);
+          if (args.ld_op) opv = lds_128(sOp_u32 + off);   // explicit shared-space access (a generic pointer compiles to LD.E / ST.E)
           const __half2* ph = reinterpret_cast<const __half2*>(&opv);
           uint4 o, o2;
           __half2* oh = reinterpret_cast<__half2*>(&o);
           __half2* o2h = reinterpret_cast<__half2*>(&o2);
           if (EPI == EPI_FWD) {
+            const float4 bf0 = lds_128f(sBias_u32 + 4u * (uint32_t)(box * 64 + q * 8));
+            const float4 bf1 = lds_128f(sBias_u32 + 4u * (uint32_t)(box * 64 + q * 8 + 4));
+            const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int col = q * 8 + 2 * j;
-              float a = __uint_as_float(v[col]) + sBias[box * 64 + col];
-              float b = __uint_as_float(v[col + 1]) + sBias[box * 64 + col + 1];
+              float a = __uint_as_float(v[col]) + bq[2 * j];
+              float b = __uint_as_float(v[col + 1]) + bq[2 * j + 1];
               if (args.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
               const __half2 h = __floats2half2_rn(a, b);
               oh[j] = h;
@@ -286,8 +290,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ob[j] = hb & __hgt2_mask(ph[j], zero2);                       // ReLU mask from the saved activation
             }
           }
-          if (args.st_out) *reinterpret_cast<uint4*>(sOut + off) = o;
-          if (args.st_out2) *reinterpret_cast<uint4*>(sOut2 + off) = o2;
+          if (args.st_out) sts_128(sOut_u32 + off, o);
+          if (args.st_out2) sts_128(sOut2_u32 + off, o2);
         }
         // the box is complete in shared memory: hand it to the TMA store engine
         fence_proxy_async();

@@ -311,6 +311,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     const bool issuer = (lane == 0) && (quarter == (G == 2 ? 2 - 2 * grp : grp));
     const uint32_t swz = (uint32_t)(rr & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sA_u32 = smem_u32(sA), sBias_u32 = smem_u32(sBiasF);
     auto bar_group = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
     auto bar_all = [&]() { asm volatile("bar.sync 6, %0;" ::"n"(kEpiThreads) : "memory"); };
     uint32_t badbits = 0;
@@ -325,10 +326,10 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
       for (int sl = 0; sl < NB; ++sl) {
         const int j = c * 4 + grp + G * sl;
         c4_wait<0>(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
-        const uint8_t* src = sA + j * kBoxBytes + rr * 128;
+        const uint32_t src = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const uint4 t = *reinterpret_cast<const uint4*>(src + ((((uint32_t)q) ^ swz) << 4));
+          const uint4 t = lds_128(src + ((((uint32_t)q) ^ swz) << 4));
           res[sl][4 * q] = t.x; res[sl][4 * q + 1] = t.y; res[sl][4 * q + 2] = t.z; res[sl][4 * q + 3] = t.w;
         }
       }
@@ -341,7 +342,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         // fp32 copy of the fp16-rounded bias slice (autocast casts the bias to fp16 before the conv adds it); every
         // epilogue warp must have finished the previous step's boxes before it is overwritten
         if (s > 0) bar_all();
-        if (etid < CN) sBiasF[etid] = __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f));
+        if (etid < CN) sts_f32(sBias_u32 + 4u * (uint32_t)etid, __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f)));
       }
       // ReLU-mask words of this thread's row for all its boxes (dgrad): in flight while the accumulator is still being computed
       uint2 mw[NB];
@@ -381,15 +382,15 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
           const int nbox = grp + G * ((p + 1) >> 1);
           tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + nbox * 64 + ((p + 1) & 1) * 32), vv[(p + 1) & 1]);
         }
-        uint8_t* dst = sA + j * kBoxBytes + rr * 128;
+        const uint32_t dst = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const int q = hf * 4 + q4;
           uint4 o;
           uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
           if (!kDgrad) {
-            const float4 bf0 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8);
-            const float4 bf1 = *reinterpret_cast<const float4*>(sBiasF + box * 64 + q * 8 + 4);
+            const float4 bf0 = lds_128f(sBias_u32 + 4u * (uint32_t)(box * 64 + q * 8));
+            const float4 bf1 = lds_128f(sBias_u32 + 4u * (uint32_t)(box * 64 + q * 8 + 4));
             const float bq[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w};
             uint32_t mm[4];
 #pragma unroll
@@ -434,7 +435,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
               ob[t] = hb & m;
             }
           }
-          *reinterpret_cast<uint4*>(dst + ((((uint32_t)q) ^ swz) << 4)) = o;
+          sts_128(dst + ((((uint32_t)q) ^ swz) << 4), o);
         }
         if (hf == 1) {
           // box complete. Its TMEM columns are rewritten by the MMAs of step s+2, which are released (transitively) by the

@@ -16,6 +16,12 @@ import torch.nn.functional as F
 from torch import optim
 
 
+def _capturable(device):
+    """torch.optim.AdamW(capturable=True) keeps its step counters on the device: the whole refinement iteration (kernels,
+    autograd of the refiners, their optimiser steps) can then be captured into one CUDA graph. Same update rule."""
+    return torch.device(device).type == "cuda"
+
+
 def special_gramschmidt(M):
     """Rotation from the first two columns of M (..., 3, 3): x = M[:, 0] normalised, y = M[:, 1] orthogonalised against
     x and normalised, z = x cross y; columns (x, y, z)."""
@@ -101,11 +107,12 @@ class PoseRefiner:
         self.pose_buffer = self.pose_buffer_orig.contiguous().to(self.device, non_blocking=True)
         if self.refinement_strategy == 'naive':
             self.pose_buffer = self.pose_buffer.detach().requires_grad_()
-            self.pose_optimizer = optim.AdamW([self.pose_buffer], lr=self.learning_rate)
+            self.pose_optimizer = optim.AdamW([self.pose_buffer], lr=self.learning_rate, capturable=_capturable(self.device))
         elif self.refinement_strategy == 'mlp':
             self.pose_network = PoseNetwork(0, 128).to(self.device)
             self.pose_network.train()
-            self.pose_optimizer = optim.AdamW(self.pose_network.parameters(), lr=self.learning_rate)
+            self.pose_optimizer = optim.AdamW(self.pose_network.parameters(), lr=self.learning_rate,
+                                              capturable=_capturable(self.device))
 
     def _orthonormalize_poses(self, poses_b33):
         if self.orthonormalization == 'none':
@@ -165,7 +172,7 @@ class CalibrationRefiner:
         self.focal_length_init = focal_lengths[0]
         self.device = device
         self.global_f = torch.zeros(1).to(device).detach().requires_grad_()
-        self.optimizer = optim.AdamW([self.global_f], lr=learning_rate)
+        self.optimizer = optim.AdamW([self.global_f], lr=learning_rate, capturable=_capturable(device))
 
     def get_focal_length(self):
         return (1 + self.global_f) * self.focal_length_init

@@ -147,10 +147,14 @@ class TrainLoop:
         self.pose_refiner = pose_refiner if (pose_refiner is not None and pose_refiner.active) else None
         self.K_optimizer = K_optimizer
         self.refining = self.pose_refiner is not None or self.K_optimizer is not None
-        # pose / calibration refinement runs PyTorch autograd between the kernels: eager launches, no CUDA graph
-        self.use_graph = use_graph and not self.refining
+        # pose / calibration refinement runs PyTorch autograd + torch optimisers (capturable) between the kernels: on one GPU
+        # the whole iteration, refiners included, is still ONE captured CUDA graph (two variants: with / without the pose
+        # optimiser step, ace_trainer.py:634-636); under data parallelism it stays eager (NCCL calls between the pieces)
+        self.use_graph = use_graph and not (self.refining and world_size > 1)
         self._graph = None
         self._warm = 0
+        self._refine_graphs = {}
+        self._refine_warm = {}
         import os
         self._dp_one_graph = world_size > 1 and os.environ.get("ACEZ_DP_ONE_GRAPH", "0") == "1"
         # experimental: the post-all-reduce check pass also reads the flag slot (3 tiny torch kernels less per iteration)
@@ -180,6 +184,29 @@ class TrainLoop:
             self.d_P = torch.zeros((self.b, 3, 4), device=d)
             self.d_Kdiag = torch.zeros((self.b, 2), device=d)
         self.loss_w_host = None
+        # ---- the schedule lives on the device (csrc/schedule.cu): lr, loss weight, cool-down trigger, max_iterations ----
+        o = options
+        sp = _lib.ScheduleParams()
+        sp.kind = _lib.SCHED_KINDS[o.learning_rate_schedule]
+        sp.iterations = int(o.iterations)
+        sp.lr_min, sp.lr_max = float(o.learning_rate_min), float(o.learning_rate_max)
+        sp.warmup_iterations = int(getattr(o, "learning_rate_warmup_iterations", 1) or 1)
+        sp.warmup_lr = float(getattr(o, "learning_rate_warmup_learning_rate", o.learning_rate_min))
+        sp.cooldown_iterations = int(getattr(o, "learning_rate_cooldown_iterations", 1) or 1)
+        sp.cooldown_trigger = float(getattr(o, "learning_rate_cooldown_trigger_percent_threshold", 2.0))
+        sp.batch_global = int(self.b_global)
+        sp.loss_dyntanh = int(o.repro_loss_type == "dyntanh")
+        sp.loss_schedule_circle = int(getattr(o, "repro_loss_schedule", "circle") == "circle")
+        sp.soft_clamp, sp.soft_clamp_min = float(o.repro_loss_soft_clamp), float(o.repro_loss_soft_clamp_min)
+        self._sp = sp
+        self.sched_state = torch.zeros(_lib.SCHED_STATE_FLOATS, dtype=torch.float32, device=d)
+        _lib.check(self.lib.acez_schedule_init(C.byref(sp), _lib.ptr(self.sched_state), _lib.stream_ptr()), "acez_schedule_init")
+        # the host mirrors max_iterations / the cool-down flag from snapshots read back with a bounded lag (never a sync)
+        self._poll_every = max(1, min(64, sp.cooldown_iterations // 4)) if sp.kind == 2 else 0
+        self._poll_ring = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._poll_events = [None] * 4
+        self._poll_pending = []   # slots in flight, oldest first
+        self._poll_slot = 0
         self.stats_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._last_lw = None
         self.last_stats = None
@@ -237,8 +264,10 @@ class TrainLoop:
         lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
                            o.depth_target, 1.0)
-        if part in ("all", "fwd_bwd") and gather:
-            self._gather()
+        if part in ("all", "fwd_bwd"):
+            self._enqueue_schedule()
+            if gather:
+                self._gather()
         bt = self.batch
         # data parallel: the fp16-overflow check must see the SUMMED gradient (a per-rank partial can pass while the sum
         # overflows), so the optimiser runs its own check pass; single GPU: the backward kernels' folded check is complete
@@ -263,11 +292,71 @@ class TrainLoop:
                 self._dp_unpack_flag()
         h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete, check_flag_slot=fused_flag)
 
-    def _enqueue_refined(self):
+    def _enqueue_schedule(self):
+        """First kernel of the iteration: device-side lr / loss weight / cool-down trigger (csrc/schedule.cu). It books the
+        PREVIOUS iteration's inlier count, which under data parallelism is the all-reduced one riding behind the gradient."""
+        h = self.head
+        src = h.stats.data_ptr() + 4 if self.world == 1 else h.grads_full.data_ptr() + 4 * (h.n_params + 2)
+        rc = self.lib.acez_schedule_step(C.byref(self._sp), _lib.ptr(self.sched_state), C.c_void_p(src), _lib.ptr(h.hyper),
+                                         _lib.stream_ptr())
+        _lib.check(rc, "acez_schedule_step")
+
+    def _poll_schedule(self, force=False):
+        """Host mirror of the device schedule: enqueue a 64-byte snapshot every `_poll_every` iterations and consume the
+        snapshots whose copies have completed (event query, no wait). `force`: synchronous read (end of training / logging)."""
+        sch = self.schedule
+        if force:
+            st = self.sched_state[:16].cpu()
+            self._apply_snapshot(st)
+            return
+        if self._poll_every and self.iteration % self._poll_every == 0 and len(self._poll_pending) < len(self._poll_ring):
+            k = self._poll_slot
+            self._poll_slot = (k + 1) % len(self._poll_ring)
+            if k not in self._poll_pending:
+                self._poll_ring[k].copy_(self.sched_state[:16], non_blocking=True)
+                if self._poll_events[k] is None:
+                    self._poll_events[k] = torch.cuda.Event()
+                self._poll_events[k].record()
+                self._poll_pending.append(k)
+        while self._poll_pending and self._poll_events[self._poll_pending[0]].query():
+            self._apply_snapshot(self._poll_ring[self._poll_pending.pop(0)])
+
+    def _apply_snapshot(self, st):
+        sch = self.schedule
+        if int(st[2]) and not sch.in_cooldown_phase:
+            sch.in_cooldown_phase = True
+            sch.cooldown_start = int(st[3])
+        sch.max_iterations = min(sch.max_iterations, int(st[4]))
+
+    def finish(self):
+        """End of training: wait for the device, take over its final schedule state (iterations the host enqueued beyond the
+        device's max_iterations ran with lr = 0 and changed nothing)."""
+        torch.cuda.current_stream().synchronize()
+        self._poll_schedule(force=True)
+        self.iteration = min(self.iteration, int(self.sched_state[0].item()))
+        return self.iteration
+
+    def _run_refined_graphed(self, step_poses):
+        """Refinement iteration as one CUDA graph per variant (captured after two eager runs of THAT variant, so that the torch
+        optimisers' lazily created state exists and every kernel attribute is set)."""
+        g = self._refine_graphs.get(step_poses)
+        if g is None:
+            if self._refine_warm.get(step_poses, 0) < 2:
+                self._refine_warm[step_poses] = self._refine_warm.get(step_poses, 0) + 1
+                self._enqueue_refined(step_poses)
+                return
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_refined(step_poses)
+            self._refine_graphs[step_poses] = g
+        g.replay()
+
+    def _enqueue_refined(self, step_poses=True):
         """Iteration with pose and / or calibration refinement (reference ace_trainer.py:527-540, 620-640): the refined
         per-image poses and the refined intrinsics are PyTorch-autograd values; the fused kernel consumes the composed
         P = A * T and K' and returns dL/dP, dL/dK00, dL/dK11, which are pushed back through autograd."""
         o, h, bt = self.o, self.head, self.batch
+        self._enqueue_schedule()
         self._gather()
         lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
@@ -303,6 +392,7 @@ class TrainLoop:
             import torch.distributed as dist
             from .parallel import allreduce_training_state
             allreduce_training_state(h.grads, h.stats, h.found_inf)
+            h.grads_full[h.n_params + 1:h.n_params + 4].copy_(h.stats[:3])   # the device schedule books the global inlier count
             extra = []
             if self.pose_refiner is not None and self.pose_refiner.pose_optimizer is not None:
                 extra += [p for g in self.pose_refiner.pose_optimizer.param_groups for p in g["params"]]
@@ -312,7 +402,7 @@ class TrainLoop:
                 if p.grad is not None:
                     dist.all_reduce(p.grad)
         h.adamw_step(use_scaler=self.use_scaler, flag_complete=self.world == 1)             # :632
-        if self.pose_refiner is not None and self.iteration > o.pose_refinement_wait:      # :634-636
+        if self.pose_refiner is not None and step_poses:                                   # :634-636
             self.pose_refiner.step()
         if self.K_optimizer is not None:                                                    # :638-640
             self.K_optimizer.step()
@@ -325,6 +415,8 @@ class TrainLoop:
             self._inf_c = torch.tensor([float("inf")], device=self.device)
             self._zero_c = torch.zeros(1, device=self.device)
         torch.where(h.found_inf > 0, self._inf_c, self._zero_c, out=h.grads_full[h.n_params:h.n_params + 1])
+        # loss sum / inlier count / valid count ride along: the device schedule books the GLOBAL inlier count
+        h.grads_full[h.n_params + 1:h.n_params + 4].copy_(h.stats[:3])
 
     def _dp_allreduce(self):
         import torch.distributed as dist
@@ -335,17 +427,21 @@ class TrainLoop:
         h.found_inf.copy_((h.grads_full[h.n_params:h.n_params + 1] != 0).to(torch.int32))
 
     def _dp_reduce_stats(self):
-        import torch.distributed as dist
-        st = self.head.stats.clone()
-        dist.all_reduce(st)
-        st[3] = (st[3] > 0).float()
+        """Global [loss sum, inlier count, valid count, non-finite flag]: the three sums travelled behind the gradient through
+        the iteration's all-reduce (no extra collective); a non-finite loss on any rank makes the summed loss non-finite."""
+        h = self.head
+        st = torch.empty(4, device=self.device, dtype=torch.float32)
+        st[:3] = h.grads_full[h.n_params + 1:h.n_params + 4]
+        st[3] = (~torch.isfinite(st[0])).float()
         return st
 
     def train_iteration(self, indices, want_stats=False):
-        """indices: int64 CPU tensor of the GLOBAL batch (b_global entries of the epoch permutation)."""
+        """indices: int64 CPU tensor of the GLOBAL batch (b_global entries of the epoch permutation). Learning rate, loss
+        weight and the cool-down trigger are evaluated on the device (first kernel of the iteration); the host only mirrors
+        max_iterations from snapshots read back with a bounded lag."""
         sch = self.schedule
-        sch.check_and_set_cooldown(self.iteration)                    # ace_trainer.py:506
-        if self.iteration >= sch.max_iterations:                      # :509
+        self._poll_schedule()
+        if self.iteration >= sch.max_iterations:                      # ace_trainer.py:509
             return False
         from .parallel import shard_bounds
         lo, hi = shard_bounds(self.rank, self.world, self.b_global)
@@ -358,22 +454,22 @@ class TrainLoop:
         self.idx_host[slot].copy_(indices[lo:hi])
         self.idx_dev.copy_(self.idx_host[slot], non_blocking=True)
         self._idx_events[slot].record()
-        self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
         if self.refining:
-            self._enqueue_refined()
+            step_poses = self.pose_refiner is not None and self.iteration > self.o.pose_refinement_wait   # :634-636
+            if self.use_graph:
+                self._run_refined_graphed(step_poses)
+            else:
+                self._enqueue_refined(step_poses)
         elif self.use_graph:
             self._run_graphed()
         else:
             self._enqueue_compute()
-        need = want_stats or sch.needs_inliers
-        inl = 0.0
-        if need:
-            src = self._dp_reduce_stats() if (self.world > 1 and not self.refining) else self.head.stats
+        if want_stats:
+            src = self._dp_reduce_stats() if self.world > 1 else self.head.stats
             self.stats_host.copy_(src, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             self.last_stats = self.stats_host.clone()
-            inl = float(self.stats_host[1]) / self.b_global
-        sch.step(inl)                                                  # :632
+            self._poll_schedule(force=True)
         self.iteration += 1
         return True
 
@@ -388,9 +484,6 @@ class TrainLoop:
 
     def _step_on_static_batch(self, read_loss):
         """One iteration on whatever the static batch tensors hold (no gather); reads the loss statistics back."""
-        sch = self.schedule
-        sch.check_and_set_cooldown(self.iteration)                    # ace_trainer.py:506
-        self.head.set_hyper(sch.lr(), loss_weight(self.o, self.iteration))
         if self.use_graph and self.world == 1:   # (NCCL all-reduces are not captured: data parallel runs this path eagerly)
             if self._graph_host is None:
                 if self._warm_host < 2:
@@ -411,7 +504,6 @@ class TrainLoop:
             self.stats_host.copy_(self._dp_reduce_stats() if self.world > 1 else self.head.stats, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             out = (float(self.stats_host[0]), float(self.stats_host[1]) / self.b_global)
-        sch.step(out[1] if out else 0.0)
         self.iteration += 1
         return out
 
@@ -464,7 +556,7 @@ class TrainLoop:
         self._aux.copy_(st[nf:], non_blocking=True)
         self._stage_free[slot].record(cur)
         self._stage_r ^= 1
-        if not read_loss or lag == 0 or self.schedule.needs_inliers or self.world > 1:
+        if not read_loss or lag == 0 or self.world > 1:
             return self._step_on_static_batch(read_loss)
         if not hasattr(self, "_lag_stats"):
             self._lag_stats = torch.zeros((2, 4), dtype=torch.float32).pin_memory()
@@ -538,4 +630,6 @@ class TrainLoop:
             if not ran:
                 # the reference keeps calling training_step for the rest of the epoch; each call returns at once
                 break
+        if self.iteration >= self.schedule.max_iterations:
+            self.finish()
         return True

@@ -242,6 +242,39 @@ int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                     acez_head_plan* plan, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Training schedule on the device. Replaces the per-iteration host logic of ScheduleACE (ace_schedule.py:22-126:
+ * OneCycleLR / LinearLR warm-up + cool-down, the cool-down trigger on the last 100 batch-inlier fractions, the mutable
+ * max_iterations) and the loss-weight schedule of ReproLoss (ace_loss.py:53-69). acez_schedule_step enqueues a one-thread
+ * kernel that (1) books the PREVIOUS iteration's inlier count (*inlier_count_dev / batch_global) into the ring, (2) runs
+ * check_and_set_cooldown for the current iteration, (3) writes hyper_dev[0] = lr (0 once iteration >= max_iterations: later
+ * optimiser steps leave the weights unchanged) and hyper_dev[5] = loss weight, (4) advances the iteration counter.
+ * It is meant to be the first node of the iteration's CUDA graph: no host -> device traffic and no read-back per iteration.
+ * state_dev: ACEZ_SCHED_STATE_FLOATS floats, initialised by acez_schedule_init; layout (integers stored as floats):
+ *   [0] iteration  [1] scheduler steps  [2] in cool-down  [3] cool-down start (steps)  [4] max_iterations
+ *   [5] ring fill  [6] ring position    [7] done          [8] lr of the last step      [9] loss weight   [16..116) ring
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ACEZ_SCHED_RING 100
+#define ACEZ_SCHED_STATE_FLOATS 128
+enum { ACEZ_SCHED_CONSTANT = 0, ACEZ_SCHED_CIRCLE = 1, ACEZ_SCHED_1CYCLEPOLY = 2 };
+typedef struct acez_schedule_params {
+  int kind;                 /* ACEZ_SCHED_* : --learning_rate_schedule constant | circle | 1cyclepoly */
+  int iterations;           /* --iterations (OneCycleLR total_steps; initial max_iterations; loss-weight horizon) */
+  float lr_min, lr_max;     /* --learning_rate_min / --learning_rate_max */
+  int warmup_iterations;    /* 1cyclepoly */
+  float warmup_lr;
+  int cooldown_iterations;
+  float cooldown_trigger;   /* --learning_rate_cooldown_trigger_percent_threshold */
+  int batch_global;         /* divisor of the inlier count (ace_trainer.py:586) */
+  int loss_dyntanh;         /* 1: dyntanh weight schedule, 0: constant soft clamp */
+  int loss_schedule_circle; /* --repro_loss_schedule circle (1) | linear (0) */
+  float soft_clamp, soft_clamp_min;
+} acez_schedule_params;
+
+int acez_schedule_init(const acez_schedule_params* p, float* state_dev, acez_stream_t stream);
+int acez_schedule_step(const acez_schedule_params* p, float* state_dev, const float* inlier_count_dev, float* hyper_dev,
+                       acez_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * DSAC* pose solver. Replaces the reference's native operator:
  *   dsacstar.forward_rgb(sceneCoordinates[1,3,H,W] f32 CPU, outPose[4,4] f32 CPU, ransacHypotheses, inlierThreshold,
  *                        focalLength, ppointX, ppointY, inlierAlpha, maxReproj, subSampling, randomSeed,
