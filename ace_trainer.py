@@ -134,6 +134,7 @@ class TrainerACE:
         self.training_start = time.time()
         t0 = time.time()
         self.create_training_buffer()
+        torch.cuda.synchronize()
         creating_buffer_time += time.time() - t0
         _logger.info(f"Filled training buffer in {creating_buffer_time:.1f}s.")
 
@@ -159,6 +160,8 @@ class TrainerACE:
             self.save_model()
             self.save_poses()
             self.log_file.close()
+        self.timing = {"buffer_s": creating_buffer_time, "train_s": training_time, "images_encoded": self.images_encoded,
+                       "iterations": self.iteration}
         _logger.info(f'Done without errors. Creating buffer time: {creating_buffer_time:.1f} seconds. '
                      f'Training time: {training_time:.1f} seconds. '
                      f'Total time: {time.time() - self.training_start:.1f} seconds.')
@@ -257,11 +260,7 @@ class TrainerACE:
                 stage_events[sl] = torch.cuda.Event()
             for k, g in enumerate(group):
                 images[k].copy_(g["image"][0], non_blocking=True)             # pinned (loader) -> device, asynchronous
-                row = mats_np[sl][k]
-                row[0:12] = g["aug_pose_inv"][0, :3].reshape(-1).numpy()
-                row[12:28] = g["pose_inv"][0].reshape(-1).numpy()
-                row[28:37] = g["K"][0].reshape(-1).numpy()
-                row[37:46] = g["Kinv"][0].reshape(-1).numpy()
+                mats_np[sl][k] = g["mats"]
             mats_dev[sl][:n].copy_(mats_host[sl][:n], non_blocking=True)
             stage_events[sl].record()
             feats = enc.forward_nhwc(images)                                  # [n,h,w,512] fp16: ONE launch sequence
@@ -288,7 +287,7 @@ class TrainerACE:
                     H, W = encoder_out_hw(image.shape[2], image.shape[3])
                     # mask at output resolution (reference :373-378), decided on the CPU copy: no GPU sync. An all-true mask
                     # (no rotation augmentation) stays all-true under NEAREST resizing: no resize, no host->device copy
-                    if bool(mask.all()):
+                    if mask.numpy().all():
                         if (H, W) not in ones_cache:
                             ones_cache[(H, W)] = torch.ones(H * W, dtype=torch.float32, device=d)
                         weights = ones_cache[(H, W)]
@@ -308,9 +307,10 @@ class TrainerACE:
                     if owner == rank:
                         if group and (group[0]["image"].shape != image.shape or len(group) == max_batch):
                             flush()
-                        group.append({"image": image, "pose_inv": pose_inv, "aug_pose_inv": aug_pose_inv, "K": K, "Kinv": Kinv,
-                                      "crds": crds, "idx": int(idx), "sample_idxs": sample_idxs, "n_sel": n_sel,
-                                      "local_row0": local_rows[rank], "hw": (H, W)})
+                        mats = np.concatenate([aug_pose_inv.numpy()[0, :3].ravel(), pose_inv.numpy()[0].ravel(),
+                                               K.numpy()[0].ravel(), Kinv.numpy()[0].ravel()]).astype(np.float32)
+                        group.append({"image": image, "mats": mats, "crds": crds, "idx": int(idx), "sample_idxs": sample_idxs,
+                                      "n_sel": n_sel, "local_row0": local_rows[rank], "hw": (H, W)})
                     records.append((owner, buffer_idx, n_sel, local_rows[owner]))
                     local_rows[owner] += n_sel
                     buffer_idx += n_sel

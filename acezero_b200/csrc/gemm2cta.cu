@@ -117,7 +117,12 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   constexpr uint32_t kTmemCols = (T2_BN + 32 <= 256) ? 256u : 512u;  // accumulator + the bias-gradient column block
   if (warp == 1) t2_tmem_alloc(tmem_ptr, kTmemCols);
-  const bool bias_col = args.bias_grad != nullptr && n0 == 0;  // dZ^T 1: one extra N = 16 UMMA per k-step (TMEM columns BN..BN+15)
+  // bias gradient dZ^T 1: one extra N = 16 UMMA per k-step against a ones tile (TMEM columns BN..BN+15). Every column tile of
+  // an M-tile sees the same A operand, so the work is SPLIT over them: tile tn takes the k-blocks kb % tiles_n == tn (round 2
+  // profile: with the whole column on the n0 == 0 tiles those CTAs ran 1.5x longer than the rest and set the kernel time);
+  // the partial sums meet in a workspace and the last tile to arrive adds them in a fixed order (deterministic).
+  const bool bias_col = args.bias_grad != nullptr;
+  const int tn = tile % args.tiles_n, tm = tile / args.tiles_n;
   if (bias_col && warp >= 2) {
     __half2* o = reinterpret_cast<__half2*>(sOnes);
     for (int i = threadIdx.x - 64; i < 1024 / 4; i += 256) o[i] = __floats2half2_rn(1.f, 1.f);
@@ -163,9 +168,11 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t idesc_ones = make_idesc_f16(2 * T2_BM, 16, A_MN, false);
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t bias_started = 0u;
     for (int kb = 0; kb < k_blocks; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
+      const bool do_bias = bias_col && (kb % args.tiles_n) == tn;
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(sA + stage * T2_ASTAGE);
         const uint32_t b_addr = smem_u32(sB + stage * T2_BSTAGE);
@@ -174,12 +181,13 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t da = make_smem_desc(a_addr + k * args.a_kstep, args.a_lbo, args.a_sbo, 2);
           const uint64_t db = make_smem_desc(b_addr + k * args.b_kstep, args.b_lbo, args.b_sbo, 2);
           t2_umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (bias_col) {
+          if (do_bias) {
             const uint64_t d1 = make_smem_desc(smem_u32(sOnes) + k * 32, 0, 1024, 2);
-            t2_umma_f16(tmem_base + T2_BN, da, d1, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+            t2_umma_f16(tmem_base + T2_BN, da, d1, idesc_ones, (bias_started | (uint32_t)k) != 0u ? 1u : 0u);
           }
         }
       }
+      if (do_bias) bias_started = 1u;
       __syncwarp();
       if (elect_one()) {
         t2_commit_both(&empty_bar[stage]);
@@ -219,13 +227,40 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if (bias_col && grp == 0) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + T2_BN, v);  // columns BN..BN+15 hold the row sum (all equal); 32 columns are allocated
-      tmem_ld_wait();
-      if (row < args.M) {
-        const float g = __uint_as_float(v[0]);
-        args.bias_grad[(long long)z * args.bias_grad_zstride + row] = g;
-        bad |= !isfinite(g) || fabsf(g) > 65504.f;
+      __shared__ int s_last;
+      const int tiles_m = (int)(gridDim.x >> 1) / args.tiles_n;
+      const int r_in_tile = rank * T2_BM + quarter * 32 + lane;            // 0..255 inside the pair's M-tile
+      float* part = args.bias_part + ((size_t)(z * tiles_m + tm) * args.tiles_n) * (2 * T2_BM);
+      float g = 0.f;
+      if (k_blocks > tn) {   // this tile issued bias UMMAs
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + T2_BN, v);  // columns BN..BN+15 hold the partial row sum (all equal); 32 columns are allocated
+        tmem_ld_wait();
+        g = __uint_as_float(v[0]);
+      }
+      part[(size_t)tn * (2 * T2_BM) + r_in_tile] = g;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (quarter == 0 && lane == 0) {
+        const unsigned int done = atomicAdd(args.bias_count + z * tiles_m + tm, 1u);
+        s_last = (done == 2u * (unsigned int)args.tiles_n - 1u) ? 1 : 0;   // both CTAs of all column tiles have stored
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        const int t128 = quarter * 32 + lane;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int rt = half * T2_BM + t128;
+          float sum = 0.f;
+          for (int j = 0; j < args.tiles_n; ++j) sum += __ldcg(part + (size_t)j * (2 * T2_BM) + rt);
+          const int grow = tm * 2 * T2_BM + rt;
+          if (grow < args.M) {
+            args.bias_grad[(long long)z * args.bias_grad_zstride + grow] = sum;
+            bad |= !isfinite(sum) || fabsf(sum) > 65504.f;
+          }
+        }
+        if (t128 == 0) args.bias_count[z * tiles_m + tm] = 0u;   // ready for the next launch
       }
     }
     if (args.nonfinite != nullptr) {
@@ -322,6 +357,26 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   a.tiles_n = (d->N + L.bn - 1) / L.bn;
   a.out32 = d->out32; a.out32_zstride = d->out32_zstride; a.ldo32 = d->ldo32;
   a.bias_grad = d->bias_grad; a.bias_grad_zstride = d->bias_grad_zstride;
+  if (d->bias_grad != nullptr) {
+    // probe entry: the partial-sum workspace and its arrival counters live in a process-wide scratch allocation
+    static float* g_part = nullptr;
+    static unsigned int* g_count = nullptr;
+    static size_t g_cap = 0;
+    const int tiles_m = (d->M + 2 * T2_BM - 1) / (2 * T2_BM);
+    const size_t need = (size_t)L.batch * tiles_m * a.tiles_n * 2 * T2_BM;
+    if (need > g_cap) {
+      if (g_part) cudaFree(g_part);
+      ACEZ_CUDA(cudaMalloc(&g_part, need * sizeof(float)));
+      g_cap = need;
+    }
+    if (g_count == nullptr) {
+      ACEZ_CUDA(cudaMalloc(&g_count, 4096 * sizeof(unsigned int)));
+      ACEZ_CUDA(cudaMemset(g_count, 0, 4096 * sizeof(unsigned int)));
+    }
+    ACEZ_REQUIRE((size_t)L.batch * tiles_m <= 4096, "gemm2cta: too many row tiles for the probe's counters");
+    a.bias_part = g_part;
+    a.bias_count = g_count;
+  }
   a.nonfinite = d->nonfinite;
   a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
   a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;

@@ -10,8 +10,10 @@ struct Gemm2Args {
   float* out32;          // [z][M][ldo32]
   long long out32_zstride;
   int ldo32;
-  float* bias_grad;      // [z][M] nullable: column sum over the contraction dimension of A 
+  float* bias_grad;      // [z][M] nullable: column sum over the contraction dimension of A
   long long bias_grad_zstride;
+  float* bias_part;      // with bias_grad: workspace [z][tiles_m][tiles_n][256] partial column sums (one per column tile)
+  unsigned int* bias_count;  // with bias_grad: [z][tiles_m] self-resetting arrival counters (zero before the first launch)
   int* nonfinite;        // nullable: OR-ed with 1 if a stored value is non-finite or exceeds the fp16 range
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
 };

@@ -45,6 +45,7 @@ struct acez_head_plan {
   uint8_t* MASKB;
   float* G3;
   float* FC3PART;
+  float* WBIAS;
   float* BLKPART;
   unsigned int* BLKCOUNT;
   bool counters_zeroed;
@@ -70,7 +71,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, blkpart, total;
+  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, wbias, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -89,6 +90,7 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.maskb = off; off = align_up(off + (size_t)(L + 1) * rows * 64, 1024);
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
     o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
+    o.wbias = off; off = align_up(off + (size_t)L * 2 * 4 * 256 * sizeof(float), 1024);  // wgrad bias partials [L][2][<=4][256]
   }
   o.blkpart = off; off = align_up(off + 4096 * 8 * sizeof(float) + 256, 1024);  // tail per-block partials + counter
   o.total = off;
@@ -742,6 +744,8 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       g.tiles_n = kC / W.bn;
       g.out32 = h->grads; g.out32_zstride = (long long)kLayerStride; g.ldo32 = kC;
       g.bias_grad = h->grads + (size_t)kC * kC; g.bias_grad_zstride = (long long)kLayerStride;
+      g.bias_part = h->WBIAS;
+      g.bias_count = h->BLKCOUNT + 8;   // [L][2] arrival counters behind the tail's; zeroed once with it (launch_tail)
       g.a_lbo = 8192; g.a_sbo = 1024; g.a_kstep = 2048;
       g.b_lbo = 8192; g.b_sbo = 1024; g.b_kstep = 2048;
     }
@@ -982,6 +986,7 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->MASKB = cfg->training ? base + lo.maskb : nullptr;
   h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
   h->FC3PART = cfg->training ? reinterpret_cast<float*>(base + lo.fc3part) : nullptr;
+  h->WBIAS = cfg->training ? reinterpret_cast<float*>(base + lo.wbias) : nullptr;
   h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);
   h->BLKCOUNT = reinterpret_cast<unsigned int*>(base + lo.blkpart + 4096 * 8 * sizeof(float));
   h->counters_zeroed = false;

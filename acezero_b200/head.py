@@ -126,6 +126,15 @@ class HeadEngine:
         """True when the plan runs each pass over the hidden layers as one fused cluster kernel (head_chain.cu)."""
         return bool(self.lib.acez_head_plan_fused_chain(self.plan))
 
+    def chain_kernel_symbol(self):
+        """Name of the kernel that runs the forward pass over the hidden layers (for profile bookkeeping in bench.py)."""
+        import os
+        if not self.fused_chain:
+            return "gemm_tcgen05_kernel<FWD>"
+        if os.environ.get("ACEZ_CHAIN_V4", "1") != "0":
+            return f"head_chain4_kernel<FWD,{2 if os.environ.get('ACEZ_CHAIN_EPI_GROUPS', '2') != '4' else 4}>"
+        return "head_chain_kernel<FWD>"
+
     def resize(self, max_rows):
         if max_rows > self.max_rows:
             self.max_rows = int(max_rows)

@@ -1,0 +1,70 @@
+"""Product-level multi-GPU check (run on a box with >= 2 GPUs, as a plain process): the stage executables re-launch themselves
+under torchrun when ACEZ_GPUS > 1 (acezero_b200/launch.py), shard the buffer creation / the batch / the images, and must
+reproduce the single-GPU run:
+  * train_ace.py     : same log lines (loss, inlier fraction at every logged iteration) within fp16 summation-order noise,
+                       same iteration count, close final weights
+  * register_mapping : the SAME pose file lines (per-image RNG keys: the poses do not depend on the number of ranks)
+"""
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def run(cmd, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    r = subprocess.run([sys.executable] + cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        print(r.stdout[-3000:], r.stderr[-3000:])
+        raise SystemExit(f"command failed: {cmd}")
+    return r.stdout + r.stderr
+
+
+def main():
+    gpus = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    ok = True
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        common = ["synthetic", None, "--synthetic", "16", "--encoder_seed", "7", "--iterations", "400", "--iterations_output", "100",
+                  "--use_external_focal_length", "525", "--max_dataset_passes", "4"]
+        outs = {}
+        for g in (1, gpus):
+            args = list(common)
+            args[1] = str(tmp / f"map{g}.pt")
+            log = run(["train_ace.py"] + args, {"ACEZ_GPUS": str(g), "CUDA_VISIBLE_DEVICES": ",".join(str(i) for i in range(g))})
+            outs[g] = np.array([[float(x) for x in l.split()] for l in (tmp / f"map{g}.txt").read_text().strip().splitlines()])
+            if g > 1:
+                assert "encoded" in log, "the sharded buffer creation did not report per-rank image counts"
+                print([l for l in log.splitlines() if "encoded" in l][:gpus])
+        a, b = outs[1], outs[gpus]
+        same_iters = a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+        rel = np.abs(a[:, 2] - b[:, 2]) / np.abs(a[:, 2])
+        print(f"train_ace.py x{gpus}: logged iterations equal: {same_iters}; loss rel diff per log line: {np.round(rel, 4)}; "
+              f"inlier fractions {np.round(a[:, 3], 3)} vs {np.round(b[:, 3], 3)}")
+        ok &= bool(same_iters) and bool(rel.max() < 5e-2)
+        w1, w2 = torch.load(tmp / "map1.pt"), torch.load(tmp / f"map{gpus}.pt")
+        d = max(float((w1[k].float() - w2[k].float()).norm() / (w1[k].float().norm() + 1e-9)) for k in w1)
+        print(f"final head weights: max relative L2 difference over tensors {d:.3e}")
+        ok &= d < 0.2
+        lines = {}
+        for g in (1, gpus):
+            run(["register_mapping.py", "synthetic", str(tmp / "map1.pt"), "--synthetic", "24", "--synthetic_offset", "3", "--encoder_seed", "7",
+                 "--session", f"s{g}", "--use_external_focal_length", "525", "--hypotheses_max_tries", "16"],
+                {"ACEZ_GPUS": str(g), "CUDA_VISIBLE_DEVICES": ",".join(str(i) for i in range(g))})
+            lines[g] = sorted((tmp / f"poses_s{g}.txt").read_text().strip().splitlines())
+        same = lines[1] == lines[gpus]
+        print(f"register_mapping.py x{gpus}: {len(lines[gpus])} pose lines, identical to the single-GPU file: {same}")
+        ok &= same and len(lines[gpus]) == 24
+    print("RESULT", "PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
