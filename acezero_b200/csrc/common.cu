@@ -105,32 +105,4 @@ int acez_device_check(void) {
   return ACEZ_OK;
 }
 
-// Experimental (ACEZ_L2_PERSIST, see acezero_b200/head.py): keep [ptr, ptr + bytes) resident in L2 for kernels launched on
-// `stream` afterwards (stream attribute; kernels captured into a CUDA graph inherit it). bytes = 0 resets the window.
-int acez_stream_set_l2_window(void* ptr, size_t bytes, float hit_ratio, acez_stream_t stream) {
-  int rc = acez_device_check();
-  if (rc) return rc;
-  int dev = 0, max_persist = 0, max_window = 0;
-  ACEZ_CUDA(cudaGetDevice(&dev));
-  ACEZ_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-  ACEZ_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-  cudaStreamAttrValue v{};
-  if (bytes > 0) {
-    ACEZ_REQUIRE(ptr != nullptr && hit_ratio > 0.f && hit_ratio <= 1.f, "l2_window: bad arguments");
-    size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
-    ACEZ_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-    v.accessPolicyWindow.base_ptr = ptr;
-    v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-    v.accessPolicyWindow.hitRatio = hit_ratio;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  } else {
-    v.accessPolicyWindow.num_bytes = 0;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-  }
-  ACEZ_CUDA(cudaStreamSetAttribute(reinterpret_cast<cudaStream_t>(stream), cudaStreamAttributeAccessPolicyWindow, &v));
-  return ACEZ_OK;
-}
-
 }  // extern "C"

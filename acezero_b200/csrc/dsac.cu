@@ -11,9 +11,11 @@
 // Kernel 2 (dsac_refine_kernel): one CTA per image: block argmax, then the refinement loop of
 //   dsacstar_util.h:522-597 with an in-kernel Levenberg-Marquardt (the algorithm of OpenCV's CvLevMarq that
 //   cv::solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess=true) runs: max 20 iterations, eps FLT_EPSILON),
-//   block-wide reduction of the 6x6 normal equations in double.
-// Arithmetic: projections in double (OpenCV's projectPoints computes in double and stores float pixels);
-// no cheirality test (z ? 1/z : 1), as in OpenCV. Not HBM-bound, no tensor cores: FP64/FP32 FMA + SFU + smem.
+//   block-wide reduction of the normal equations in double, accumulated in the rotation's tangent space and with ONE pass
+//   over the inliers per LM iteration (dsac_refine_body.inc).
+// Arithmetic: the soft-inlier SCORES are summed in FP32 (11 FFMA + 4 MUFU per hypothesis and cell); every hard decision - the
+// 4-point acceptance test of a minimal set, inlier sets, the LM - is taken in double (OpenCV's projectPoints computes in
+// double and stores float pixels); no cheirality test (z ? 1/z : 1), as in OpenCV. Not HBM-bound, no tensor cores.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,6 +31,7 @@ struct HypRec {
 };
 
 static constexpr int kDsacThreads = 256;
+static constexpr int kRefineThreads = 128;   // refinement: one CTA per image, 3-4 CTAs per SM (60x80 maps: 62 KB of shared memory each)
 static constexpr int kMaxSmemCells = 16000;  // 3 floats + 1 flag byte per cell must fit in ~200 KB
 
 // ---------------------------------------------------------------- RNG
@@ -329,7 +332,7 @@ __device__ void block_sum(double (&v)[CNT], double* s_part /*[warps][CNT]*/, dou
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kDsacThreads) dsac_refine_kernel(const DsacArgs a) {
+__global__ void __launch_bounds__(kRefineThreads, 3) dsac_refine_kernel(const DsacArgs a) {
 #include "dsac_refine_body.inc"
 }
 
@@ -385,7 +388,7 @@ extern "C" int acez_dsac_forward_rgb_batch(const float* sc, int n, int h, int w,
   dim3 grid1(chunks, n);
   dsac_sample_score_kernel<<<grid1, kDsacThreads, smem1, s>>>(a);
   ACEZ_CUDA(cudaGetLastError());
-  dsac_refine_kernel<<<n, kDsacThreads, smem2, s>>>(a);
+  dsac_refine_kernel<<<n, kRefineThreads, smem2, s>>>(a);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;
 }

@@ -47,26 +47,13 @@ class HeadEngine:
         self.cfg = self._config()
         self.n_params = int(self.lib.acez_head_param_count(C.byref(self.cfg)))
         assert self.n_params == self.L * LAYER_STRIDE + self.C3 * 512 + self.C3
-        import os
-        self._l2_persist = training and os.environ.get("ACEZ_L2_PERSIST", "0") == "1"
-        if self._l2_persist:
-            # experimental: ONE allocation for params | grads (+4) | exp_avg | exp_avg_sq so that a single L2 persistence
-            # window covers the optimiser state (set by `enable_l2_persistence` on the stream the step runs on)
-            n, pad = self.n_params, (-self.n_params) % 64 + 64   # >= 4 spare floats behind every section
-            self._opt_pool = torch.zeros(4 * (n + pad) + 64, device=self.device, dtype=torch.float32)
-            off = [i * (n + pad) for i in range(4)]
-            self.params = self._opt_pool[off[0]:off[0] + n]
-            self.grads_full = self._opt_pool[off[1]:off[1] + n + 4]
-            self.grads = self.grads_full[:n]
-            self.exp_avg = self._opt_pool[off[2]:off[2] + n]
-            self.exp_avg_sq = self._opt_pool[off[3]:off[3] + n]
-        else:
-            self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
-            # 4 spare floats behind the gradient: data-parallel runs carry the GradScaler flag through the SAME all-reduce
-            self.grads_full = torch.zeros(self.n_params + 4, device=self.device, dtype=torch.float32) if training else None
-            self.grads = self.grads_full[:self.n_params] if training else None
-            self.exp_avg = torch.zeros_like(self.params) if training else None
-            self.exp_avg_sq = torch.zeros_like(self.params) if training else None
+        self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
+        # 4 spare floats behind the gradient: data-parallel runs carry the GradScaler flag and the loss statistics through the
+        # SAME all-reduce as the gradient
+        self.grads_full = torch.zeros(self.n_params + 4, device=self.device, dtype=torch.float32) if training else None
+        self.grads = self.grads_full[:self.n_params] if training else None
+        self.exp_avg = torch.zeros_like(self.params) if training else None
+        self.exp_avg_sq = torch.zeros_like(self.params) if training else None
         self.plan = None
         self._build_plan()
         # device-resident optimiser / GradScaler state (no host sync in the step)
@@ -110,16 +97,6 @@ class HeadEngine:
         self.plan = plan
         in_ptr = self.lib.acez_head_input_ptr(self.plan)
         self._input_off = in_ptr - self.workspace.data_ptr()
-
-    def enable_l2_persistence(self, stream=None, hit_ratio=1.0):
-        """Experimental (ACEZ_L2_PERSIST=1): L2 persistence window over the optimiser state for kernels launched on `stream`
-        from now on (call before the CUDA graph of the iteration is captured). No-op unless the engine was created with it."""
-        if not self._l2_persist:
-            return False
-        rc = self.lib.acez_stream_set_l2_window(_lib.ptr(self._opt_pool), self._opt_pool.numel() * 4, hit_ratio,
-                                                _lib.stream_ptr(stream))
-        _lib.check(rc, "acez_stream_set_l2_window")
-        return True
 
     @property
     def fused_chain(self):

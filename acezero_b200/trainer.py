@@ -259,8 +259,6 @@ class TrainLoop:
     def _enqueue_compute(self, P=None, d_P=None, d_Kdiag=None, gather=True, part="all"):
         """gather + forward + loss + backward (+ all-reduce) + GradScaler/AdamW on the current stream."""
         o, h = self.o, self.head
-        if h._l2_persist:   # experimental (ACEZ_L2_PERSIST=1): optimiser state pinned in L2 for the kernels enqueued below
-            h.enable_l2_persistence()
         lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
                            o.depth_target, 1.0)

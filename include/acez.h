@@ -40,10 +40,6 @@ int acez_version(void);
 const char* acez_last_error(void);
 /* 0 iff a compute-capability-10.x device is current. */
 int acez_device_check(void);
-/* Experimental: L2 persistence window [ptr, ptr + bytes) for kernels launched on `stream` from now on (bytes = 0: reset).
- * Used (opt-in, ACEZ_L2_PERSIST=1) to keep the 34 MB of fp32 parameters / gradients / AdamW moments resident between the
- * optimiser steps (reference state: torch.optim.AdamW, ace_schedule.py:15-19). */
-int acez_stream_set_l2_window(void* ptr, size_t bytes, float hit_ratio, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Generic fp16 tensor-core GEMM (tcgen05 + TMA). Building block of the head and encoder; exported for the parity
