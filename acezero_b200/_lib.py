@@ -92,7 +92,7 @@ _lib = None
 
 # every symbol include/acez.h declares (the CPU test checks the .so exports all of them)
 EXPORTS = [
-    "acez_version", "acez_last_error", "acez_device_check", "acez_gemm_f16", "acez_gemm2cta_f16", "acez_repro_loss_fwd_bwd",
+    "acez_version", "acez_last_error", "acez_device_check", "acez_gemm_f16", "acez_gemm2cta_f16", "acez_debug_gemm2_clocks", "acez_repro_loss_fwd_bwd",
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
     "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_plan_fused_chain", "acez_debug_chain_clocks", "acez_head_forward", "acez_head_forward_train",
     "acez_head_backward", "acez_head_train_fwd_bwd",
@@ -116,6 +116,7 @@ def load():
     vp, i, f = C.c_void_p, C.c_int, C.c_float
     lib.acez_gemm_f16.argtypes = [C.POINTER(GemmDesc), vp]
     lib.acez_gemm2cta_f16.argtypes = [C.POINTER(GemmDesc), vp]
+    lib.acez_debug_gemm2_clocks.argtypes = [vp, C.c_size_t]
     lib.acez_repro_loss_fwd_bwd.argtypes = [C.POINTER(LossParams), i] + [vp] * 13
     lib.acez_head_param_count.argtypes = [C.POINTER(HeadConfig)]
     lib.acez_head_param_count.restype = C.c_size_t

@@ -16,6 +16,8 @@
 //   - tcgen05.commit.cta_group::2 ... multicast::cluster : stage release / accumulator-ready to BOTH CTAs
 // PTX forms follow the vendored CUTLASS headers (cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp,
 // tmem_allocator_sm100.hpp, cutlass/arch/barrier.h).
+#include <stdlib.h>
+
 #include "gemm2cta.cuh"
 
 namespace acez {
@@ -141,8 +143,12 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long t_wait = 0;
+      const long long t_begin = args.dbg ? clock64() : 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
+        const long long t0 = args.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (args.dbg) t_wait += clock64() - t0;
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * T2_STAGE);
         else t2_arrive_leader(&full_bar[stage]);
         uint8_t* a_dst = sA + stage * T2_ASTAGE;
@@ -161,6 +167,10 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (args.dbg) {
+        long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
+        d[2] = t_wait; d[3] = clock64() - t_begin;
+      }
     }
   } else if (warp == 1 && leader) {
     // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
@@ -169,8 +179,12 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     uint32_t bias_started = 0u;
+    long long t_wait = 0;
+    const long long t_begin = args.dbg ? clock64() : 0;
     for (int kb = 0; kb < k_blocks; ++kb) {
+      const long long t0 = args.dbg ? clock64() : 0;
       mbar_wait(&full_bar[stage], phase);
+      if (args.dbg) t_wait += clock64() - t0;
       tcgen05_fence_after();
       const bool do_bias = bias_col && (kb % args.tiles_n) == tn;
       if (elect_one()) {
@@ -196,6 +210,10 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
     }
+    if (args.dbg && lane == 0) {
+      long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
+      d[0] = t_wait; d[1] = clock64() - t_begin;
+    }
   } else if (warp >= 2) {
     // ------------------------------ epilogue (both CTAs: 128 rows x 256 columns each) ------------------------------
     const int quarter = warp & 3;
@@ -203,6 +221,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int row = m0 + quarter * 32 + lane;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    const long long t_epi = args.dbg ? clock64() : 0;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     bool bad = false;
 #pragma unroll 1
@@ -266,6 +285,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (args.nonfinite != nullptr) {
       if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
+    if (args.dbg && warp == 2 && lane == 0) args.dbg[8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x) + 4] = clock64() - t_epi;
   }
 
   __syncwarp();
@@ -335,6 +355,15 @@ int gemm2_launch(const Gemm2Launch& L, cudaStream_t s, bool pdl) {
 
 }  // namespace acez
 
+static long long* g_gemm2_dbg = nullptr;
+// profiling probe: copies the per-CTA cycle counters of the last acez_gemm2cta_f16 call with ACEZ_GEMM2_DBG=1 (8 slots per CTA)
+extern "C" int acez_debug_gemm2_clocks(long long* host_out, size_t n_ctas) {
+  if (g_gemm2_dbg == nullptr || host_out == nullptr || n_ctas > 4096) return ACEZ_ERR_INVALID;
+  ACEZ_CUDA(cudaDeviceSynchronize());
+  ACEZ_CUDA(cudaMemcpy(host_out, g_gemm2_dbg, n_ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return ACEZ_OK;
+}
+
 // C ABI: experimental entry (same descriptor as acez_gemm_f16; epilogue must be ACEZ_EPI_F32, plain fp32 store)
 extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) {
   using namespace acez;
@@ -380,6 +409,16 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   a.nonfinite = d->nonfinite;
   a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
   a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;
+  {
+    static const bool want = [] { const char* e = getenv("ACEZ_GEMM2_DBG"); return e != nullptr && atoi(e) != 0; }();
+    static long long* g_dbg = nullptr;
+    if (want) {
+      if (g_dbg == nullptr) ACEZ_CUDA(cudaMalloc(&g_dbg, 8 * 4096 * sizeof(long long)));
+      ACEZ_CUDA(cudaMemsetAsync(g_dbg, 0, 8 * 4096 * sizeof(long long), reinterpret_cast<cudaStream_t>(stream)));
+      a.dbg = g_dbg;
+      g_gemm2_dbg = g_dbg;
+    }
+  }
   if (d->a_lbo) a.a_lbo = d->a_lbo;
   if (d->a_sbo) a.a_sbo = d->a_sbo;
   if (d->a_kstep) a.a_kstep = d->a_kstep;

@@ -16,6 +16,8 @@ struct Gemm2Args {
   unsigned int* bias_count;  // with bias_grad: [z][tiles_m] self-resetting arrival counters (zero before the first launch)
   int* nonfinite;        // nullable: OR-ed with 1 if a stored value is non-finite or exceeds the fp16 range
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+  long long* dbg;        // nullable (ACEZ_GEMM2_DBG=1): per CTA [0] MMA-warp cycles waiting for operands, [1] MMA loop cycles,
+                         // [2] producer cycles waiting for free stages, [3] producer loop cycles, [4] epilogue cycles
 };
 
 struct Gemm2Launch {

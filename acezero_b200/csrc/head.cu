@@ -185,13 +185,13 @@ __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __r
 
 // ----------------------------------------------------------------------------------------------
 // tail kernel: fc3 + homogeneous + (loss + backward into DZ[L-1]) + per-block partial of the fc3 weight gradient.
-// One block = 32 rows, three phases:
-//   A  warp w, rows 4w..4w+3: the 4 fc3 dot products of a row (lane owns columns [16 lane, 16 lane + 16), its slice of the fc3
+// One block = 40 rows (8 warps x 5), three phases:
+//   A  warp w, rows 5w..5w+4: the 4 fc3 dot products of a row (lane owns columns [16 lane, 16 lane + 16), its slice of the fc3
 //      weights in registers, the 4 rows' activations stay in registers for phase C) -> shared memory
-//   B  ONE THREAD PER ROW (warp 0): de-homogenisation, pose compose, reprojection loss and its analytic backward, back through
+//   B  ONE THREAD PER ROW (warps 0, 1): de-homogenisation, pose compose, reprojection loss and its analytic backward, back through
 //      the de-homogenisation -> g[4]. The per-row chain (divisions, exp / log / tanh) is latency bound; 32 rows advance in
 //      parallel instead of one per warp with all lanes redundant (round 1: 20 us for 5120 rows)
-//   C  warp w, rows 4w..4w+3: dX = g W3 with the ReLU mask -> DZ[L-1] (1 KB per row, coalesced) and the warp's partial of
+//   C  warp w, rows 5w..5w+4: dX = g W3 with the ReLU mask -> DZ[L-1] (1 KB per row, coalesced) and the warp's partial of
 //      dW3 = sum_rows g x^T; block partial -> FC3PART[block] (summed by fc3_reduce_kernel)
 // ----------------------------------------------------------------------------------------------
 struct TailArgs {
@@ -217,14 +217,16 @@ struct TailArgs {
 };
 
 static constexpr int kTailThreads = 256;
-static constexpr int kTailRows = 32;                                   // rows per block
+static constexpr int kTailRW = 5;                                      // rows per warp
+static constexpr int kTailRows = (kTailThreads / 32) * kTailRW;        // 40 rows per block: 128 blocks for 5120 rows = ONE wave on 148 SMs
+                                                                       // (round 2: 32 rows = 160 blocks = two waves, 18 us instead of 9)
 static constexpr int kTailAccBytes = (kTailThreads / 32) * 4 * kC * 4;  // dynamic smem of the fc3-gradient variant: 64 KB
 
 __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs a) {
   extern __shared__ float sAcc[];              // [8 warps][4][512] (only when a.fc3_part != nullptr)
   __shared__ float sS[kTailRows][4];           // fc3 outputs (fp16-rounded, as the autocast conv produces them)
   __shared__ float sG[kTailRows][4];           // gradient w.r.t. the fc3 outputs (fp16-rounded values)
-  __shared__ float sRed[3];
+  __shared__ float sRed[2][3];
   __shared__ int sLast;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * kTailRows;
@@ -262,10 +264,10 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
 #pragma unroll
     for (int k = 0; k < 4; ++k) { w[j][k] = h0[k]; w[j][4 + k] = h1[k]; }
   }
-  uint4 xr[4][2];
+  uint4 xr[kTailRW][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = r0 + 4 * warp + i;
+  for (int i = 0; i < kTailRW; ++i) {
+    const int row = r0 + kTailRW * warp + i;
     if (row < a.rows) {
       const uint4* xp = reinterpret_cast<const uint4*>(a.x + (size_t)row * kC + lane * 16);
       xr[i][0] = xp[0]; xr[i][1] = xp[1];
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < kTailRW; ++i) {
     const __half2* xh = reinterpret_cast<const __half2*>(xr[i]);
     float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
     if (lane < 4) {
       const float dj = lane == 0 ? d[0] : (lane == 1 ? d[1] : (lane == 2 ? d[2] : d[3]));
       const float bj = (lane < a.C3) ? __half2float(__float2half_rn(a.b3[lane])) : 0.f;
-      sS[4 * warp + i][lane] = __half2float(__float2half_rn(dj + bj));
+      sS[kTailRW * warp + i][lane] = __half2float(__float2half_rn(dj + bj));
     }
   }
   __syncthreads();
@@ -375,10 +377,10 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
       }
     }
     *reinterpret_cast<float4*>(&sG[tid][0]) = make_float4(g[0], g[1], g[2], g[3]);
-    if (a.training == 1) {   // warp 0 holds all 32 rows of the block
-      loss_sum = warp_sum(loss_sum); inl_sum = warp_sum(inl_sum); valid_sum = warp_sum(valid_sum);
-      if (tid == 0) { sRed[0] = loss_sum; sRed[1] = inl_sum; sRed[2] = valid_sum; }
-    }
+  }
+  if (a.training == 1 && warp < 2) {   // warps 0 and 1 hold the block's 40 rows (idle lanes carry zeros)
+    loss_sum = warp_sum(loss_sum); inl_sum = warp_sum(inl_sum); valid_sum = warp_sum(valid_sum);
+    if (lane == 0) { sRed[warp][0] = loss_sum; sRed[warp][1] = inl_sum; sRed[warp][2] = valid_sum; }
   }
   if (!a.training) return;
   __syncthreads();
@@ -392,10 +394,10 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
       for (int k = 0; k < 16; ++k) acc[j][k] = 0.f;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = r0 + 4 * warp + i;
+  for (int i = 0; i < kTailRW; ++i) {
+    const int row = r0 + kTailRW * warp + i;
     if (row >= a.rows) continue;
-    const float4 gv = *reinterpret_cast<const float4*>(&sG[4 * warp + i][0]);
+    const float4 gv = *reinterpret_cast<const float4*>(&sG[kTailRW * warp + i][0]);
     const float g[4] = {gv.x, gv.y, gv.z, gv.w};
     const __half2* xh = reinterpret_cast<const __half2*>(xr[i]);
     uint4 outv[2];
@@ -452,7 +454,8 @@ __global__ void __launch_bounds__(kTailThreads) head_tail_kernel(const TailArgs 
   // per-block partials, then the last block to finish writes the totals (no pre-zeroing, deterministic order)
   if (tid == 0) {
     float* p = a.blk_part + 8 * (size_t)blockIdx.x;
-    p[0] = a.training == 1 ? sRed[0] : 0.f; p[1] = a.training == 1 ? sRed[1] : 0.f; p[2] = a.training == 1 ? sRed[2] : 0.f;
+    p[0] = a.training == 1 ? sRed[0][0] + sRed[1][0] : 0.f; p[1] = a.training == 1 ? sRed[0][1] + sRed[1][1] : 0.f;
+    p[2] = a.training == 1 ? sRed[0][2] + sRed[1][2] : 0.f;
     p[3] = any_bad ? 1.f : 0.f; p[4] = any_bad_g ? 1.f : 0.f;
     __threadfence();
     const unsigned int done = atomicAdd(a.blk_count, 1u);

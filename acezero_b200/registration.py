@@ -11,6 +11,17 @@ import torch
 from . import dsac
 
 
+def collate_same_size(items):
+    """DataLoader collate for registration with batch_size > 1 (extension; the reference loads one image per step,
+    register_mapping.py:147): images of equal size are stacked into one 9-tuple batch, a mixed batch falls apart into
+    single-image batches. Returns a LIST of 9-tuple batches; `register` accepts both forms."""
+    from torch.utils.data.dataloader import default_collate
+    groups = {}
+    for it in items:
+        groups.setdefault(tuple(it[0].shape), []).append(it)
+    return [default_collate(g) for g in groups.values()]
+
+
 def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0, max_pixel_error=100.0,
              base_seed=1305, max_tries=1000000, max_estimates=-1, micro_batch=16, rank=0, world_size=1,
              device="cuda"):
@@ -22,7 +33,10 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
     def flush():
         if not pending:
             return
-        imgs = torch.cat([p[0] for p in pending], 0).to(device, non_blocking=True)
+        # image by image from the loader's (pinned) tensors straight into the device batch: asynchronous copies, no host-side cat
+        imgs = torch.empty((len(pending),) + tuple(pending[0][0].shape[1:]), dtype=pending[0][0].dtype, device=device)
+        for k, p in enumerate(pending):
+            imgs[k].copy_(p[0][0], non_blocking=True)
         K = torch.stack([p[1] for p in pending], 0)
         f = K[:, 0, 0].contiguous()
         with torch.no_grad():
@@ -37,8 +51,16 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
             results.append({"file": p[2], "index": int(p[3]), "pose": poses[j], "inliers": inl[j], "focal": p[4]})
         pending.clear()
 
+    def batches():
+        for item in loader:
+            if isinstance(item, list) and item and isinstance(item[0], (list, tuple)):   # collate_same_size: list of batches
+                for sub in item:
+                    yield sub
+            else:
+                yield item
+
     count = 0
-    for image, _, _, _, K, _, _, filenames, indices in loader:
+    for image, _, _, _, K, _, _, filenames, indices in batches():
         B = image.shape[0]
         for b in range(B):
             i = int(indices[b]) if torch.is_tensor(indices) else int(indices)

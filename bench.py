@@ -318,26 +318,31 @@ def run_pipeline(dev):
     esd = random_encoder_state(77)
     train = CachedDataset(SyntheticDataset(n, H=480, W=640, focal=525.0, device=str(dev)))
     with tempfile.TemporaryDirectory() as tmp:
-        o = train_ace.build_parser().parse_args(["synthetic", str(Path(tmp) / "map.pt"), "--iterations", "3000",
+        o = train_ace.build_parser().parse_args(["synthetic", str(Path(tmp) / "map.pt"), "--iterations", "5000",
                                                   "--use_external_focal_length", "525", "--iterations_output", "1000"])
         o.encoder_state_dict = esd
         o.num_data_workers = 0
         tr = TrainerACE(o, dataset=train)
         tr.train()
         timing = tr.timing
+        log_last = [float(x) for x in (Path(tmp) / "map.txt").read_text().strip().splitlines()[-1].split()]
         head_sd = torch.load(Path(tmp) / "map.pt", map_location="cpu")
     net = Regressor.create_from_split_state_dict(esd, head_sd).to(dev).eval()
     test = SyntheticDataset(n, H=480, W=640, focal=525.0, device=str(dev), s_offset=0.5)   # views between the mapping frames
     test.gt_poses = trajectory(n, s_offset=0.5)
     test.poses = [p.clone() for p in test.gt_poses]
     test = CachedDataset(test)
+    from acezero_b200.registration import collate_same_size
     gen = torch.Generator().manual_seed(1305)
-    register(net, DataLoader(test, shuffle=True, num_workers=0, generator=gen), hypotheses=64, max_tries=16, device=dev)   # warm-up
+
+    def loader():   # what register_mapping.py builds: shuffled, batches of 8 collated + pinned
+        return DataLoader(test, shuffle=True, num_workers=0, generator=gen, batch_size=8, collate_fn=collate_same_size, pin_memory=True)
+    register(net, loader(), hypotheses=64, max_tries=16, device=dev)   # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 4
     for _ in range(reps):
-        res, _ = register(net, DataLoader(test, shuffle=True, num_workers=0, generator=gen), hypotheses=64, max_tries=16, device=dev)
+        res, _ = register(net, loader(), hypotheses=64, max_tries=16, device=dev)
     dt = (time.perf_counter() - t0) / reps
     rot, tra = [], []
     for r in res:
@@ -347,11 +352,12 @@ def run_pipeline(dev):
         tra.append(float(np.linalg.norm(T[:3, 3] - G[:3, 3])))
     ok = float(np.mean([(a < 5.0) and (b < 0.05) for a, b in zip(rot, tra)]))
     return {
-        "what": "64 rendered 480x640 frames: TrainerACE.train (buffer fill + 3000 iterations) then registration.register on 64 "
+        "what": "64 rendered 480x640 frames: TrainerACE.train (buffer fill + 5000 iterations) then registration.register on 64 "
                 "held-out views through a shuffled DataLoader (host images in, host poses out)",
         "buffer_fill_images_per_s": timing["images_encoded"] / timing["buffer_s"],
         "buffer_fill_s": timing["buffer_s"], "images_encoded": timing["images_encoded"],
         "train_iters_per_s": timing["iterations"] / timing["train_s"], "train_s": timing["train_s"],
+        "final_loss": log_last[2], "final_batch_inliers": log_last[3],
         "register_poses_per_s": n / dt, "register_ms_per_image": dt / n * 1e3,
         "median_rot_deg": float(np.median(rot)), "median_trans_m": float(np.median(tra)), "acc_5cm_5deg": ok,
         "median_inliers": float(np.median([r["inliers"] for r in res])),

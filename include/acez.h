@@ -85,6 +85,9 @@ int acez_gemm_f16(const acez_gemm_desc* d, acez_stream_t stream);
  * or both MN-major. Exists to validate the 2-CTA primitives the next versions of the weight-gradient GEMM and of the fused layer
  * chain are built on. */
 int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream);
+/* Profiling probe (ACEZ_GEMM2_DBG=1): per-CTA cycle counters of the last acez_gemm2cta_f16 call, 8 slots per CTA:
+ * [0] MMA warp waiting for operands, [1] MMA loop, [2] TMA producer waiting for free stages, [3] producer loop, [4] epilogue. */
+int acez_debug_gemm2_clocks(long long* host_out, size_t n_ctas);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused reprojection loss + backward.

@@ -52,6 +52,8 @@ def build_parser():
     p.add_argument("--gpus", type=int, default=0,
                    help="extension: GPUs (ranks) for this stage; 0 = $ACEZ_GPUS or 1 (acezero_b200/launch.py)")
     p.add_argument("--micro_batch", type=int, default=16, help="extension: images per DSAC* launch pair")
+    p.add_argument("--loader_batch", type=int, default=8,
+                   help="extension: images per DataLoader step (collated on the workers, pinned); 1 = the reference's loader")
     return p
 
 
@@ -97,7 +99,11 @@ def main(argv=None):
         if opt.use_external_focal_length > 0:
             testset.set_external_focal_length(opt.use_external_focal_length)
         workers = opt.num_data_workers
-    loader = DataLoader(testset, shuffle=True, num_workers=workers)   # reference :147 (order only affects line order)
+    # reference :147 (shuffle: the order only affects the line order of the pose file). Batches are collated by the workers
+    # and pinned, so that the main process only enqueues copies and kernels
+    from acezero_b200.registration import collate_same_size
+    loader = DataLoader(testset, shuffle=True, num_workers=workers, batch_size=max(1, opt.loader_batch),
+                        collate_fn=collate_same_size, pin_memory=True)
 
     if opt.encoder_seed is not None:
         from acezero_b200.weights import random_encoder_state

@@ -5,6 +5,7 @@ cta_group::1 kernel on the weight-gradient shape (8 x 512 x 512 x 5120, MN-major
 Run each case in the order printed: the first ones are the smallest (one cluster, one k-block).
 """
 import ctypes as C
+import os
 import sys
 
 import torch
@@ -85,6 +86,37 @@ def timing():
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1000
         print(f"wgrad shape, {name}: {us:.1f} us = {2 * L * C5 * C5 * rows / us / 1e6:.0f} TFLOP/s", flush=True)
+        if fn == "acez_gemm2cta_f16" and os.environ.get("ACEZ_GEMM2_DBG", "0") == "1":
+            import numpy as np
+            n_cta = 2 * (C5 // 256) * (C5 // (bn or 256)) * L
+            buf = np.zeros(n_cta * 8, dtype=np.int64)
+            _lib.check(_lib.load().acez_debug_gemm2_clocks(buf.ctypes.data_as(C.c_void_p), n_cta))
+            b = buf.reshape(n_cta, 8)
+            lead = b[b[:, 1] > 0]
+            print(f"   MMA warp (leaders): loop {np.median(lead[:, 1]):.0f} cycles, of which waiting for operands {np.median(lead[:, 0]):.0f} "
+                  f"(max {lead[:, 0].max()}); producers: loop {np.median(b[:, 3]):.0f}, waiting for free stages {np.median(b[:, 2]):.0f}; "
+                  f"epilogue {np.median(b[:, 4]):.0f}", flush=True)
+
+
+def timing_kmajor():
+    """The same FLOPs with K-major operands (rows contiguous): is the MN-major operand layout what holds the weight-gradient
+    GEMM back?"""
+    L, C5, rows = 8, 512, 5120
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = (torch.randn((L, C5, rows), device="cuda", generator=g) * 0.1).half()
+    B = (torch.randn((L, C5, rows), device="cuda", generator=g) * 0.1).half()
+    for bn in (128, 0):
+        for _ in range(3):
+            run("acez_gemm2cta_f16", A, B, 0, C5, C5, rows, L, bn)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            run("acez_gemm2cta_f16", A, B, 0, C5, C5, rows, L, bn)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1000
+        print(f"same shape, K-major operands, 256x{bn or 256} tiles: {us:.1f} us = {2 * L * C5 * C5 * rows / us / 1e6:.0f} TFLOP/s", flush=True)
 
 
 def main():
@@ -105,6 +137,7 @@ def main():
     print("RESULT", "PASS" if ok else "FAIL", flush=True)
     if ok:
         timing()
+        timing_kmajor()
     sys.exit(0 if ok else 1)
 
 
