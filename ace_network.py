@@ -142,8 +142,12 @@ class Head(nn.Module):
         mods = dict(self.named_modules())
         return [getattr(mods[n], s) for n in self._layer_names() for s in ("weight", "bias")]
 
+    def _homogeneous_buffers(self):
+        return (self.h_beta, self.max_inv_scale, self.min_inv_scale) if self.use_homogeneous else ()
+
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self._params()) + (self.mean.data_ptr(), self.mean._version)
+        return tuple((p.data_ptr(), p._version) for p in self._params()) + (self.mean.data_ptr(), self.mean._version) + \
+            tuple((b.data_ptr(), b._version) for b in self._homogeneous_buffers())
 
     def engine(self, training=False, max_rows=5120):
         """HeadEngine holding a copy of the current weights (rebuilt / reloaded when the module's tensors change)."""
@@ -151,12 +155,14 @@ class Head(nn.Module):
         dev = self.mean.device
         if dev.type != "cuda":
             raise RuntimeError("ace_network.Head runs on CUDA (sm_100a) only; move the module to the GPU")
-        if self._engine is None or (training and not self._engine.training):
-            max_scale = float(self.max_scale) if self.use_homogeneous else 4.0
-            min_scale = float(self.min_scale) if self.use_homogeneous else 0.01
+        hom = tuple(float(b) for b in self._homogeneous_buffers())
+        if self._engine is None or (training and not self._engine.training) or \
+                (hom and hom != (self._engine.h_beta, self._engine.max_inv_scale, self._engine.min_inv_scale)):
+            # the engine reads the de-homogenisation constants from the module's BUFFERS, as the reference's forward does
+            # (ace_network.py:139-144) — for an fp16 head file these are the fp16-rounded values stored in it
+            kw = dict(h_beta=hom[0], max_inv_scale=hom[1], min_inv_scale=hom[2]) if hom else {}
             self._engine = HeadEngine(self.num_head_blocks, self.use_homogeneous, self.mean.reshape(3).cpu(),
-                                      max_rows=max_rows, training=training, homogeneous_min_scale=min_scale,
-                                      homogeneous_max_scale=max_scale, device=dev)
+                                      max_rows=max_rows, training=training, device=dev, **kw)
             self._engine_version = None
         v = self._weights_version()
         if v != self._engine_version:

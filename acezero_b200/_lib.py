@@ -98,7 +98,7 @@ EXPORTS = [
     "acez_head_backward", "acez_head_train_fwd_bwd",
     "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_schedule_init", "acez_schedule_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
-    "acez_encoder_forward",
+    "acez_encoder_forward", "acez_pointcloud_metrics",
 ]
 
 
@@ -151,6 +151,7 @@ def load():
     lib.acez_encoder_plan_destroy.restype = None
     lib.acez_encoder_out_hw.argtypes = [i, i, C.POINTER(i), C.POINTER(i)]
     lib.acez_encoder_forward.argtypes = [vp, vp, i, i, i, i, vp, vp]
+    lib.acez_pointcloud_metrics.argtypes = [vp, i, i, i, vp, vp, i, vp, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -105,6 +105,9 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n0 = (tile % args.tiles_n) * T2_BN;
   const int nb0 = n0 + rank * (T2_BN / 2);                            // this CTA's half of B
   const int z = blockIdx.z;
+  const int split = blockIdx.y, n_split = args.split_k > 1 ? args.split_k : 1;
+  const int kb_begin = (int)((long long)args.k_blocks * split / n_split);
+  const int kb_end = (int)((long long)args.k_blocks * (split + 1) / n_split);
   const int k_blocks = args.k_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -145,7 +148,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       long long t_wait = 0;
       const long long t_begin = args.dbg ? clock64() : 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         const long long t0 = args.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (args.dbg) t_wait += clock64() - t0;
@@ -168,7 +171,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
       }
       if (args.dbg) {
-        long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
+        long long* d = args.dbg + 8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
         d[2] = t_wait; d[3] = clock64() - t_begin;
       }
     }
@@ -181,7 +184,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t bias_started = 0u;
     long long t_wait = 0;
     const long long t_begin = args.dbg ? clock64() : 0;
-    for (int kb = 0; kb < k_blocks; ++kb) {
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
       const long long t0 = args.dbg ? clock64() : 0;
       mbar_wait(&full_bar[stage], phase);
       if (args.dbg) t_wait += clock64() - t0;
@@ -194,7 +197,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int k = 0; k < T2_BK / 16; ++k) {
           const uint64_t da = make_smem_desc(a_addr + k * args.a_kstep, args.a_lbo, args.a_sbo, 2);
           const uint64_t db = make_smem_desc(b_addr + k * args.b_kstep, args.b_lbo, args.b_sbo, 2);
-          t2_umma_f16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          t2_umma_f16(tmem_base, da, db, idesc, (kb != kb_begin || k != 0) ? 1u : 0u);
           if (do_bias) {
             const uint64_t d1 = make_smem_desc(smem_u32(sOnes) + k * 32, 0, 1024, 2);
             t2_umma_f16(tmem_base + T2_BN, da, d1, idesc_ones, (bias_started | (uint32_t)k) != 0u ? 1u : 0u);
@@ -205,13 +208,13 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (elect_one()) {
         t2_commit_both(&empty_bar[stage]);
-        if (kb == k_blocks - 1) t2_commit_both(tmem_full_bar);
+        if (kb == kb_end - 1) t2_commit_both(tmem_full_bar);
       }
       __syncwarp();
       if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
     }
     if (args.dbg && lane == 0) {
-      long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
+      long long* d = args.dbg + 8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
       d[0] = t_wait; d[1] = clock64() - t_begin;
     }
   } else if (warp >= 2) {
@@ -224,12 +227,53 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const long long t_epi = args.dbg ? clock64() : 0;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     bool bad = false;
+    // split-K: the first CTA of this (tile, half) to arrive parks its partial in the workspace, the second one adds it to its own
+    // accumulator and writes the result (+ the fp16-range check of the SUM). role: 0 = no split / write out, 1 = first, 2 = second
+    __shared__ int s_role;
+    int role = 0;
+    float* part_tile = nullptr;
+    unsigned int* sync = nullptr;
+    if (n_split > 1) {
+      const size_t unit = ((size_t)z * (gridDim.x >> 1) + tile) * 2 + rank;
+      part_tile = args.split_part + unit * (size_t)T2_BM * T2_BN;
+      sync = args.split_sync + unit * 2;
+      if (warp == 2 && lane == 0) s_role = atomicAdd(&sync[0], 1u) == 0u ? 1 : 2;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      role = s_role;
+      if (role == 2) {
+        if (warp == 2 && lane == 0) {
+          while (atomicAdd(&sync[1], 0u) == 0u) __nanosleep(64);   // the first CTA is running (it has arrived): bounded wait
+          __threadfence();
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
+    const int lrow = quarter * 32 + lane;   // row inside this CTA's 128-row half
 #pragma unroll 1
     for (int c = grp; c < T2_BN / 32; c += 2) {
       uint32_t v[32];
       tmem_ld_32x32(t_row + c * 32, v);
       tmem_ld_wait();
       const int ncol = n0 + c * 32;
+      if (role == 1) {   // park the partial (whole tile, no bounds: the workspace is tile sized)
+        float4* dstp = reinterpret_cast<float4*>(part_tile + (size_t)lrow * T2_BN + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dstp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        continue;
+      }
+      if (role == 2) {
+        const float4* srcp = reinterpret_cast<const float4*>(part_tile + (size_t)lrow * T2_BN + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 p = __ldcg(srcp + j);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + p.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + p.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + p.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + p.w);
+        }
+      }
       if (row >= args.M || ncol >= args.N) continue;
       float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol);
 #pragma unroll
@@ -245,24 +289,35 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    if (role == 1) {      // publish the parked partial
+      __threadfence();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) atomicExch(&sync[1], 1u);
+    } else if (role == 2) {   // consumed: reset for the next launch
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) { sync[0] = 0u; sync[1] = 0u; }
+    }
     if (bias_col && grp == 0) {
       __shared__ int s_last;
       const int tiles_m = (int)(gridDim.x >> 1) / args.tiles_n;
       const int r_in_tile = rank * T2_BM + quarter * 32 + lane;            // 0..255 inside the pair's M-tile
-      float* part = args.bias_part + ((size_t)(z * tiles_m + tm) * args.tiles_n) * (2 * T2_BM);
+      const int slots = args.tiles_n * n_split;                            // partial row sums per M-tile: one per (column tile, split)
+      float* part = args.bias_part + ((size_t)(z * tiles_m + tm) * slots) * (2 * T2_BM);
       float g = 0.f;
-      if (k_blocks > tn) {   // this tile issued bias UMMAs
+      bool any_bias = false;
+      for (int kb = kb_begin; kb < kb_end; ++kb) any_bias |= (kb % args.tiles_n) == tn;
+      if (any_bias) {   // this CTA pair issued bias UMMAs
         uint32_t v[32];
         tmem_ld_32x32(t_row + T2_BN, v);  // columns BN..BN+15 hold the partial row sum (all equal); 32 columns are allocated
         tmem_ld_wait();
         g = __uint_as_float(v[0]);
       }
-      part[(size_t)tn * (2 * T2_BM) + r_in_tile] = g;
+      part[(size_t)(tn * n_split + split) * (2 * T2_BM) + r_in_tile] = g;
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (quarter == 0 && lane == 0) {
         const unsigned int done = atomicAdd(args.bias_count + z * tiles_m + tm, 1u);
-        s_last = (done == 2u * (unsigned int)args.tiles_n - 1u) ? 1 : 0;   // both CTAs of all column tiles have stored
+        s_last = (done == 2u * (unsigned int)slots - 1u) ? 1 : 0;   // both CTAs of all (column tile, split) pairs have stored
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (s_last) {
@@ -272,7 +327,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int half = 0; half < 2; ++half) {
           const int rt = half * T2_BM + t128;
           float sum = 0.f;
-          for (int j = 0; j < args.tiles_n; ++j) sum += __ldcg(part + (size_t)j * (2 * T2_BM) + rt);
+          for (int j = 0; j < slots; ++j) sum += __ldcg(part + (size_t)j * (2 * T2_BM) + rt);
           const int grow = tm * 2 * T2_BM + rt;
           if (grow < args.M) {
             args.bias_grad[(long long)z * args.bias_grad_zstride + grow] = sum;
@@ -285,7 +340,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (args.nonfinite != nullptr) {
       if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
-    if (args.dbg && warp == 2 && lane == 0) args.dbg[8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x) + 4] = clock64() - t_epi;
+    if (args.dbg && warp == 2 && lane == 0) args.dbg[8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 4] = clock64() - t_epi;
   }
 
   __syncwarp();
@@ -325,7 +380,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Ar
   }
   const int tiles_m = (a.M + 2 * T2_BM - 1) / (2 * T2_BM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * tiles_m * a.tiles_n, 1, batch);
+  cfg.gridDim = dim3(2 * tiles_m * a.tiles_n, a.split_k > 1 ? a.split_k : 1, batch);
   cfg.blockDim = dim3(T2_THREADS);
   cfg.dynamicSmemBytes = T2_SMEM;
   cfg.stream = stream;
@@ -405,6 +460,31 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
     ACEZ_REQUIRE((size_t)L.batch * tiles_m <= 4096, "gemm2cta: too many row tiles for the probe's counters");
     a.bias_part = g_part;
     a.bias_count = g_count;
+  }
+  {
+    // probe entry: ACEZ_GEMM2_SPLITK=2 contracts each tile in two halves (two CTAs per tile and half)
+    static const int want_split = [] { const char* e = getenv("ACEZ_GEMM2_SPLITK"); return e != nullptr ? atoi(e) : 1; }();
+    a.split_k = (want_split == 2 && a.k_blocks >= 2) ? 2 : 1;
+    if (a.split_k == 2) {
+      static float* g_split = nullptr;
+      static unsigned int* g_sync = nullptr;
+      static size_t g_cap2 = 0;
+      const int tiles_m = (d->M + 2 * T2_BM - 1) / (2 * T2_BM);
+      const size_t units = (size_t)L.batch * tiles_m * a.tiles_n * 2;
+      const size_t need = units * T2_BM * (size_t)L.bn;
+      if (need > g_cap2) {
+        if (g_split) cudaFree(g_split);
+        ACEZ_CUDA(cudaMalloc(&g_split, need * sizeof(float)));
+        g_cap2 = need;
+      }
+      if (g_sync == nullptr) {
+        ACEZ_CUDA(cudaMalloc(&g_sync, 8192 * sizeof(unsigned int)));
+        ACEZ_CUDA(cudaMemset(g_sync, 0, 8192 * sizeof(unsigned int)));
+      }
+      ACEZ_REQUIRE(units * 2 <= 8192, "gemm2cta: too many tiles for the probe's split-K counters");
+      a.split_part = g_split;
+      a.split_sync = g_sync;
+    }
   }
   a.nonfinite = d->nonfinite;
   a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;

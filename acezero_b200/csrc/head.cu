@@ -46,6 +46,7 @@ struct acez_head_plan {
   float* G3;
   float* FC3PART;
   float* WBIAS;
+  float* WSPLIT;
   float* BLKPART;
   unsigned int* BLKCOUNT;
   bool counters_zeroed;
@@ -71,7 +72,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, wbias, blkpart, total;
+  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, wbias, wsplit, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -91,8 +92,9 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
     o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
     o.wbias = off; off = align_up(off + (size_t)L * 2 * 4 * 256 * sizeof(float), 1024);  // wgrad bias partials [L][2][<=4][256]
+    o.wsplit = off; off = align_up(off + (size_t)L * 8 * 128 * 256 * sizeof(float), 1024);  // split-K partial tiles [L][4 tiles][2][128][256]
   }
-  o.blkpart = off; off = align_up(off + 4096 * 8 * sizeof(float) + 256, 1024);  // tail per-block partials + counter
+  o.blkpart = off; off = align_up(off + 4096 * 8 * sizeof(float) + 4096, 1024);  // tail per-block partials + 1024 counters
   o.total = off;
   return o;
 }
@@ -739,8 +741,10 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       W.batch = L;
       W.a_mn = W.b_mn = 1;
       {
+        // 256 x 256 tiles per SM pair with split-K 2 (128 CTAs; per k-block 64 B/clk of operand fill instead of 96: the N = 128
+        // tiles ran the tensor pipe at ~50 %, round-2 cycle counters) or 256 x 128 tiles without split (ACEZ_WGRAD_2CTA_BN=128)
         const char* e = getenv("ACEZ_WGRAD_2CTA_BN");
-        W.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;  // 128: 64 pairs = 128 CTAs without split-K
+        W.bn = (e != nullptr && atoi(e) == 128) ? 128 : 256;
       }
       Gemm2Args& g = W.args;
       g.M = kC; g.N = kC; g.k_blocks = (rows + 63) / 64;
@@ -749,6 +753,9 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       g.bias_grad = h->grads + (size_t)kC * kC; g.bias_grad_zstride = (long long)kLayerStride;
       g.bias_part = h->WBIAS;
       g.bias_count = h->BLKCOUNT + 8;   // [L][2] arrival counters behind the tail's; zeroed once with it (launch_tail)
+      g.split_k = (W.bn == 256 && g.k_blocks >= 2) ? 2 : 1;
+      g.split_part = h->WSPLIT;
+      g.split_sync = h->BLKCOUNT + 64;  // [L][2 x 2 tiles][2 CTAs][2]
       g.a_lbo = 8192; g.a_sbo = 1024; g.a_kstep = 2048;
       g.b_lbo = 8192; g.b_sbo = 1024; g.b_kstep = 2048;
     }
@@ -864,7 +871,7 @@ static int ensure_side_stream(acez_head_plan* h) {
 static int launch_tail(acez_head_plan* h, TailArgs& t, int rows, cudaStream_t s, int* nonfinite, bool with_fc3_grad,
                        bool pdl) {
   if (!h->counters_zeroed) {  // once per plan: the completion counter is self-resetting afterwards
-    ACEZ_CUDA(cudaMemsetAsync(h->BLKCOUNT, 0, 256, s));
+    ACEZ_CUDA(cudaMemsetAsync(h->BLKCOUNT, 0, 4096, s));   // tail counter [0], wgrad bias counters [8..), split-K sync [64..)
     h->counters_zeroed = true;
     pdl = false;  // predecessor is a memset
   }
@@ -970,6 +977,24 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   ACEZ_REQUIRE(!cfg->training || grads != nullptr, "head_plan_create: training plan needs a gradient buffer");
   ACEZ_REQUIRE(workspace_bytes >= acez_head_workspace_bytes(cfg), "head_plan_create: workspace too small (%zu < %zu)",
                workspace_bytes, acez_head_workspace_bytes(cfg));
+  {
+    // The chain / GEMM kernels run with the maximum shared-memory carve-out (227 KB per SM). A kernel that prefers another
+    // L1 / shared split makes the SMs re-partition between launches; the small kernels of the iteration stream their data and
+    // gain nothing from L1, so they ask for the same carve-out (ACEZ_SMEM_CARVEOUT=0 leaves the driver's default).
+    static bool done = false;
+    const char* e = getenv("ACEZ_SMEM_CARVEOUT");
+    if (!done && (e == nullptr || atoi(e) != 0)) {
+      const int pct = cudaSharedmemCarveoutMaxShared;
+      cudaFuncSetAttribute(gather_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(gather_rows_multi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(head_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(fc3_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(grad_check_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(adamw_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaGetLastError();   // a hint: failures are not errors
+      done = true;
+    }
+  }
   acez_head_plan* h = new acez_head_plan();
   h->cfg = *cfg;
   h->nres = cfg->num_res_blocks;
@@ -990,6 +1015,7 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
   h->FC3PART = cfg->training ? reinterpret_cast<float*>(base + lo.fc3part) : nullptr;
   h->WBIAS = cfg->training ? reinterpret_cast<float*>(base + lo.wbias) : nullptr;
+  h->WSPLIT = cfg->training ? reinterpret_cast<float*>(base + lo.wsplit) : nullptr;
   h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);
   h->BLKCOUNT = reinterpret_cast<unsigned int*>(base + lo.blkpart + 4096 * 8 * sizeof(float));
   h->counters_zeroed = false;

@@ -101,21 +101,21 @@ __device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity, uint3
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);  // ~1 s
+    if (clock64() - t0 > kChainWatchdogCycles) chain_wait_timeout(tag, parity);  // ~1 s
   }
 }
 __device__ __forceinline__ void chain_wait_cluster_relaxed(uint64_t* bar, uint32_t parity, uint32_t tag) {
   if (mbar_try_wait_cluster_relaxed(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster_relaxed(bar, parity)) {
-    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);
+    if (clock64() - t0 > kChainWatchdogCycles) chain_wait_timeout(tag, parity);
   }
 }
 __device__ __forceinline__ void chain_wait_cluster(uint64_t* bar, uint32_t parity, uint32_t tag) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 2000000000ll) chain_wait_timeout(tag, parity);
+    if (clock64() - t0 > kChainWatchdogCycles) chain_wait_timeout(tag, parity);
   }
 }
 // bulk copy local shared memory -> the peer CTA's shared memory; completion (bytes) is signalled on the peer's mbarrier

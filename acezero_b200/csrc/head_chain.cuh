@@ -15,6 +15,10 @@
 namespace acez {
 
 enum ChainMode : int { CHAIN_FWD = 0, CHAIN_DGRAD = 1 };
+// A barrier wait of the chain kernels that lasts longer than this is reported (tag of the wait, step, index) and trapped
+// instead of hanging the GPU: ~10 s at 1.9 GHz, far above any legitimate stall (profiler replay, time slicing, throttling);
+// the clock is only read on the slow path, after a first failed try_wait.
+static constexpr long long kChainWatchdogCycles = 20000000000ll;
 static constexpr int kChainMaxSteps = 20;      // hidden layers handled by one launch (3 * res blocks + 2 <= 20)
 static constexpr int kChainFlagResInit = 64;   // ChainArgs.flags: FWD has residual layers, res_0 = the input tile
 

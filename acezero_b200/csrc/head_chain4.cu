@@ -81,7 +81,7 @@ __device__ __forceinline__ void c4_wait(uint64_t* bar, uint32_t parity, uint32_t
   if (c4_try_wait(bar, parity, SEM)) return;
   const long long t0 = clock64();
   while (!c4_try_wait(bar, parity, SEM)) {
-    if (clock64() - t0 > 2000000000ll) c4_timeout(tag, parity);
+    if (clock64() - t0 > kChainWatchdogCycles) c4_timeout(tag, parity);
   }
 }
 __device__ __forceinline__ void c4_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {

@@ -111,6 +111,12 @@ extern "C" int acez_schedule_step(const acez_schedule_params* p, float* state_de
   ACEZ_REQUIRE(p->batch_global > 0, "schedule_step: batch_global must be positive");
   int rc = acez_device_check();
   if (rc) return rc;
+  static bool hinted = false;
+  if (!hinted) {   // same shared-memory carve-out as the big kernels of the iteration (see acez_head_plan_create)
+    cudaFuncSetAttribute(schedule_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+    hinted = true;
+  }
   schedule_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*p, state_dev, inlier_count_dev, hyper_dev);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;

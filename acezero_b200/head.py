@@ -29,7 +29,8 @@ class HeadEngine:
     """Flat-buffer head. `params` is one fp32 CUDA tensor; `views()` exposes reference-named tensors aliasing it."""
 
     def __init__(self, num_head_blocks=1, use_homogeneous=True, mean=(0.0, 0.0, 0.0), max_rows=5120, training=False,
-                 homogeneous_min_scale=0.01, homogeneous_max_scale=4.0, device="cuda"):
+                 homogeneous_min_scale=0.01, homogeneous_max_scale=4.0, device="cuda", h_beta=None, max_inv_scale=None,
+                 min_inv_scale=None):
         self.lib = _lib.load()
         _lib.check(self.lib.acez_device_check(), "acez_device_check")
         self.device = torch.device(device)
@@ -40,9 +41,12 @@ class HeadEngine:
         self.names = head_layer_names(num_head_blocks)
         self.L = len(self.names)
         self.C3 = 4 if use_homogeneous else 3
-        self.max_inv_scale = 1.0 / homogeneous_max_scale
-        self.min_inv_scale = 1.0 / homogeneous_min_scale
-        self.h_beta = math.log(2) / (1.0 - self.max_inv_scale)
+        # the de-homogenisation constants the reference's forward reads are BUFFERS of the state dict (ace_network.py:108-114,
+        # 139-144): a checkpoint stored in fp16 carries h_beta = 0.92432 and min_inv_scale = 100.0, not the values recomputed
+        # from max_scale / min_scale — callers that hold the buffers pass them
+        self.max_inv_scale = 1.0 / homogeneous_max_scale if max_inv_scale is None else float(max_inv_scale)
+        self.min_inv_scale = 1.0 / homogeneous_min_scale if min_inv_scale is None else float(min_inv_scale)
+        self.h_beta = math.log(2) / (1.0 - self.max_inv_scale) if h_beta is None else float(h_beta)
         self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(3).clone()
         self.cfg = self._config()
         self.n_params = int(self.lib.acez_head_param_count(C.byref(self.cfg)))

@@ -14,13 +14,15 @@ from torch.utils.data.dataloader import default_collate
 class BoxRoom:
     """Axis-aligned room [-hx,hx] x [-hy,hy] x [-hz,hz] with a smooth multi-scale texture f(x,y,z) in [0,1]."""
 
-    def __init__(self, seed=2089, half=(3.0, 2.0, 2.5), n_waves=48):
+    def __init__(self, seed=2089, half=(3.0, 2.0, 2.5), n_waves=48, octave_shift=0.0):
         rs = np.random.RandomState(seed)
         self.half = torch.tensor(half, dtype=torch.float32)
-        # random plane waves over several octaves; view-consistent, high-entropy, alias-free at 480x640
+        # random plane waves over several octaves; view-consistent, high-entropy. `octave_shift` moves the band with the image
+        # resolution (one octave per doubling of the focal length) so that the 81-pixel receptive field of the encoder sees the
+        # same amount of texture at 480x640 / f = 525 as at 240x320 / f = 262.5
         freq = rs.standard_normal((n_waves, 3)).astype(np.float32)
         freq /= np.linalg.norm(freq, axis=1, keepdims=True)
-        octave = (2.0 ** rs.uniform(0.5, 4.5, n_waves)).astype(np.float32)
+        octave = (2.0 ** (rs.uniform(0.5, 4.5, n_waves) + octave_shift)).astype(np.float32)
         self.freq = torch.from_numpy(freq * octave[:, None])
         self.phase = torch.from_numpy(rs.uniform(0, 2 * math.pi, n_waves).astype(np.float32))
         self.amp = torch.from_numpy((1.0 / np.sqrt(octave)).astype(np.float32))
@@ -84,7 +86,7 @@ class SyntheticDataset(Dataset):
 
     def __init__(self, n_images=64, H=480, W=640, focal=525.0, seed=2089, with_coords=False, device="cpu",
                  pose_noise=0.0, indices=None, s_offset=0.0):
-        self.room = BoxRoom(seed).to(device)
+        self.room = BoxRoom(seed, octave_shift=math.log2(max(float(focal), 1.0) / 262.5)).to(device)
         self.device = device
         self.H, self.W, self.focal = H, W, float(focal)
         all_poses = trajectory(n_images if indices is None else max(indices) + 1, seed, s_offset=s_offset)

@@ -335,6 +335,16 @@ int acez_encoder_out_hw(int H, int W, int* h8, int* w8);
 int acez_encoder_forward(acez_encoder_plan* plan, const void* image, int image_is_fp16, int n, int H, int W,
                          void* features_out, acez_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Point-cloud export metrics (reference ace_vis_util.py:431-592): per cell of n predicted scene-coordinate maps
+ * [n,3,h,w] (device), under the mapping poses pose_inv [n,3,4] (world -> camera) and intrinsics K [n,3,3]:
+ *   err   [n,h*w]  L1 reprojection error against the cell's pixel subsample * (x + 0.5, y + 0.5)  (:489-503)
+ *   grad  [n,h*w]  max(|X(x,y) - X(x-1,y)|, |X(x,y) - X(x,y-1)|), reflect-padded first column / row  (:506-515)
+ *   depth [n,h*w]  camera-space z                                                                   (:528)
+ * ---------------------------------------------------------------------------------------------------------- */
+int acez_pointcloud_metrics(const float* sc, int n, int h, int w, const float* pose_inv_n34, const float* K_n33,
+                            int subsample, float* err, float* grad, float* depth, acez_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
