@@ -137,24 +137,30 @@ class SyntheticDataset(Dataset):
 class CachedDataset(Dataset):
     """The items of another dataset rendered ONCE and served from host memory (benchmarks: the procedural renderer of
     SyntheticDataset costs more than the encoder; real datasets decode on DataLoader workers). Same 9-tuples, same
-    accessor surface as CamLocDataset / SyntheticDataset."""
+    accessor surface as CamLocDataset / SyntheticDataset. keep_base=False drops the reference to the source dataset (and
+    with it any CUDA state), so that the object can be handed to forked DataLoader workers."""
 
-    def __init__(self, base):
-        self.base = base
+    def __init__(self, base, keep_base=True):
         self.items = [base[i] for i in range(len(base))]
         self.rgb_files = base.rgb_files
         self.poses = base.poses
+        self.gt_poses = getattr(base, "gt_poses", base.poses)
         self.mean_cam_center = base.mean_cam_center
+        self._focals = [base.get_focal_length(i) for i in range(len(base))]
+        self.base = base if keep_base else None
 
     def __len__(self):
         return len(self.items)
 
     def set_external_focal_length(self, f):
+        if self.base is None:
+            raise RuntimeError("CachedDataset(keep_base=False) cannot re-render for another focal length")
         self.base.set_external_focal_length(f)
         self.items = [self.base[i] for i in range(len(self.base))]
+        self._focals = [self.base.get_focal_length(i) for i in range(len(self.base))]
 
     def get_focal_length(self, idx):
-        return self.base.get_focal_length(idx)
+        return self._focals[idx]
 
     def __getitem__(self, idx):
         if isinstance(idx, list):

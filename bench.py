@@ -331,7 +331,7 @@ def run_pipeline(dev):
     test = SyntheticDataset(n, H=480, W=640, focal=525.0, device=str(dev), s_offset=0.5)   # views between the mapping frames
     test.gt_poses = trajectory(n, s_offset=0.5)
     test.poses = [p.clone() for p in test.gt_poses]
-    test = CachedDataset(test)
+    test = CachedDataset(test, keep_base=False)   # no CUDA state: the loader forks worker processes
     from acezero_b200.registration import collate_same_size
     gen = torch.Generator().manual_seed(1305)
 
@@ -348,7 +348,7 @@ def run_pipeline(dev):
     dt = (time.perf_counter() - t0) / reps
     rot, tra = [], []
     for r in res:
-        T, G = r["pose"].astype(np.float64), test.base.gt_poses[r["index"]].numpy().astype(np.float64)
+        T, G = r["pose"].astype(np.float64), test.gt_poses[r["index"]].numpy().astype(np.float64)
         dR = T[:3, :3].T @ G[:3, :3]
         rot.append(float(np.rad2deg(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))))
         tra.append(float(np.linalg.norm(T[:3, 3] - G[:3, 3])))
