@@ -447,7 +447,7 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
     static unsigned int* g_count = nullptr;
     static size_t g_cap = 0;
     const int tiles_m = (d->M + 2 * T2_BM - 1) / (2 * T2_BM);
-    const size_t need = (size_t)L.batch * tiles_m * a.tiles_n * 2 * T2_BM;
+    const size_t need = (size_t)L.batch * tiles_m * a.tiles_n * 2 /*split-K slots*/ * 2 * T2_BM;
     if (need > g_cap) {
       if (g_part) cudaFree(g_part);
       ACEZ_CUDA(cudaMalloc(&g_part, need * sizeof(float)));

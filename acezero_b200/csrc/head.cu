@@ -741,10 +741,11 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       W.batch = L;
       W.a_mn = W.b_mn = 1;
       {
-        // 256 x 256 tiles per SM pair with split-K 2 (128 CTAs; per k-block 64 B/clk of operand fill instead of 96: the N = 128
-        // tiles ran the tensor pipe at ~50 %, round-2 cycle counters) or 256 x 128 tiles without split (ACEZ_WGRAD_2CTA_BN=128)
+        // 256 x 128 tiles per SM pair: 64 pairs = 128 CTAs, no split-K (default). ACEZ_WGRAD_2CTA_BN=256: 256 x 256 tiles with
+        // split-K 2 (also 128 CTAs; the tensor pipe runs at 87 % instead of 50 % per CTA, round-2 cycle counters, but the
+        // two-arriver reduction of 128 KB partial tiles costs more than it saves: 182.9 vs 177.8 us per iteration)
         const char* e = getenv("ACEZ_WGRAD_2CTA_BN");
-        W.bn = (e != nullptr && atoi(e) == 128) ? 128 : 256;
+        W.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;
       }
       Gemm2Args& g = W.args;
       g.M = kC; g.N = kC; g.k_blocks = (rows + 63) / 64;

@@ -147,8 +147,8 @@ __device__ __forceinline__ uint32_t c4_prmt(uint32_t a, uint32_t b, uint32_t sel
 // bit 16 + t = column 2t + 1 (t = 0..15). A packed half2 compare (HSET2: 0xFFFF per true half) then needs ONE LOP3 per column
 // pair to deposit both bits, and the dgrad side one shift + one prmt (sign replication) to expand them again.
 template <bool RES_ADD, bool WANT_MASK>
-__device__ __forceinline__ void c4_fwd_half(const uint32_t (&vv)[32], uint32_t (&res)[32], const int hf, const uint32_t bias_addr,
-                                            const uint32_t dst, const uint32_t swz, uint32_t& bits) {
+__device__ __forceinline__ void c4_fwd_half(const uint32_t (&vv)[32], uint32_t* __restrict__ res /*16 words: this half*/, const int hf,
+                                            const uint32_t bias_addr, const uint32_t dst, const uint32_t swz, uint32_t& bits) {
   const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
   uint32_t word = 0u;
 #pragma unroll
@@ -167,7 +167,7 @@ __device__ __forceinline__ void c4_fwd_half(const uint32_t (&vv)[32], uint32_t (
       __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(vv[vc]) + bq[2 * t], __uint_as_float(vv[vc + 1]) + bq[2 * t + 1]), zero2);
       if (WANT_MASK) word |= __hgt2_mask(h, zero2) & ((1u << tt) | (1u << (16 + tt)));   // pre-residual x > 0
       if (RES_ADD) {
-        uint32_t& rs = res[4 * q + t];
+        uint32_t& rs = res[4 * q4 + t];
         h = __hadd2(*reinterpret_cast<const __half2*>(&rs), h);  // residual sum in fp16, as the reference's `res + x`
         rs = *reinterpret_cast<const uint32_t*>(&h);
       }
@@ -179,8 +179,8 @@ __device__ __forceinline__ void c4_fwd_half(const uint32_t (&vv)[32], uint32_t (
 }
 
 template <bool RES_ADD, bool RES_SAVE>
-__device__ __forceinline__ void c4_dgrad_half(const uint32_t (&vv)[32], uint32_t (&res)[32], const int hf, const uint32_t mask_word,
-                                              const uint32_t dst, const uint32_t swz, uint32_t& badbits) {
+__device__ __forceinline__ void c4_dgrad_half(const uint32_t (&vv)[32], uint32_t* __restrict__ res /*16 words: this half*/, const int hf,
+                                              const uint32_t mask_word, const uint32_t dst, const uint32_t swz, uint32_t& badbits) {
 #pragma unroll
   for (int q4 = 0; q4 < 4; ++q4) {
     const int q = hf * 4 + q4;
@@ -190,7 +190,7 @@ __device__ __forceinline__ void c4_dgrad_half(const uint32_t (&vv)[32], uint32_t
     for (int t = 0; t < 4; ++t) {
       const int vc = q4 * 8 + 2 * t;
       const int tt = q4 * 4 + t;
-      uint32_t& rs = res[4 * q + t];
+      uint32_t& rs = res[4 * q4 + t];
       // autograd: the conv-backward result is rounded to fp16 first, the skip gradient is added in fp16
       __half2 h = __floats2half2_rn(__uint_as_float(vv[vc]), __uint_as_float(vv[vc + 1]));
       if (RES_ADD) h = __hadd2(h, *reinterpret_cast<const __half2*>(&rs));
@@ -207,12 +207,15 @@ __device__ __forceinline__ void c4_dgrad_half(const uint32_t (&vv)[32], uint32_t
 
 // G = number of epilogue groups (each = 4 warps, one per TMEM lane quarter): 2 -> a group drains two 64-column boxes per
 // step in sequence (the round-1 epilogue), 4 -> one box per group, all four boxes of a step in parallel.
-template <int MODE, int G>
+// SPLIT (two groups only): both groups work on the SAME box, each on one 32-column half, box after box: the first box of a
+// step is published after one half-box time instead of one box time, the four boxes come out in index order.
+template <int MODE, int G, bool SPLIT>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
   constexpr bool kDgrad = (MODE == CHAIN_DGRAD);
-  constexpr int NB = 4 / G;            // boxes per epilogue group and step
+  static_assert(!SPLIT || G == 2, "the split epilogue is written for two groups");
+  constexpr int NB = SPLIT ? 4 : 4 / G;   // boxes a group touches per step (SPLIT: half of each of the four)
   constexpr int kEpiThreads = 128 * G;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -371,7 +374,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     const bool row_ok = row < args.rows;
     const int etid = threadIdx.x - 64;
     // one issuing thread per group, on different warps / SM sub-partitions
-    const bool issuer = (lane == 0) && (quarter == (G == 2 ? 2 - 2 * grp : grp));
+    const bool issuer = SPLIT ? (lane == 0 && grp == 0 && quarter == 2) : ((lane == 0) && (quarter == (G == 2 ? 2 - 2 * grp : grp)));
     const uint32_t swz = (uint32_t)(rr & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sA_u32 = smem_u32(sA), sBias_u32 = smem_u32(sBiasF);
@@ -379,12 +382,26 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     auto bar_all = [&]() { asm volatile("bar.sync 6, %0;" ::"n"(kEpiThreads) : "memory"); };
     uint32_t badbits = 0;
     // residual stream (forward) / skip-path gradient (dgrad) of this thread's row and boxes: stays in registers
-    uint32_t res[NB][32];
+    uint32_t res[NB][SPLIT ? 16 : 32];
 #pragma unroll
     for (int sl = 0; sl < NB; ++sl)
 #pragma unroll
-      for (int t = 0; t < 32; ++t) res[sl][t] = 0u;
-    if (!kDgrad && (args.flags & kChainFlagResInit)) {
+      for (int t = 0; t < (SPLIT ? 16 : 32); ++t) res[sl][t] = 0u;
+    if (SPLIT && !kDgrad && (args.flags & kChainFlagResInit)) {
+      // res_0 = the input tile: this thread's row, its 32-column half of each of the CTA's four boxes
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = c * 4 + b;
+        c4_wait<0>(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
+        const uint32_t src = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 t = lds_128(src + ((((uint32_t)(grp * 4 + q4)) ^ swz) << 4));
+          res[b][4 * q4] = t.x; res[b][4 * q4 + 1] = t.y; res[b][4 * q4 + 2] = t.z; res[b][4 * q4 + 3] = t.w;
+        }
+      }
+    }
+    if (!SPLIT && !kDgrad && (args.flags & kChainFlagResInit)) {
 #pragma unroll
       for (int sl = 0; sl < NB; ++sl) {
         const int j = c * 4 + grp + G * sl;
@@ -407,6 +424,69 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         if (s > 0) bar_all();
         if (etid < CN) sts_f32(sBias_u32 + 4u * (uint32_t)etid, __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f)));
       }
+      if constexpr (SPLIT) {
+        // ReLU-mask word of this thread's row and half for each box (dgrad): in flight while the accumulator is computed
+        uint32_t mwb[4] = {0u, 0u, 0u, 0u};
+        if (kDgrad && row_ok) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) mwb[b] = __ldcg(reinterpret_cast<const uint32_t*>(st.mask_in + (size_t)row * 64 + (c * 4 + b) * 8 + 4 * grp));
+        }
+        if (issuer) {
+          c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));   // see the comment in the other branch
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (dbg) dbg[8 + 8 * s + 5] = clock64();
+        }
+        c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
+        tcgen05_fence_after();
+        if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
+        bar_all();   // bias slice visible; the issuer's permissions hold for every epilogue thread
+        const int res_add = st.res_add, res_save = st.res_save;
+        const bool want_mask = !kDgrad && st.mask_out != nullptr;
+        uint32_t vv[2][32];
+        tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + grp * 32), vv[0]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = c * 4 + b;
+          tmem_ld_wait_for(vv[b & 1]);
+          if (b + 1 < 4) tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + (b + 1) * 64 + grp * 32), vv[(b + 1) & 1]);
+          const uint32_t dst = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
+          if (!kDgrad) {
+            uint32_t word = 0u;
+            const uint32_t bias_addr = sBias_u32 + 4u * (uint32_t)(b * 64);
+            if (res_add) {
+              if (want_mask) c4_fwd_half<true, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+              else c4_fwd_half<true, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+            } else {
+              if (want_mask) c4_fwd_half<false, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+              else c4_fwd_half<false, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+            }
+            if (want_mask && row_ok) *reinterpret_cast<uint32_t*>(st.mask_out + (size_t)row * 64 + j * 8 + 4 * grp) = word;
+          } else {
+            if (res_add) {
+              if (res_save) c4_dgrad_half<true, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+              else c4_dgrad_half<true, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+            } else {
+              if (res_save) c4_dgrad_half<false, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+              else c4_dgrad_half<false, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+            }
+          }
+          // box complete once both groups are here. Its TMEM columns are rewritten by the MMAs of step s+2, which are released
+          // (transitively) by the barrier arrival below: order the completed tcgen05.ld before it
+          tcgen05_fence_before();
+          fence_proxy_async();   // publish the half box to the tensor core / copy engines (async proxy)
+          bar_all();
+          if (issuer) {
+            const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+            if (!last) {
+              mbar_arrive(&a_ready[j]);
+              c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
+            }
+            if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, n_base + b * 64, m0, st.out_slot);
+            tma_store_commit();
+            if (dbg && (b == 0 || b == 2)) dbg[8 + 8 * s + (b == 0 ? 6 : 7)] = clock64();
+          }
+        }
+      } else {
       // ReLU-mask words of this thread's row for all its boxes (dgrad): in flight while the accumulator is still being computed
       uint2 mw[NB];
 #pragma unroll
@@ -449,22 +529,22 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
           uint32_t word = 0u;
           const uint32_t bias_addr = sBias_u32 + 4u * (uint32_t)(box * 64);
           if (res_add) {
-            if (want_mask) c4_fwd_half<true, true>(vv[p & 1], res[sl], hf, bias_addr, dst, swz, word);
-            else c4_fwd_half<true, false>(vv[p & 1], res[sl], hf, bias_addr, dst, swz, word);
+            if (want_mask) c4_fwd_half<true, true>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
+            else c4_fwd_half<true, false>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
           } else {
-            if (want_mask) c4_fwd_half<false, true>(vv[p & 1], res[sl], hf, bias_addr, dst, swz, word);
-            else c4_fwd_half<false, false>(vv[p & 1], res[sl], hf, bias_addr, dst, swz, word);
+            if (want_mask) c4_fwd_half<false, true>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
+            else c4_fwd_half<false, false>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
           }
           if (hf == 0) bits_lo = word;
           else bits_hi = word;
         } else {
           const uint32_t mword = hf == 0 ? mw[sl].x : mw[sl].y;
           if (res_add) {
-            if (res_save) c4_dgrad_half<true, true>(vv[p & 1], res[sl], hf, mword, dst, swz, badbits);
-            else c4_dgrad_half<true, false>(vv[p & 1], res[sl], hf, mword, dst, swz, badbits);
+            if (res_save) c4_dgrad_half<true, true>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
+            else c4_dgrad_half<true, false>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
           } else {
-            if (res_save) c4_dgrad_half<false, true>(vv[p & 1], res[sl], hf, mword, dst, swz, badbits);
-            else c4_dgrad_half<false, false>(vv[p & 1], res[sl], hf, mword, dst, swz, badbits);
+            if (res_save) c4_dgrad_half<false, true>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
+            else c4_dgrad_half<false, false>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
           }
         }
         if (hf == 1) {
@@ -487,6 +567,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
           }
         }
       }
+          }
     }
     if (issuer) tma_store_wait_all();
     if (kDgrad && args.nonfinite != nullptr) {
@@ -504,9 +585,9 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   }
 }
 
-template <int MODE, int G>
+template <int MODE, int G, bool SPLIT>
 static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
-  auto kern = head_chain4_kernel<MODE, G>;
+  auto kern = head_chain4_kernel<MODE, G, SPLIT>;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4));
@@ -557,12 +638,20 @@ int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
     const char* e = getenv("ACEZ_CHAIN_EPI_GROUPS");   // 2 (default): two boxes per epilogue group; 4: one box per group
     return (e != nullptr && atoi(e) == 4) ? 4 : 2;
   }();
-  if (groups == 2) {
-    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2>(C, stream, pdl);
-    return chain4_launch_mode<CHAIN_DGRAD, 2>(C, stream, pdl);
+  static const bool split = [] {
+    const char* e = getenv("ACEZ_CHAIN_EPI_SPLIT");   // both groups on the same box, half each (round-2 experiment)
+    return e != nullptr && atoi(e) != 0;
+  }();
+  if (groups == 2 && split) {
+    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2, true>(C, stream, pdl);
+    return chain4_launch_mode<CHAIN_DGRAD, 2, true>(C, stream, pdl);
   }
-  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 4>(C, stream, pdl);
-  return chain4_launch_mode<CHAIN_DGRAD, 4>(C, stream, pdl);
+  if (groups == 2) {
+    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2, false>(C, stream, pdl);
+    return chain4_launch_mode<CHAIN_DGRAD, 2, false>(C, stream, pdl);
+  }
+  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 4, false>(C, stream, pdl);
+  return chain4_launch_mode<CHAIN_DGRAD, 4, false>(C, stream, pdl);
 }
 
 }  // namespace acez
