@@ -96,7 +96,7 @@ EXPORTS = [
     "acez_head_param_count", "acez_head_workspace_bytes", "acez_head_plan_create", "acez_head_plan_destroy",
     "acez_head_sync_weights", "acez_head_input_ptr", "acez_head_plan_fused_chain", "acez_debug_chain_clocks", "acez_head_forward", "acez_head_forward_train",
     "acez_head_backward", "acez_head_train_fwd_bwd",
-    "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_schedule_init", "acez_schedule_step", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
+    "acez_gather_rows", "acez_gather_rows_multi", "acez_buffer_fill", "acez_adamw_step", "acez_schedule_init", "acez_schedule_step", "acez_gather_rows_multi_sched", "acez_dsac_workspace_bytes", "acez_dsac_forward_rgb_batch",
     "acez_encoder_workspace_bytes", "acez_encoder_plan_create", "acez_encoder_plan_destroy", "acez_encoder_out_hw",
     "acez_encoder_forward", "acez_pointcloud_metrics",
 ]
@@ -140,6 +140,7 @@ def load():
     lib.acez_adamw_step.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, vp, i, vp, vp]
     lib.acez_schedule_init.argtypes = [C.POINTER(ScheduleParams), vp, vp]
     lib.acez_schedule_step.argtypes = [C.POINTER(ScheduleParams), vp, vp, vp, vp]
+    lib.acez_gather_rows_multi_sched.argtypes = [vp, vp, vp, i, vp, i, C.POINTER(ScheduleParams), vp, vp, vp, vp]
     lib.acez_dsac_workspace_bytes.argtypes = [i, i, i, i]
     lib.acez_dsac_workspace_bytes.restype = C.c_size_t
     lib.acez_dsac_forward_rgb_batch.argtypes = [vp, i, i, i, vp, vp, vp, C.POINTER(DsacParams), vp, vp, vp,

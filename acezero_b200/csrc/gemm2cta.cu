@@ -275,11 +275,21 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       if (row >= args.M || ncol >= args.N) continue;
-      float4* dst = reinterpret_cast<float4*>(args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol);
+      // 256-bit stores: one full 32-byte sector per lane and instruction (with 16-byte stores every warp store touched 32
+      // half-written sectors and the epilogue ran at the L1 -> L2 request rate: 8.8 k cycles for a 128 x 256 tile, round 2)
+      float* dst = args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol;
+      if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(v[8 * j]), "r"(v[8 * j + 1]),
+                       "r"(v[8 * j + 2]), "r"(v[8 * j + 3]), "r"(v[8 * j + 4]), "r"(v[8 * j + 5]), "r"(v[8 * j + 6]), "r"(v[8 * j + 7])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
       if (args.nonfinite != nullptr) {
         // GradScaler check folded in: autocast materialises weight gradients in fp16, so |g| > 65504 is an overflow
 #pragma unroll

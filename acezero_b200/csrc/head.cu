@@ -18,6 +18,7 @@
 
 #include "gemm.cuh"
 #include "gemm2cta.cuh"
+#include "schedule.cuh"
 #include "head_chain.cuh"
 #include "repro_loss.cuh"
 
@@ -163,9 +164,20 @@ struct MultiGather {
   uint8_t* dst[8];
   int row_bytes[8];
 };
-__global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows, int n_arrays) {
+// Optional rider of the batch gather: the device-side schedule of the iteration (schedule.cuh) evaluated by thread 0 of
+// block 0, so that the first kernel of the iteration's graph does both (a separate one-thread kernel costs ~3 us of launch)
+struct GatherSched {
+  int enabled;
+  acez_schedule_params p;
+  float* state;
+  const float* inlier_count;
+  float* hyper;
+};
+__global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __restrict__ idx, int rows, int n_arrays,
+                                         const GatherSched sch) {
   pdl_wait();
   pdl_launch_dependents();
+  if (sch.enabled && blockIdx.x == 0 && threadIdx.x == 0) schedule_step_device(sch.p, sch.state, sch.inlier_count, sch.hyper);
   // one warp per batch row, all arrays: the 1 KB feature row moves as 2 x 16 B per lane, the small arrays as words
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1191,8 +1203,28 @@ extern "C" int acez_gather_rows(const void* src, const int64_t* idx, int rows, i
   return ACEZ_OK;
 }
 
+static int gather_multi_impl(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays, const int64_t* idx,
+                             int rows, const acez::GatherSched& sch, acez_stream_t stream);
+
 extern "C" int acez_gather_rows_multi(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
                                       const int64_t* idx, int rows, acez_stream_t stream) {
+  acez::GatherSched sch{};
+  return gather_multi_impl(srcs, dsts, row_bytes, n_arrays, idx, rows, sch, stream);
+}
+
+extern "C" int acez_gather_rows_multi_sched(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
+                                            const int64_t* idx, int rows, const acez_schedule_params* p, float* state_dev,
+                                            const float* inlier_count_dev, float* hyper_dev, acez_stream_t stream) {
+  ACEZ_REQUIRE(p && state_dev && inlier_count_dev && hyper_dev, "gather_rows_multi_sched: null schedule argument");
+  ACEZ_REQUIRE(p->kind >= ACEZ_SCHED_CONSTANT && p->kind <= ACEZ_SCHED_1CYCLEPOLY && p->batch_global > 0 && rows >= 1,
+               "gather_rows_multi_sched: bad schedule parameters");
+  acez::GatherSched sch{};
+  sch.enabled = 1; sch.p = *p; sch.state = state_dev; sch.inlier_count = inlier_count_dev; sch.hyper = hyper_dev;
+  return gather_multi_impl(srcs, dsts, row_bytes, n_arrays, idx, rows, sch, stream);
+}
+
+static int gather_multi_impl(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays, const int64_t* idx,
+                             int rows, const acez::GatherSched& sch, acez_stream_t stream) {
   ACEZ_REQUIRE(srcs && dsts && row_bytes && idx && n_arrays >= 1 && n_arrays <= 8 && rows >= 0,
                "gather_rows_multi: bad arguments");
   MultiGather g{};
@@ -1208,7 +1240,7 @@ extern "C" int acez_gather_rows_multi(const void* const* srcs, void* const* dsts
   const int threads = 256;
   dim3 grid((rows * 32 + threads - 1) / threads);
   return launch_pdl(gather_rows_multi_kernel, grid, dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), false, g, idx, rows,
-                    n_arrays);
+                    n_arrays, sch);
 }
 
 extern "C" int acez_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,

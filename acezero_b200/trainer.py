@@ -246,12 +246,22 @@ class TrainLoop:
         self.buffer = {k: buffer[k].contiguous() for k in BUFFER_KEYS}
         self.buffer_size = self.buffer["features"].shape[0]
 
-    def _gather(self, stream=None):
+    def _gather(self, stream=None, with_schedule=False):
+        """Batch rows of all 8 buffer arrays in one launch; with_schedule: the device-side schedule step rides in its first
+        block (then the iteration needs no separate schedule kernel)."""
         keys = list(BUFFER_KEYS)
         n = len(keys)
         srcs = (C.c_void_p * n)(*[self.buffer[k].data_ptr() for k in keys])
         dsts = (C.c_void_p * n)(*([self.head.input_buffer(self.b).data_ptr()] + [self.batch[k].data_ptr() for k in keys[1:]]))
         rbs = (C.c_int * n)(*[ROW_BYTES[k] for k in keys])
+        if with_schedule:
+            h = self.head
+            src = h.stats.data_ptr() + 4 if self.world == 1 else h.grads_full.data_ptr() + 4 * (h.n_params + 2)
+            rc = self.lib.acez_gather_rows_multi_sched(srcs, dsts, rbs, n, _lib.ptr(self.idx_dev), self.b, C.byref(self._sp),
+                                                       _lib.ptr(self.sched_state), C.c_void_p(src), _lib.ptr(h.hyper),
+                                                       _lib.stream_ptr(stream))
+            _lib.check(rc, "acez_gather_rows_multi_sched")
+            return
         rc = self.lib.acez_gather_rows_multi(srcs, dsts, rbs, n, _lib.ptr(self.idx_dev), self.b, _lib.stream_ptr(stream))
         _lib.check(rc, "acez_gather_rows_multi")
 
@@ -263,9 +273,10 @@ class TrainLoop:
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
                            o.depth_target, 1.0)
         if part in ("all", "fwd_bwd"):
-            self._enqueue_schedule()
             if gather:
-                self._gather()
+                self._gather(with_schedule=True)
+            else:
+                self._enqueue_schedule()
         bt = self.batch
         # data parallel: the fp16-overflow check must see the SUMMED gradient (a per-rank partial can pass while the sum
         # overflows), so the optimiser runs its own check pass; single GPU: the backward kernels' folded check is complete
@@ -354,8 +365,7 @@ class TrainLoop:
         per-image poses and the refined intrinsics are PyTorch-autograd values; the fused kernel consumes the composed
         P = A * T and K' and returns dL/dP, dL/dK00, dL/dK11, which are pushed back through autograd."""
         o, h, bt = self.o, self.head, self.batch
-        self._enqueue_schedule()
-        self._gather()
+        self._gather(with_schedule=True)
         lp = h.loss_params(o.repro_loss_type, 0.0, self.b_global, self.use_depth, o.depth_min, o.depth_max,
                            float(o.repro_loss_hard_clamp), float(o.learning_rate_cooldown_trigger_px_threshold),
                            o.depth_target, 1.0)

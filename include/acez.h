@@ -272,6 +272,11 @@ typedef struct acez_schedule_params {
 int acez_schedule_init(const acez_schedule_params* p, float* state_dev, acez_stream_t stream);
 int acez_schedule_step(const acez_schedule_params* p, float* state_dev, const float* inlier_count_dev, float* hyper_dev,
                        acez_stream_t stream);
+/* acez_gather_rows_multi with the schedule step riding in its first block: the first kernel of a training iteration then does
+ * both (one launch less in the iteration's graph). */
+int acez_gather_rows_multi_sched(const void* const* srcs, void* const* dsts, const int* row_bytes, int n_arrays,
+                                 const int64_t* idx, int rows, const acez_schedule_params* p, float* state_dev,
+                                 const float* inlier_count_dev, float* hyper_dev, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * DSAC* pose solver. Replaces the reference's native operator:
