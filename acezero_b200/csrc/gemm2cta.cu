@@ -75,14 +75,17 @@ __device__ __forceinline__ void t2_umma_f16(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 // arrive (once all prior UMMAs retire) on the barrier of this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void t2_commit_both(uint64_t* bar) {
-  const uint16_t mask = 0x3;
+__device__ __forceinline__ void t2_commit_both(uint64_t* bar, uint16_t mask = 0x3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(mask)
                : "memory");
 }
 
-template <bool A_MN, bool B_MN, int T2_BN>
+// C4 = false: one CTA pair per 256 x BN tile (cluster of 2). C4 = true: cluster of FOUR CTAs = two pairs on the same tile, each
+// contracting half of the k-blocks into its own TMEM (split-K 2); pair B then ships its accumulator to pair A through
+// distributed shared memory (bulk copies into the drained pipeline stages) and pair A adds and stores: the reduction never
+// leaves the chip (a split-K through a global workspace cost more than it saved, round 2).
+template <bool A_MN, bool B_MN, int T2_BN, bool C4>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,17 +98,22 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOnes + 1024);
   uint64_t* empty_bar = full_bar + T2_STAGES;
   uint64_t* tmem_full_bar = empty_bar + T2_STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* part_bar = tmem_full_bar + 1;   // C4, pair A: the partner pair's accumulator has landed in this CTA's staging area
+  uint64_t* free_bar = part_bar + 1;        // C4, pair B: pair A's pipeline stages are drained, its staging area may be written
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(free_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)t2_cluster_ctarank();
+  const int crank = (int)t2_cluster_ctarank();
+  const int rank = crank & 1;               // CTA inside its pair
+  const int kpair = C4 ? (crank >> 1) : 0;  // C4: 0 = pair A (first half of K, stores), 1 = pair B (second half, ships)
   const bool leader = rank == 0;
-  const int tile = blockIdx.x >> 1;
+  const int tile = C4 ? (int)(blockIdx.x >> 2) : (int)(blockIdx.x >> 1);
+  const uint16_t pair_mask = (uint16_t)(0x3u << (2 * kpair));
   const int m0 = (tile / args.tiles_n) * (2 * T2_BM) + rank * T2_BM;  // this CTA's 128 rows
   const int n0 = (tile % args.tiles_n) * T2_BN;
   const int nb0 = n0 + rank * (T2_BN / 2);                            // this CTA's half of B
   const int z = blockIdx.z;
-  const int split = blockIdx.y, n_split = args.split_k > 1 ? args.split_k : 1;
+  const int split = kpair, n_split = C4 ? 2 : 1;
   const int kb_begin = (int)((long long)args.k_blocks * split / n_split);
   const int kb_end = (int)((long long)args.k_blocks * (split + 1) / n_split);
   const int k_blocks = args.k_blocks;
@@ -118,6 +126,8 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA warp
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(part_bar, 1);
+    mbar_init(free_bar, 1);
     fence_barrier_init();
   }
   constexpr uint32_t kTmemCols = (T2_BN + 32 <= 256) ? 256u : 512u;  // accumulator + the bias-gradient column block
@@ -171,7 +181,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
       }
       if (args.dbg) {
-        long long* d = args.dbg + 8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
         d[2] = t_wait; d[3] = clock64() - t_begin;
       }
     }
@@ -207,14 +217,14 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (do_bias) bias_started = 1u;
       __syncwarp();
       if (elect_one()) {
-        t2_commit_both(&empty_bar[stage]);
-        if (kb == kb_end - 1) t2_commit_both(tmem_full_bar);
+        t2_commit_both(&empty_bar[stage], pair_mask);
+        if (kb == kb_end - 1) t2_commit_both(tmem_full_bar, pair_mask);
       }
       __syncwarp();
       if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
     }
     if (args.dbg && lane == 0) {
-      long long* d = args.dbg + 8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+      long long* d = args.dbg + 8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x);
       d[0] = t_wait; d[1] = clock64() - t_begin;
     }
   } else if (warp >= 2) {
@@ -227,107 +237,128 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const long long t_epi = args.dbg ? clock64() : 0;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     bool bad = false;
-    // split-K: the first CTA of this (tile, half) to arrive parks its partial in the workspace, the second one adds it to its own
-    // accumulator and writes the result (+ the fp16-range check of the SUM). role: 0 = no split / write out, 1 = first, 2 = second
-    __shared__ int s_role;
-    int role = 0;
-    float* part_tile = nullptr;
-    unsigned int* sync = nullptr;
-    if (n_split > 1) {
-      const size_t unit = ((size_t)z * (gridDim.x >> 1) + tile) * 2 + rank;
-      part_tile = args.split_part + unit * (size_t)T2_BM * T2_BN;
-      sync = args.split_sync + unit * 2;
-      if (warp == 2 && lane == 0) s_role = atomicAdd(&sync[0], 1u) == 0u ? 1 : 2;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      role = s_role;
-      if (role == 2) {
-        if (warp == 2 && lane == 0) {
-          while (atomicAdd(&sync[1], 0u) == 0u) __nanosleep(64);   // the first CTA is running (it has arrived): bounded wait
-          __threadfence();
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-      }
-    }
     const int lrow = quarter * 32 + lane;   // row inside this CTA's 128-row half
+    // C4: staging area in the drained pipeline stages, [128 rows][BN floats] with a 16-byte pad per row (conflict-free
+    // 128-bit accesses by a quarter warp), followed by the 128 partial row sums of the bias column
+    constexpr uint32_t kPitch = T2_BN * 4 + 16;
+    constexpr uint32_t kStageBytes = T2_BM * kPitch + T2_BM * 4;
+    static_assert(!C4 || kStageBytes <= (uint32_t)(T2_STAGES * T2Cfg<T2_BN>::kStage), "staging area exceeds the pipeline stages");
+    const uint32_t stg = smem_u32(smem);
+    const bool my_bias = bias_col && [&] { bool anyb = false; for (int kb = kb_begin; kb < kb_end; ++kb) anyb |= (kb % args.tiles_n) == tn; return anyb; }();
+    if (C4 && kpair == 1) {
+      // ---- pair B: accumulator -> own staging -> bulk copies into the partner's staging ----
 #pragma unroll 1
-    for (int c = grp; c < T2_BN / 32; c += 2) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_row + c * 32, v);
-      tmem_ld_wait();
-      const int ncol = n0 + c * 32;
-      if (role == 1) {   // park the partial (whole tile, no bounds: the workspace is tile sized)
-        float4* dstp = reinterpret_cast<float4*>(part_tile + (size_t)lrow * T2_BN + c * 32);
+      for (int c = grp; c < T2_BN / 32; c += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dstp[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                __uint_as_float(v[4 * j + 3]));
-        continue;
+          sts_128(stg + (uint32_t)lrow * kPitch + (uint32_t)(c * 128 + j * 16), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
-      if (role == 2) {
-        const float4* srcp = reinterpret_cast<const float4*>(part_tile + (size_t)lrow * T2_BN + c * 32);
+      if (grp == 0) {
+        float g = 0.f;
+        if (my_bias) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + T2_BN, v);
+          tmem_ld_wait();
+          g = __uint_as_float(v[0]);
+        }
+        sts_f32(stg + T2_BM * kPitch + 4u * (uint32_t)lrow, g);
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy engine
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        mbar_wait(free_bar, 0);   // pair A has retired all its MMAs: its stages are free
+        const uint32_t dst_rank = (uint32_t)(crank - 2);
+        uint32_t dst, bar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(stg), "r"(dst_rank));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(smem_u32(part_bar)), "r"(dst_rank));
+        constexpr uint32_t kChunk = 32 * kPitch;   // 4 copies of 32 rows + the bias rows
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 p = __ldcg(srcp + j);
-          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + p.x);
-          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + p.y);
-          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + p.z);
-          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + p.w);
+        for (uint32_t o = 0; o < T2_BM * kPitch; o += kChunk)
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + o),
+                       "r"(stg + o), "r"(kChunk), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + T2_BM * kPitch),
+                     "r"(stg + T2_BM * kPitch), "r"((uint32_t)(T2_BM * 4)), "r"(bar) : "memory");
+      }
+    } else {
+      float bias_partner = 0.f;
+      if (C4) {
+        // ---- pair A: arm the landing barrier, tell the partner that the stages are free, wait for its accumulator ----
+        if (warp == 2 && lane == 0) {
+          mbar_arrive_expect_tx(part_bar, kStageBytes);
+          uint32_t fb;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fb) : "r"(smem_u32(free_bar)), "r"((uint32_t)(crank + 2)));
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(fb) : "memory");
+        }
+        mbar_wait(part_bar, 0);
+        if (grp == 0) {
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(stg + T2_BM * kPitch + 4u * (uint32_t)lrow) : "memory");
+          bias_partner = t;
         }
       }
-      if (row >= args.M || ncol >= args.N) continue;
-      // 256-bit stores: one full 32-byte sector per lane and instruction (with 16-byte stores every warp store touched 32
-      // half-written sectors and the epilogue ran at the L1 -> L2 request rate: 8.8 k cycles for a 128 x 256 tile, round 2)
-      float* dst = args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol;
-      if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+#pragma unroll 1
+      for (int c = grp; c < T2_BN / 32; c += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (C4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(v[8 * j]), "r"(v[8 * j + 1]),
-                       "r"(v[8 * j + 2]), "r"(v[8 * j + 3]), "r"(v[8 * j + 4]), "r"(v[8 * j + 5]), "r"(v[8 * j + 6]), "r"(v[8 * j + 7])
-                       : "memory");
-      } else {
+          for (int j = 0; j < 8; ++j) {
+            const float4 pq = lds_128f(stg + (uint32_t)lrow * kPitch + (uint32_t)(c * 128 + j * 16));
+            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + pq.x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + pq.y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + pq.z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + pq.w);
+          }
+        }
+        const int ncol = n0 + c * 32;
+        if (row >= args.M || ncol >= args.N) continue;
+        // 256-bit stores: one full 32-byte sector per lane and instruction (with 16-byte stores every warp store touched 32
+        // half-written sectors and the epilogue ran at the L1 -> L2 request rate: 8.8 k cycles for a 128 x 256 tile, round 2)
+        float* dst = args.out32 + (long long)z * args.out32_zstride + (long long)row * args.ldo32 + ncol;
+        if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-      }
-      if (args.nonfinite != nullptr) {
-        // GradScaler check folded in: autocast materialises weight gradients in fp16, so |g| > 65504 is an overflow
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "r"(v[8 * j]), "r"(v[8 * j + 1]),
+                         "r"(v[8 * j + 2]), "r"(v[8 * j + 3]), "r"(v[8 * j + 4]), "r"(v[8 * j + 5]), "r"(v[8 * j + 6]), "r"(v[8 * j + 7])
+                         : "memory");
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float g = __uint_as_float(v[j]);
-          bad |= !isfinite(g) || fabsf(g) > 65504.f;
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        if (args.nonfinite != nullptr) {
+          // GradScaler check folded in: autocast materialises weight gradients in fp16, so |g| > 65504 is an overflow
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float g = __uint_as_float(v[j]);
+            bad |= !isfinite(g) || fabsf(g) > 65504.f;
+          }
         }
       }
-    }
-    if (role == 1) {      // publish the parked partial
-      __threadfence();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) atomicExch(&sync[1], 1u);
-    } else if (role == 2) {   // consumed: reset for the next launch
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) { sync[0] = 0u; sync[1] = 0u; }
-    }
     if (bias_col && grp == 0) {
       __shared__ int s_last;
-      const int tiles_m = (int)(gridDim.x >> 1) / args.tiles_n;
+      const int tiles_m = (int)(gridDim.x >> (C4 ? 2 : 1)) / args.tiles_n;
       const int r_in_tile = rank * T2_BM + quarter * 32 + lane;            // 0..255 inside the pair's M-tile
-      const int slots = args.tiles_n * n_split;                            // partial row sums per M-tile: one per (column tile, split)
+      const int slots = args.tiles_n;                                      // partial row sums per M-tile: one per column tile
       float* part = args.bias_part + ((size_t)(z * tiles_m + tm) * slots) * (2 * T2_BM);
-      float g = 0.f;
-      bool any_bias = false;
-      for (int kb = kb_begin; kb < kb_end; ++kb) any_bias |= (kb % args.tiles_n) == tn;
-      if (any_bias) {   // this CTA pair issued bias UMMAs
+      float g = bias_partner;
+      if (my_bias) {   // this CTA pair issued bias UMMAs
         uint32_t v[32];
         tmem_ld_32x32(t_row + T2_BN, v);  // columns BN..BN+15 hold the partial row sum (all equal); 32 columns are allocated
         tmem_ld_wait();
-        g = __uint_as_float(v[0]);
+        g += __uint_as_float(v[0]);
       }
-      part[(size_t)(tn * n_split + split) * (2 * T2_BM) + r_in_tile] = g;
+      part[(size_t)tn * (2 * T2_BM) + r_in_tile] = g;
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (quarter == 0 && lane == 0) {
         const unsigned int done = atomicAdd(args.bias_count + z * tiles_m + tm, 1u);
-        s_last = (done == 2u * (unsigned int)slots - 1u) ? 1 : 0;   // both CTAs of all (column tile, split) pairs have stored
+        s_last = (done == 2u * (unsigned int)slots - 1u) ? 1 : 0;   // both CTAs of all column tiles have stored
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (s_last) {
@@ -347,10 +378,11 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (t128 == 0) args.bias_count[z * tiles_m + tm] = 0u;   // ready for the next launch
       }
     }
+    }   // pair A / plain pair
     if (args.nonfinite != nullptr) {
       if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(args.nonfinite, 1);
     }
-    if (args.dbg && warp == 2 && lane == 0) args.dbg[8 * (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 4] = clock64() - t_epi;
+    if (args.dbg && warp == 2 && lane == 0) args.dbg[8 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x) + 4] = clock64() - t_epi;
   }
 
   __syncwarp();
@@ -379,9 +411,9 @@ static int encode2(CUtensorMap* tm, const __half* base, int mn_major, int rows_m
   return make_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <bool A_MN, bool B_MN, int BN>
+template <bool A_MN, bool B_MN, int BN, bool C4>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Args& a, int batch, cudaStream_t stream, bool pdl) {
-  auto kern = gemm2cta_kernel<A_MN, B_MN, BN>;
+  auto kern = gemm2cta_kernel<A_MN, B_MN, BN, C4>;
   constexpr int T2_SMEM = T2Cfg<BN>::kSmem;
   static bool configured = false;
   if (!configured) {
@@ -390,13 +422,13 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Ar
   }
   const int tiles_m = (a.M + 2 * T2_BM - 1) / (2 * T2_BM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * tiles_m * a.tiles_n, a.split_k > 1 ? a.split_k : 1, batch);
+  cfg.gridDim = dim3((C4 ? 4 : 2) * tiles_m * a.tiles_n, 1, batch);
   cfg.blockDim = dim3(T2_THREADS);
   cfg.dynamicSmemBytes = T2_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = C4 ? 4 : 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -410,12 +442,18 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm2Ar
 int gemm2_launch(const Gemm2Launch& L, cudaStream_t s, bool pdl) {
   ACEZ_REQUIRE(L.a_mn == L.b_mn, "gemm2cta: operands must both be K-major or both MN-major");
   ACEZ_REQUIRE(L.bn == 128 || L.bn == 256, "gemm2cta: bn must be 128 or 256");
+  const bool c4 = L.args.split_k == 2;   // on-chip split-K 2: cluster of four (two pairs per tile)
+  ACEZ_REQUIRE(!c4 || (L.bn == 256 && L.args.k_blocks >= 2), "gemm2cta: split-K 2 is built for 256-column tiles");
   if (L.bn == 128) {
-    if (L.a_mn) return launch2<true, true, 128>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
-    return launch2<false, false, 128>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+    if (L.a_mn) return launch2<true, true, 128, false>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+    return launch2<false, false, 128, false>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
   }
-  if (L.a_mn) return launch2<true, true, 256>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
-  return launch2<false, false, 256>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+  if (c4) {
+    if (L.a_mn) return launch2<true, true, 256, true>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+    return launch2<false, false, 256, true>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+  }
+  if (L.a_mn) return launch2<true, true, 256, false>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
+  return launch2<false, false, 256, false>(L.tmA, L.tmB, L.args, L.batch, s, pdl);
 }
 
 }  // namespace acez
@@ -457,7 +495,7 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
     static unsigned int* g_count = nullptr;
     static size_t g_cap = 0;
     const int tiles_m = (d->M + 2 * T2_BM - 1) / (2 * T2_BM);
-    const size_t need = (size_t)L.batch * tiles_m * a.tiles_n * 2 /*split-K slots*/ * 2 * T2_BM;
+    const size_t need = (size_t)L.batch * tiles_m * a.tiles_n * 2 * T2_BM;
     if (need > g_cap) {
       if (g_part) cudaFree(g_part);
       ACEZ_CUDA(cudaMalloc(&g_part, need * sizeof(float)));
@@ -474,31 +512,8 @@ extern "C" int acez_gemm2cta_f16(const acez_gemm_desc* d, acez_stream_t stream) 
   {
     // probe entry: ACEZ_GEMM2_SPLITK=2 contracts each tile in two halves (two CTAs per tile and half)
     static const int want_split = [] { const char* e = getenv("ACEZ_GEMM2_SPLITK"); return e != nullptr ? atoi(e) : 1; }();
-    a.split_k = (want_split == 2 && a.k_blocks >= 2) ? 2 : 1;
-    if (a.split_k == 2) {
-      static float* g_split = nullptr;
-      static unsigned int* g_sync = nullptr;
-      static size_t g_cap2 = 0;
-      const int tiles_m = (d->M + 2 * T2_BM - 1) / (2 * T2_BM);
-      const size_t units = (size_t)L.batch * tiles_m * a.tiles_n * 2;
-      const size_t need = units * T2_BM * (size_t)L.bn;
-      if (need > g_cap2) {
-        if (g_split) cudaFree(g_split);
-        ACEZ_CUDA(cudaMalloc(&g_split, need * sizeof(float)));
-        g_cap2 = need;
-      }
-      if (g_sync == nullptr) {
-        ACEZ_CUDA(cudaMalloc(&g_sync, 8192 * sizeof(unsigned int)));
-        ACEZ_CUDA(cudaMemset(g_sync, 0, 8192 * sizeof(unsigned int)));
-      }
-      ACEZ_REQUIRE(units * 2 <= 8192, "gemm2cta: too many tiles for the probe's split-K counters");
-      a.split_part = g_split;
-      a.split_sync = g_sync;
-    }
+    a.split_k = (want_split == 2 && a.k_blocks >= 2 && L.bn == 256) ? 2 : 1;
   }
-  a.nonfinite = d->nonfinite;
-  a.a_lbo = d->a_mn_major ? 8192 : 0; a.a_sbo = 1024; a.a_kstep = d->a_mn_major ? 2048 : 32;
-  a.b_lbo = d->b_mn_major ? 8192 : 0; a.b_sbo = 1024; a.b_kstep = d->b_mn_major ? 2048 : 32;
   {
     static const bool want = [] { const char* e = getenv("ACEZ_GEMM2_DBG"); return e != nullptr && atoi(e) != 0; }();
     static long long* g_dbg = nullptr;

@@ -16,10 +16,8 @@ struct Gemm2Args {
   unsigned int* bias_count;  // with bias_grad: [z][tiles_m] self-resetting arrival counters (zero before the first launch)
   int* nonfinite;        // nullable: OR-ed with 1 if a stored value is non-finite or exceeds the fp16 range
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
-  int split_k;           // 1 or 2: grid.y = split; each split contracts half of the k-blocks, the second CTA of a tile to arrive
-                         // adds the first one's partial (a + b == b + a: the result does not depend on the arrival order)
-  float* split_part;     // split_k == 2: workspace [batch][tiles][2 CTAs][128][bn] floats
-  unsigned int* split_sync;  // split_k == 2: [batch][tiles][2 CTAs][2] = {arrival counter, partial-ready flag}, zero before the first launch
+  int split_k;           // 1, or 2 (256-column tiles only): a cluster of four CTAs = two pairs per tile, each contracting half of the
+                         // k-blocks; the second pair's accumulator travels to the first through distributed shared memory
   long long* dbg;        // nullable (ACEZ_GEMM2_DBG=1): per CTA [0] MMA-warp cycles waiting for operands, [1] MMA loop cycles,
                          // [2] producer cycles waiting for free stages, [3] producer loop cycles, [4] epilogue cycles
 };

@@ -47,7 +47,6 @@ struct acez_head_plan {
   float* G3;
   float* FC3PART;
   float* WBIAS;
-  float* WSPLIT;
   float* BLKPART;
   unsigned int* BLKCOUNT;
   bool counters_zeroed;
@@ -73,7 +72,7 @@ struct acez_head_plan {
 namespace acez {
 
 struct HeadLayout {
-  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, wbias, wsplit, blkpart, total;
+  size_t w16, w3h, act, xtra, dz, gres, maskb, g3, fc3part, wbias, blkpart, total;
 };
 
 static HeadLayout head_layout(const acez_head_config& cfg) {
@@ -93,7 +92,6 @@ static HeadLayout head_layout(const acez_head_config& cfg) {
     o.g3 = off; off = align_up(off + rows * 4 * sizeof(float), 1024);
     o.fc3part = off; off = align_up(off + ((rows + 31) / 32) * (size_t)(4 * kC + 4) * sizeof(float), 1024);
     o.wbias = off; off = align_up(off + (size_t)L * 2 * 4 * 256 * sizeof(float), 1024);  // wgrad bias partials [L][2][<=4][256]
-    o.wsplit = off; off = align_up(off + (size_t)L * 8 * 128 * 256 * sizeof(float), 1024);  // split-K partial tiles [L][4 tiles][2][128][256]
   }
   o.blkpart = off; off = align_up(off + 4096 * 8 * sizeof(float) + 4096, 1024);  // tail per-block partials + 1024 counters
   o.total = off;
@@ -753,9 +751,9 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       W.batch = L;
       W.a_mn = W.b_mn = 1;
       {
-        // 256 x 128 tiles per SM pair: 64 pairs = 128 CTAs, no split-K (default). ACEZ_WGRAD_2CTA_BN=256: 256 x 256 tiles with
-        // split-K 2 (also 128 CTAs; the tensor pipe runs at 87 % instead of 50 % per CTA, round-2 cycle counters, but the
-        // two-arriver reduction of 128 KB partial tiles costs more than it saves: 182.9 vs 177.8 us per iteration)
+        // 256 x 128 tiles per SM pair: 64 pairs = 128 CTAs, no split-K (default). ACEZ_WGRAD_2CTA_BN=256: 256 x 256 tiles with an
+        // on-chip split-K 2 (cluster of four = two pairs per tile, also 128 CTAs; the tensor pipe runs at 87 % instead of 50 %
+        // per CTA, round-2 cycle counters; the second pair's accumulator travels through distributed shared memory)
         const char* e = getenv("ACEZ_WGRAD_2CTA_BN");
         W.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;
       }
@@ -766,9 +764,7 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       g.bias_grad = h->grads + (size_t)kC * kC; g.bias_grad_zstride = (long long)kLayerStride;
       g.bias_part = h->WBIAS;
       g.bias_count = h->BLKCOUNT + 8;   // [L][2] arrival counters behind the tail's; zeroed once with it (launch_tail)
-      g.split_k = (W.bn == 256 && g.k_blocks >= 2) ? 2 : 1;
-      g.split_part = h->WSPLIT;
-      g.split_sync = h->BLKCOUNT + 64;  // [L][2 x 2 tiles][2 CTAs][2]
+      g.split_k = (W.bn == 256 && g.k_blocks >= 2) ? 2 : 1;   // on-chip split-K 2 (cluster of four)
       g.a_lbo = 8192; g.a_sbo = 1024; g.a_kstep = 2048;
       g.b_lbo = 8192; g.b_sbo = 1024; g.b_kstep = 2048;
     }
@@ -1028,7 +1024,6 @@ extern "C" int acez_head_plan_create(const acez_head_config* cfg, float* params,
   h->G3 = cfg->training ? reinterpret_cast<float*>(base + lo.g3) : nullptr;
   h->FC3PART = cfg->training ? reinterpret_cast<float*>(base + lo.fc3part) : nullptr;
   h->WBIAS = cfg->training ? reinterpret_cast<float*>(base + lo.wbias) : nullptr;
-  h->WSPLIT = cfg->training ? reinterpret_cast<float*>(base + lo.wsplit) : nullptr;
   h->BLKPART = reinterpret_cast<float*>(base + lo.blkpart);
   h->BLKCOUNT = reinterpret_cast<unsigned int*>(base + lo.blkpart + 4096 * 8 * sizeof(float));
   h->counters_zeroed = false;

@@ -45,9 +45,8 @@ def test_head_param_count_and_workspace(lib):
     ws = lib.acez_head_workspace_bytes(C.byref(cfg))
     act = (9 + 2 + 8 + 1) * 5120 * 512 * 2 + 9 * 5120 * 64   # ACT[L+1], XTRA[nres], DZ[L], GRES; MASKB[L+1] (bits)
     # + fp16 weight shadow + fc3 output-gradient rows + fc3 slab partials (160 x 2052 floats) + bias-gradient partials of the
-    # 2-CTA weight-gradient GEMM (8 layers x 2 x 4 x 256 floats) and its split-K partial tiles (8 x 8 x 128 x 256 floats) + tail
-    # block partials
-    assert act < ws < act + 8 * 512 * 512 * 2 + 5120 * 16 + 160 * 2052 * 4 + 8 * 2 * 4 * 256 * 4 + 8 * 8 * 128 * 256 * 4 + 4096 * 32 + 64 * 1024
+    # 2-CTA weight-gradient GEMM (8 layers x 2 x 4 x 256 floats) + tail block partials
+    assert act < ws < act + 8 * 512 * 512 * 2 + 5120 * 16 + 160 * 2052 * 4 + 8 * 2 * 4 * 256 * 4 + 4096 * 32 + 64 * 1024
     cfg.num_res_blocks = 0
     assert lib.acez_head_param_count(C.byref(cfg)) == 0
 
