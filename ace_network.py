@@ -149,8 +149,10 @@ class Head(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self._params()) + (self.mean.data_ptr(), self.mean._version) + \
             tuple((b.data_ptr(), b._version) for b in self._homogeneous_buffers())
 
-    def engine(self, training=False, max_rows=5120):
-        """HeadEngine holding a copy of the current weights (rebuilt / reloaded when the module's tensors change)."""
+    def engine(self, training=False, max_rows=5120, peer_group=None):
+        """HeadEngine holding a copy of the current weights (rebuilt / reloaded when the module's tensors change).
+        peer_group: torch.distributed group of the GPUs of this box -> parameters / gradient / workspace in symmetric memory
+        (data-parallel optimiser over NVLink peer memory, acezero_b200/csrc/adamw_dp.cu)."""
         from acezero_b200.head import HeadEngine
         dev = self.mean.device
         if dev.type != "cuda":
@@ -162,7 +164,7 @@ class Head(nn.Module):
             # (ace_network.py:139-144) — for an fp16 head file these are the fp16-rounded values stored in it
             kw = dict(h_beta=hom[0], max_inv_scale=hom[1], min_inv_scale=hom[2]) if hom else {}
             self._engine = HeadEngine(self.num_head_blocks, self.use_homogeneous, self.mean.reshape(3).cpu(),
-                                      max_rows=max_rows, training=training, device=dev, **kw)
+                                      max_rows=max_rows, training=training, device=dev, peer_group=peer_group, **kw)
             self._engine_version = None
         v = self._weights_version()
         if v != self._engine_version:

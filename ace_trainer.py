@@ -143,7 +143,7 @@ class TrainerACE:
         self.log_file = open(base_file_name + '.txt', 'w') if self.rank == 0 else None
 
         self.pose_refiner.create_pose_buffer()            # reference :231 (after the buffer: same RNG order)
-        head = self.regressor.heads.engine(training=True, max_rows=self.options.batch_size)
+        head = self._training_engine()
         self.loop = TrainLoop(head, self.options, self.training_buffer, use_depth=self.use_depth,
                               pose_refiner=self.pose_refiner, K_optimizer=self.K_optimizer, rank=self.rank,
                               world_size=self.world)
@@ -151,6 +151,7 @@ class TrainerACE:
         while self.loop.run_epoch(on_iteration=self._log_iteration):
             pass
         self.loop.finish()            # device schedule -> host: the final iteration count (cool-down may have shortened it)
+        head.gather_params_from_shards()   # peer-memory data parallel: fp32 master weights live on their owner rank
         torch.cuda.synchronize()
         training_time = time.time() - t0
         self.iteration, self.epoch = self.loop.iteration, self.loop.epoch
@@ -165,6 +166,23 @@ class TrainerACE:
         _logger.info(f'Done without errors. Creating buffer time: {creating_buffer_time:.1f} seconds. '
                      f'Training time: {training_time:.1f} seconds. '
                      f'Total time: {time.time() - self.training_start:.1f} seconds.')
+
+    def _training_engine(self):
+        """The head engine of this rank. Data parallel: parameters / gradient / workspace in symmetric memory, so that the
+        optimiser step runs over NVLink peer memory (csrc/adamw_dp.cu); ACEZ_DP_PEERS=0 or a failing rendezvous (no peer access
+        between the GPUs) selects the NCCL all-reduce path."""
+        heads = self.regressor.heads
+        refining = self.pose_refiner.active or self.K_optimizer is not None
+        if self.world > 1 and not refining and os.environ.get("ACEZ_DP_PEERS", "1") != "0":
+            import torch.distributed as dist
+            try:
+                head = heads.engine(training=True, max_rows=self.options.batch_size, peer_group=dist.group.WORLD)
+                head.setup_peers()
+                return head
+            except Exception as e:  # noqa: BLE001
+                _logger.warning(f"peer-memory data parallel unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path")
+                heads._engine = None
+        return heads.engine(training=True, max_rows=self.options.batch_size)
 
     def _log_iteration(self, loop):
         """reference ace_trainer.py:642-673 (pose statistics are zero without pose refinement)."""

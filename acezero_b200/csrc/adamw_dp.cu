@@ -1,0 +1,238 @@
+// Data-parallel optimiser step over NVLink peer memory: the gradient all-reduce, GradScaler check, AdamW and the broadcast of
+// the new fp16 weights as TWO kernels that read / write the other GPUs' buffers directly (symmetric-memory peer pointers),
+// instead of an NCCL all-reduce of the full 8.4 MB gradient followed by a replicated AdamW over all 2.1 M parameters
+// (reference: ace_schedule.py:106-113 on one GPU; SURVEY.md section 8e for the sharding).
+//
+//   rank r owns the parameter shard [r S, (r+1) S), S = ceil(n / G / 8) * 8:
+//   kernel 1 (reduce)  g_sum[i] = sum_q grads_q[i] for i in the shard, peers read in rank order 0..G-1 (every rank computes the
+//                      sum of ITS shard exactly once, so all GPUs later see bit-identical weights); fp16-range / inf check of the
+//                      summed shard -> this rank's flag, stored into EVERY rank's flag array (remote 4-byte stores); the 4 spare
+//                      slots behind the gradient (GradScaler flag of the ranks' local backward passes, loss / inlier / valid
+//                      sums) are summed by every rank for itself
+//   -- cross-GPU barrier (torch symmetric-memory barrier kernel) --
+//   kernel 2 (apply)   found = any rank's shard flag | non-finite flag slot; unless found: unscale, AdamW on the shard's fp32
+//                      master weights / moments (local), new weights rounded to fp16 and stored into EVERY rank's fp16 shadow
+//                      (the operand the forward / dgrad GEMMs read), the biases (read in fp32) into every rank's parameter
+//                      buffer; GradScaler.update() on every rank (same inputs, same state)
+//   -- cross-GPU barrier --
+// Traffic per GPU and iteration: (G-1)/G * 8.4 MB of gradient reads + (G-1)/G * 4.2 MB of weight writes over NVLink, AdamW
+// state traffic 1/G of the single-GPU kernel. fp32 master weights are valid on their owner only (gathered when exported).
+#include "common.cuh"
+
+namespace acez {
+
+static constexpr int kC = 512;
+static constexpr size_t kLayerStride = (size_t)kC * kC + kC;
+static constexpr int kMaxRanks = 8;
+
+struct DpPeers {
+  const float* grads[kMaxRanks];   // every rank's flat gradient (+4 spare floats)
+  int* flags[kMaxRanks];           // every rank's flag array [world]
+  __half* w16[kMaxRanks];          // every rank's fp16 hidden-layer weights [L][512][512]
+  __half* w3h[kMaxRanks];          // every rank's fp16 fc3 weights [4][512]
+  float* params[kMaxRanks];        // every rank's fp32 parameters: the BIASES are read in fp32 by the kernels, so they travel too
+};
+
+__global__ void adamw_dp_reduce_kernel(const DpPeers P, int world, int rank, size_t n, size_t shard, float* __restrict__ reduced,
+                                       float* __restrict__ local_extras /* = local grads + n: receives the 4 summed spare slots */) {
+  pdl_wait();
+  const size_t lo = (size_t)rank * shard;
+  const size_t hi = lo + shard < n ? lo + shard : n;
+  bool bad = false;
+  const size_t n4 = hi > lo ? (hi - lo) / 4 : 0;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {   // fixed order: the sum does not depend on who computes it
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(P.grads[r] + lo) + q);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    reinterpret_cast<float4*>(reduced)[q] = s;
+    // under autocast the weight gradient is materialised in fp16: |g| > 65504 overflows to inf there
+    bad |= !isfinite(s.x) || fabsf(s.x) > 65504.f || !isfinite(s.y) || fabsf(s.y) > 65504.f;
+    bad |= !isfinite(s.z) || fabsf(s.z) > 65504.f || !isfinite(s.w) || fabsf(s.w) > 65504.f;
+  }
+  for (size_t i = lo + 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) s += __ldcg(P.grads[r] + i);
+    reduced[i - lo] = s;
+    bad |= !isfinite(s) || fabsf(s) > 65504.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4) {   // the spare slots: every rank for itself (all ranks get the same sums)
+    float s = 0.f;
+    for (int r = 0; r < world; ++r) s += __ldcg(P.grads[r] + n + threadIdx.x);
+    reduced[shard + threadIdx.x] = s;         // kept next to the shard until the apply kernel copies them home (the peers may
+  }                                           // still be reading this rank's gradient buffer)
+  (void)local_extras;
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) {
+    for (int r = 0; r < world; ++r) *reinterpret_cast<volatile int*>(P.flags[r] + rank) = 1;   // remote stores: every rank learns this shard's verdict
+  }
+}
+
+__global__ void adamw_dp_apply_kernel(const DpPeers P, int world, int rank, size_t n, size_t shard, const float* __restrict__ reduced,
+                                      float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                      const float* __restrict__ hyper, float* __restrict__ scaler_state, int* __restrict__ my_flags,
+                                      int* __restrict__ found_inf_out, float* __restrict__ local_extras, int L, int C3) {
+  pdl_wait();
+  int found = 0;
+  for (int r = 0; r < world; ++r) found |= my_flags[r];
+  const float flag_slot = reduced[shard];    // sum of the ranks' +inf markers (local backward overflow)
+  if (!isfinite(flag_slot) || flag_slot != 0.f) found = 1;
+  const size_t lo = (size_t)rank * shard;
+  const size_t hi = lo + shard < n ? lo + shard : n;
+  if (!found) {
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+    const float inv_scale = 1.f / scaler_state[0];
+    const float t = scaler_state[2] + 1.f;
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1;
+    const float bc2_sqrt = sqrtf(bc2);
+    const size_t wsz = (size_t)kC * kC;
+    auto update = [&](float gi, float& pi, float& mi, float& vi) {
+      gi = __half2float(__float2half_rn(gi)) * inv_scale;   // fp16 weight gradient of the autocast conv, GradScaler.unscale_
+      pi *= (1.f - lr * wd);
+      mi = mi + (1.f - b1) * (gi - mi);
+      vi = b2 * vi + (1.f - b2) * gi * gi;
+      pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    };
+    // groups of 8 consecutive parameters (shard bounds, layer strides and the weight / bias boundaries are multiples of 8): the
+    // fp16 shadow travels to every rank as ONE 16-byte store per group and peer
+    const size_t n8 = hi > lo ? (hi - lo) / 8 : 0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (size_t)gridDim.x * blockDim.x) {
+      const size_t i = lo + 8 * q;
+      float g8[8], p8[8], m8[8], v8[8];
+      *reinterpret_cast<float4*>(g8) = reinterpret_cast<const float4*>(reduced)[2 * q];
+      *reinterpret_cast<float4*>(g8 + 4) = reinterpret_cast<const float4*>(reduced)[2 * q + 1];
+      *reinterpret_cast<float4*>(p8) = *reinterpret_cast<const float4*>(p + i);
+      *reinterpret_cast<float4*>(p8 + 4) = *reinterpret_cast<const float4*>(p + i + 4);
+      *reinterpret_cast<float4*>(m8) = *reinterpret_cast<const float4*>(m + i);
+      *reinterpret_cast<float4*>(m8 + 4) = *reinterpret_cast<const float4*>(m + i + 4);
+      *reinterpret_cast<float4*>(v8) = *reinterpret_cast<const float4*>(v + i);
+      *reinterpret_cast<float4*>(v8 + 4) = *reinterpret_cast<const float4*>(v + i + 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) update(g8[k], p8[k], m8[k], v8[k]);
+      *reinterpret_cast<float4*>(p + i) = *reinterpret_cast<float4*>(p8);
+      *reinterpret_cast<float4*>(p + i + 4) = *reinterpret_cast<float4*>(p8 + 4);
+      *reinterpret_cast<float4*>(m + i) = *reinterpret_cast<float4*>(m8);
+      *reinterpret_cast<float4*>(m + i + 4) = *reinterpret_cast<float4*>(m8 + 4);
+      *reinterpret_cast<float4*>(v + i) = *reinterpret_cast<float4*>(v8);
+      *reinterpret_cast<float4*>(v + i + 4) = *reinterpret_cast<float4*>(v8 + 4);
+      uint4 pk;
+      __half2 h0 = __floats2half2_rn(p8[0], p8[1]), h1 = __floats2half2_rn(p8[2], p8[3]);
+      __half2 h2 = __floats2half2_rn(p8[4], p8[5]), h3 = __floats2half2_rn(p8[6], p8[7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      const size_t l = i / kLayerStride, r = i % kLayerStride;
+      if (l < (size_t)L) {
+        if (r < wsz) {
+          for (int qq = 0; qq < world; ++qq) *reinterpret_cast<uint4*>(P.w16[qq] + l * wsz + r) = pk;
+        } else {   // a bias group: the fp32 values go to every rank's parameter buffer (the kernels read biases in fp32)
+          for (int qq = 0; qq < world; ++qq) {
+            if (qq == rank) continue;
+            *reinterpret_cast<float4*>(P.params[qq] + i) = *reinterpret_cast<float4*>(p8);
+            *reinterpret_cast<float4*>(P.params[qq] + i + 4) = *reinterpret_cast<float4*>(p8 + 4);
+          }
+        }
+      } else if (r + 8 <= (size_t)C3 * kC) {
+        for (int qq = 0; qq < world; ++qq) *reinterpret_cast<uint4*>(P.w3h[qq] + r) = pk;
+      } else {
+        for (int k = 0; k < 8; ++k) {
+          if (r + k < (size_t)C3 * kC) { for (int qq = 0; qq < world; ++qq) P.w3h[qq][r + k] = __float2half_rn(p8[k]); }
+          else if (i + k < n) { for (int qq = 0; qq < world; ++qq) if (qq != rank) P.params[qq][i + k] = p8[k]; }   // fc3 bias
+        }
+      }
+    }
+    for (size_t i = lo + 8 * n8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      update(reduced[i - lo], pi, mi, vi);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      const size_t l = i / kLayerStride, r = i % kLayerStride;
+      const __half hv = __float2half_rn(pi);
+      if (l < (size_t)L) {
+        if (r < wsz) { for (int qq = 0; qq < world; ++qq) P.w16[qq][l * wsz + r] = hv; }
+        else { for (int qq = 0; qq < world; ++qq) if (qq != rank) P.params[qq][i] = pi; }
+      } else if (r < (size_t)C3 * kC) {
+        for (int qq = 0; qq < world; ++qq) P.w3h[qq][r] = hv;
+      } else {
+        for (int qq = 0; qq < world; ++qq) if (qq != rank) P.params[qq][i] = pi;   // fc3 bias
+      }
+    }
+  }
+  // bookkeeping by one thread: summed spare slots home (statistics / schedule read them there), flags cleared for the next
+  // iteration, GradScaler.update()
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) local_extras[k] = reduced[shard + k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(scaler_state + 3);
+    if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+      if (found) { scaler_state[0] *= 0.5f; scaler_state[1] = 0.f; }
+      else {
+        scaler_state[2] += 1.f;
+        scaler_state[1] += 1.f;
+        if (scaler_state[1] >= 2000.f) { scaler_state[0] *= 2.f; scaler_state[1] = 0.f; }
+      }
+      *found_inf_out = found;
+      for (int r = 0; r < world; ++r) my_flags[r] = 0;   // every block has read them (this is the last block to get here)
+      *cnt = 0u;
+    }
+  }
+}
+
+}  // namespace acez
+
+using namespace acez;
+
+extern "C" size_t acez_adamw_dp_shard(size_t n, int world) {
+  if (world < 1) return 0;
+  const size_t per = (n + (size_t)world - 1) / (size_t)world;
+  return (per + 7) / 8 * 8;
+}
+
+extern "C" int acez_adamw_dp_reduce(const void* const* peer_grads, void* const* peer_flags, int world, int rank, size_t n,
+                                    float* reduced_shard, acez_stream_t stream) {
+  ACEZ_REQUIRE(peer_grads && peer_flags && reduced_shard && world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
+               "adamw_dp_reduce: bad arguments");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  DpPeers P{};
+  for (int r = 0; r < world; ++r) {
+    ACEZ_REQUIRE(peer_grads[r] && peer_flags[r], "adamw_dp_reduce: null peer pointer %d", r);
+    P.grads[r] = reinterpret_cast<const float*>(peer_grads[r]);
+    P.flags[r] = reinterpret_cast<int*>(peer_flags[r]);
+  }
+  const size_t shard = acez_adamw_dp_shard(n, world);
+  const int grid = 2 * sm_count();
+  adamw_dp_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, world, rank, n, shard, reduced_shard, nullptr);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" int acez_adamw_dp_apply(void* const* peer_w16, void* const* peer_w3h, void* const* peer_params, int world, int rank, size_t n,
+                                   const float* reduced_shard, float* params, float* exp_avg, float* exp_avg_sq,
+                                   const float* hyper_dev, float* scaler_state_dev, int* my_flags, int* found_inf_dev,
+                                   float* local_extras, int L, int C3, acez_stream_t stream) {
+  ACEZ_REQUIRE(peer_w16 && peer_w3h && peer_params && reduced_shard && params && exp_avg && exp_avg_sq && hyper_dev && scaler_state_dev &&
+                   my_flags && found_inf_dev && local_extras,
+               "adamw_dp_apply: null argument");
+  ACEZ_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && L >= 1 && (C3 == 3 || C3 == 4),
+               "adamw_dp_apply: bad arguments");
+  ACEZ_REQUIRE(n == (size_t)L * kLayerStride + (size_t)C3 * kC + (size_t)C3, "adamw_dp_apply: parameter count does not match the head");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  DpPeers P{};
+  for (int r = 0; r < world; ++r) {
+    ACEZ_REQUIRE(peer_w16[r] && peer_w3h[r] && peer_params[r], "adamw_dp_apply: null peer pointer %d", r);
+    P.w16[r] = reinterpret_cast<__half*>(peer_w16[r]);
+    P.w3h[r] = reinterpret_cast<__half*>(peer_w3h[r]);
+    P.params[r] = reinterpret_cast<float*>(peer_params[r]);
+  }
+  const size_t shard = acez_adamw_dp_shard(n, world);
+  const int grid = 2 * sm_count();
+  adamw_dp_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, world, rank, n, shard, reduced_shard, params, exp_avg,
+                                                                                  exp_avg_sq, hyper_dev, scaler_state_dev, my_flags,
+                                                                                  found_inf_dev, local_extras, L, C3);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}

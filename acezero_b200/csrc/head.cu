@@ -1076,6 +1076,11 @@ extern "C" int acez_head_sync_weights(acez_head_plan* h, acez_stream_t stream) {
 
 extern "C" void* acez_head_input_ptr(acez_head_plan* h) { return h ? h->ACT : nullptr; }
 
+extern "C" void* acez_head_w16_ptr(acez_head_plan* h, int which) {
+  if (h == nullptr) return nullptr;
+  return which == 0 ? static_cast<void*>(h->W16) : static_cast<void*>(h->W3h);
+}
+
 extern "C" int acez_head_plan_fused_chain(const acez_head_plan* h) { return (h != nullptr && h->use_chain) ? 1 : 0; }
 
 extern "C" int acez_debug_chain_clocks(long long* host_out, size_t max_slots, int* n_ctas) {

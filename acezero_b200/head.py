@@ -30,7 +30,7 @@ class HeadEngine:
 
     def __init__(self, num_head_blocks=1, use_homogeneous=True, mean=(0.0, 0.0, 0.0), max_rows=5120, training=False,
                  homogeneous_min_scale=0.01, homogeneous_max_scale=4.0, device="cuda", h_beta=None, max_inv_scale=None,
-                 min_inv_scale=None):
+                 min_inv_scale=None, peer_group=None):
         self.lib = _lib.load()
         _lib.check(self.lib.acez_device_check(), "acez_device_check")
         self.device = torch.device(device)
@@ -51,10 +51,23 @@ class HeadEngine:
         self.cfg = self._config()
         self.n_params = int(self.lib.acez_head_param_count(C.byref(self.cfg)))
         assert self.n_params == self.L * LAYER_STRIDE + self.C3 * 512 + self.C3
-        self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
+        # Data parallel over NVLink peer memory (peer_group = a torch.distributed group of the GPUs of this box): parameters,
+        # gradient and workspace are symmetric-memory allocations, so that the optimiser kernels of csrc/adamw_dp.cu can read
+        # the other ranks' gradients and write the other ranks' weights directly
+        self.peer = None
+        self._symm = None
+        if peer_group is not None and training:
+            import torch.distributed._symmetric_memory as symm_mem
+            self._symm = symm_mem
+            self._peer_group = peer_group
+            self.params = symm_mem.empty(self.n_params, dtype=torch.float32, device=self.device).zero_()
+            self.grads_full = symm_mem.empty(self.n_params + 4, dtype=torch.float32, device=self.device).zero_()
+        else:
+            self.params = torch.zeros(self.n_params, device=self.device, dtype=torch.float32)
         # 4 spare floats behind the gradient: data-parallel runs carry the GradScaler flag and the loss statistics through the
-        # SAME all-reduce as the gradient
-        self.grads_full = torch.zeros(self.n_params + 4, device=self.device, dtype=torch.float32) if training else None
+        # SAME reduction as the gradient
+        if self._symm is None:
+            self.grads_full = torch.zeros(self.n_params + 4, device=self.device, dtype=torch.float32) if training else None
         self.grads = self.grads_full[:self.n_params] if training else None
         self.exp_avg = torch.zeros_like(self.params) if training else None
         self.exp_avg_sq = torch.zeros_like(self.params) if training else None
@@ -93,7 +106,12 @@ class HeadEngine:
         self.cfg = self._config()
         ws_bytes = int(self.lib.acez_head_workspace_bytes(C.byref(self.cfg)))
         if getattr(self, "workspace", None) is None or self.workspace.numel() < ws_bytes:
-            self.workspace = torch.empty(ws_bytes, device=self.device, dtype=torch.uint8)
+            if self._symm is not None:
+                if getattr(self, "workspace", None) is not None:
+                    raise RuntimeError("a peer-memory head cannot grow its workspace (create it with the final max_rows)")
+                self.workspace = self._symm.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            else:
+                self.workspace = torch.empty(ws_bytes, device=self.device, dtype=torch.uint8)
         plan = C.c_void_p()
         rc = self.lib.acez_head_plan_create(C.byref(self.cfg), _lib.ptr(self.params), _lib.ptr(self.grads),
                                             _lib.ptr(self.workspace), ws_bytes, C.byref(plan))
@@ -233,6 +251,65 @@ class HeadEngine:
         h[5] = float(prev[5]) if loss_weight is None else loss_weight
         self.hyper.copy_(h, non_blocking=True)
         ev.record()
+
+    # ------------------------------------------------------------------ data parallel over peer memory
+    def setup_peers(self):
+        """Rendezvous of the symmetric allocations (collective over the peer group): peer pointers of every rank's parameters,
+        gradient, fp16 weight shadows and flag array."""
+        import torch.distributed as dist
+        sm, g = self._symm, self._peer_group
+        world, rank = dist.get_world_size(g), dist.get_rank(g)
+        self.dp_flags = sm.empty(8, dtype=torch.int32, device=self.device).zero_()
+        torch.cuda.synchronize()
+        hp = sm.rendezvous(self.params, g)
+        hg = sm.rendezvous(self.grads_full, g)
+        hw = sm.rendezvous(self.workspace, g)
+        hf = sm.rendezvous(self.dp_flags, g)
+        off16 = int(self.lib.acez_head_w16_ptr(self.plan, 0)) - self.workspace.data_ptr()
+        off3 = int(self.lib.acez_head_w16_ptr(self.plan, 1)) - self.workspace.data_ptr()
+        arr = lambda ptrs: (C.c_void_p * world)(*[int(p) for p in ptrs])
+        shard = int(self.lib.acez_adamw_dp_shard(self.n_params, world))
+        self.peer = {
+            "world": world, "rank": rank, "shard": shard, "handles": (hp, hg, hw, hf), "barrier": hg,
+            "params": arr(hp.buffer_ptrs), "grads": arr(hg.buffer_ptrs), "flags": arr(hf.buffer_ptrs),
+            "w16": arr([p + off16 for p in hw.buffer_ptrs]), "w3h": arr([p + off3 for p in hw.buffer_ptrs]),
+            "reduced": torch.zeros(shard + 4, device=self.device, dtype=torch.float32),
+        }
+        return self.peer
+
+    def adamw_step_peers(self, stream=None):
+        """Optimiser step of one data-parallel iteration over peer memory (csrc/adamw_dp.cu): barrier, reduce this rank's shard
+        of the gradient from all ranks, barrier, AdamW on the shard + the new fp16 weights to all ranks, barrier."""
+        P = self.peer
+        bar = P["barrier"]
+        st = _lib.stream_ptr(stream)
+        bar.barrier(channel=0)
+        _lib.check(self.lib.acez_adamw_dp_reduce(P["grads"], P["flags"], P["world"], P["rank"], self.n_params,
+                                                 _lib.ptr(P["reduced"]), st), "acez_adamw_dp_reduce")
+        bar.barrier(channel=1)
+        _lib.check(self.lib.acez_adamw_dp_apply(P["w16"], P["w3h"], P["params"], P["world"], P["rank"], self.n_params,
+                                                _lib.ptr(P["reduced"]), _lib.ptr(self.params), _lib.ptr(self.exp_avg),
+                                                _lib.ptr(self.exp_avg_sq), _lib.ptr(self.hyper), _lib.ptr(self.scaler_state),
+                                                _lib.ptr(self.dp_flags), _lib.ptr(self.found_inf),
+                                                C.c_void_p(self.grads_full.data_ptr() + 4 * self.n_params), self.L, self.C3, st),
+                   "acez_adamw_dp_apply")
+        bar.barrier(channel=2)
+
+    def gather_params_from_shards(self):
+        """fp32 master weights live on their owner rank during peer-memory training: collect them on every rank (export)."""
+        if self.peer is None:
+            return
+        import torch.distributed as dist
+        P = self.peer
+        world, rank, shard = P["world"], P["rank"], P["shard"]
+        mine = torch.zeros(shard, device=self.device, dtype=torch.float32)
+        lo = rank * shard
+        hi = min(lo + shard, self.n_params)
+        if hi > lo:
+            mine[:hi - lo] = self.params[lo:hi]
+        full = torch.empty(world * shard, device=self.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, mine, group=self._peer_group)
+        self.params.copy_(full[:self.n_params])
 
     def adamw_step(self, use_scaler=True, flag_complete=True, stream=None, check_flag_slot=False):
         """flag_complete: found_inf already covers all gradients (true after train_fwd_bwd).

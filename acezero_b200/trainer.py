@@ -156,9 +156,14 @@ class TrainLoop:
         self._refine_graphs = {}
         self._refine_warm = {}
         import os
-        self._dp_one_graph = world_size > 1 and os.environ.get("ACEZ_DP_ONE_GRAPH", "0") == "1"
-        # experimental: the post-all-reduce check pass also reads the flag slot (3 tiny torch kernels less per iteration)
-        self._dp_fused_flag = world_size > 1 and os.environ.get("ACEZ_DP_FUSED_FLAG", "0") == "1"
+        # the post-all-reduce check pass also reads the flag slot behind the gradient (no separate unpack kernels; validated at
+        # N = 2 in round 2)
+        self._dp_fused_flag = world_size > 1 and os.environ.get("ACEZ_DP_FUSED_FLAG", "1") != "0"
+        # peer-memory optimiser (csrc/adamw_dp.cu) when the head was created over symmetric memory (HeadEngine(peer_group=...))
+        self._dp_peers = world_size > 1 and getattr(head, "_symm", None) is not None and not self.refining
+        if self._dp_peers and head.peer is None:
+            head.setup_peers()
+        self._dp_peers_graph = os.environ.get("ACEZ_DP_PEERS_GRAPH", "0") == "1"
         self._graph_host = None
         self._warm_host = 0
         self.set_buffer(buffer)
@@ -283,6 +288,9 @@ class TrainLoop:
         flag_complete = self.world == 1
         fused_flag = self.world > 1 and self._dp_fused_flag and self.use_scaler
         if part == "optimizer":
+            if self._dp_peers:
+                h.adamw_step_peers()
+                return
             if self.world > 1 and not fused_flag:
                 self._dp_unpack_flag()
             h.adamw_step(use_scaler=self.use_scaler, flag_complete=flag_complete, check_flag_slot=fused_flag)
@@ -294,6 +302,9 @@ class TrainLoop:
         if self.world > 1:
             self._dp_pack_flag()
         if part == "fwd_bwd":
+            return
+        if self._dp_peers:
+            h.adamw_step_peers()   # reduce-scatter + AdamW + weight all-gather over NVLink peer memory (csrc/adamw_dp.cu)
             return
         if self.world > 1:
             self._dp_allreduce()
@@ -597,16 +608,25 @@ class TrainLoop:
                 self._warm += 1
                 self._enqueue_compute()
                 return
-            if self.world == 1 or self._dp_one_graph:
-                # (data parallel + ACEZ_DP_ONE_GRAPH=1: the NCCL all-reduce is captured inside the graph as well —
-                # experimental, to be measured at N >= 2; the communicator exists by now: the eager warm-up
-                # iterations above have run an all-reduce)
+            if self.world == 1:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue_compute()
                 self._graph = (g,)
+            elif self._dp_peers and self._dp_peers_graph:
+                # data parallel over peer memory: the optimiser kernels and the cross-GPU barriers are kernels on this stream,
+                # so the whole iteration is ONE graph
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_compute()
+                self._graph = (g,)
+            elif self._dp_peers:
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    self._enqueue_compute(part="fwd_bwd")
+                self._graph = (ga, None)
             else:
-                # data parallel: the NCCL all-reduces stay outside the graphs (two graphs around them)
+                # data parallel through NCCL: the all-reduce stays outside the graphs (two graphs around it)
                 ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
                     self._enqueue_compute(part="fwd_bwd")
@@ -615,6 +635,9 @@ class TrainLoop:
                 self._graph = (ga, gb)
         if len(self._graph) == 1:
             self._graph[0].replay()
+        elif self._graph[1] is None:
+            self._graph[0].replay()
+            self.head.adamw_step_peers()
         else:
             self._graph[0].replay()
             self._dp_allreduce()

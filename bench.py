@@ -436,7 +436,8 @@ def run_ours(args):
 
     # ---------------- training ----------------
     o = options(B * world, max(5000, 2 * (args.steps + args.warmup + 400)))
-    head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B, training=True, device=dev)
+    peers = dist.group.WORLD if (world > 1 and os.environ.get("ACEZ_DP_PEERS", "1") != "0") else None
+    head = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B, training=True, device=dev, peer_group=peers)
     head.load_state(ace_ref.make_head_state(200, 1, True))
     buf = synth_buffer(BUFFER_ROWS, dev, 2089)   # identical on every rank (same seed), as the replicated buffer is
     loop = TrainLoop(head, o, buf, rank=rank, world_size=world, use_graph=True)
@@ -473,7 +474,7 @@ def run_ours(args):
     strong = None
     if world > 1 and B % world == 0:
         o_s = options(B, max(5000, 2 * (args.steps + args.warmup + 400)))
-        head_s = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B // world, training=True, device=dev)
+        head_s = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=B // world, training=True, device=dev, peer_group=peers)
         head_s.load_state(ace_ref.make_head_state(200, 1, True))
         loop_s = TrainLoop(head_s, o_s, buf, rank=rank, world_size=world, use_graph=True)
         n_b = BUFFER_ROWS // B
@@ -700,6 +701,8 @@ def run_ours(args):
         "config": {"workload": "configs[1] 'chess'-shaped: ACE head training (b=5120/GPU, 1 head block, homogeneous, dyntanh, "
                                "one-cycle lr, GradScaler) + register_mapping's DSAC* (64 hyps, 60x80 maps)",
                    "global_batch": B * world, "buffer_rows": BUFFER_ROWS, "parallelism": f"dp{world}",
+                   "gradient_exchange": ("none" if world == 1 else ("NVLink peer memory: reduce-scatter + AdamW + fp16 weight "
+                                         "all-gather in two kernels (csrc/adamw_dp.cu)" if loop._dp_peers else "NCCL all-reduce")),
                    "l2": "inputs larger than L2 (1.26 GB patch buffer, fresh random rows gathered every step)"},
         "roofline": {"bound": "tensor", "kernel": roof_kernel,
                      "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

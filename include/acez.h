@@ -279,6 +279,34 @@ int acez_gather_rows_multi_sched(const void* const* srcs, void* const* dsts, con
                                  const float* inlier_count_dev, float* hyper_dev, acez_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel optimiser step over NVLink peer memory (G ranks of one box, one process per GPU): replaces "NCCL all-reduce
+ * of the 8.4 MB gradient + replicated AdamW" with two kernels that read / write the other GPUs' buffers directly.
+ * Rank r owns the parameter shard [r S, (r+1) S), S = acez_adamw_dp_shard(n, G).
+ *   acez_adamw_dp_reduce  reduced_shard[i] = sum over ranks (in rank order) of peer_grads[q][r S + i]; the 4 spare floats
+ *                         behind the gradient (+inf marker of the local GradScaler flag, loss / inlier / valid sums) are summed
+ *                         into reduced_shard[S .. S+4); the fp16-range / inf verdict of the summed shard is OR-ed into slot
+ *                         `rank` of EVERY rank's flag array (peer_flags[q], int[G], zero before the first step)
+ *   -- cross-GPU barrier (the caller's: e.g. torch symmetric memory) --
+ *   acez_adamw_dp_apply   found = any flag | non-finite marker; unless found: unscale + AdamW on the shard (params / moments of
+ *                         this rank), the new weights rounded to fp16 and stored into EVERY rank's fp16 shadows (peer_w16 /
+ *                         peer_w3h), the biases (the kernels read them in fp32) into every rank's parameters (peer_params); GradScaler.update(); the summed spare slots are copied to local_extras[0..4) (= this rank's
+ *                         grads + n); my_flags cleared; *found_inf_dev = found
+ *   -- cross-GPU barrier --
+ * peer_* are HOST arrays of G device pointers (peer mappings of the same buffer on every rank).
+ * fp32 master weights and moments are valid on their owner rank only.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t acez_adamw_dp_shard(size_t n, int world);
+int acez_adamw_dp_reduce(const void* const* peer_grads, void* const* peer_flags, int world, int rank, size_t n,
+                         float* reduced_shard, acez_stream_t stream);
+int acez_adamw_dp_apply(void* const* peer_w16, void* const* peer_w3h, void* const* peer_params, int world, int rank, size_t n,
+                        const float* reduced_shard, float* params, float* exp_avg, float* exp_avg_sq, const float* hyper_dev,
+                        float* scaler_state_dev, int* my_flags, int* found_inf_dev, float* local_extras, int L, int C3,
+                        acez_stream_t stream);
+/* Device pointers of the plan's fp16 weight shadows (which = 0: hidden layers [L][512][512], 1: fc3 [4][512]); they live in the
+ * caller's workspace, so a peer's copy sits at the same offset of the peer's workspace. */
+void* acez_head_w16_ptr(acez_head_plan* plan, int which);
+
+/* ------------------------------------------------------------------------------------------------------------
  * DSAC* pose solver. Replaces the reference's native operator:
  *   dsacstar.forward_rgb(sceneCoordinates[1,3,H,W] f32 CPU, outPose[4,4] f32 CPU, ransacHypotheses, inlierThreshold,
  *                        focalLength, ppointX, ppointY, inlierAlpha, maxReproj, subSampling, randomSeed,

@@ -159,3 +159,13 @@ def test_chain_protocol_model_check():
     for seed in range(16):
         for n in (1, 2, 3, 8):
             sim4.Sim(n, seed).run()
+
+
+def test_dp_shard_partition(lib):
+    """Shards of the peer-memory optimiser (csrc/adamw_dp.cu): multiples of 8 parameters (one 16-byte fp16 store per group and
+    peer), G of them cover the 2 103 300 head parameters, the layer strides keep every group inside one weight / bias block."""
+    n = 2103300
+    for g in (1, 2, 4, 8):
+        s = lib.acez_adamw_dp_shard(n, g)
+        assert s % 8 == 0 and g * s >= n and (g - 1) * s < n
+    assert (512 * 512 + 512) % 8 == 0 and (512 * 512) % 8 == 0

@@ -19,7 +19,8 @@ import bench  # noqa: E402
 
 def run(world, rank, dev, iters=40):
     o = bench.options(1024, iterations=1000)
-    head = HeadEngine(1, True, (0, 0, 0), max_rows=1024 // world, training=True, device=dev)
+    peers = dist.group.WORLD if (world > 1 and os.environ.get("ACEZ_DP_PEERS", "1") != "0") else None
+    head = HeadEngine(1, True, (0, 0, 0), max_rows=1024 // world, training=True, device=dev, peer_group=peers)
     head.load_state(ace_ref.make_head_state(200, 1, True))
     buf = bench.synth_buffer(65536, dev, 7)
     loop = TrainLoop(head, o, buf, rank=rank, world_size=world, use_graph=False)
@@ -28,6 +29,9 @@ def run(world, rank, dev, iters=40):
     for i in range(iters):
         loop.train_iteration(perm[i * 1024:(i + 1) * 1024], want_stats=True)
         losses.append(float(loop.last_stats[0]))
+    head.gather_params_from_shards()
+    if rank == 0 and world > 1:
+        print(f"[dp{world}] gradient exchange: {'NVLink peer memory (adamw_dp.cu)' if loop._dp_peers else 'NCCL all-reduce'}")
     return losses, head.params.clone(), float(head.scaler_state[0])
 
 
