@@ -175,7 +175,12 @@ __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __r
                                          const GatherSched sch) {
   pdl_wait();
   pdl_launch_dependents();
-  if (sch.enabled && blockIdx.x == 0 && threadIdx.x == 0) schedule_step_device(sch.p, sch.state, sch.inlier_count, sch.hyper);
+  // the schedule rides in an EXTRA block at the end of the grid (its serial double-precision chain would otherwise lengthen a
+  // block that also gathers rows: measured +2 us)
+  if (sch.enabled && blockIdx.x == gridDim.x - 1) {
+    if (threadIdx.x == 0) schedule_step_device(sch.p, sch.state, sch.inlier_count, sch.hyper);
+    return;
+  }
   // one warp per batch row, all arrays: the 1 KB feature row moves as 2 x 16 B per lane, the small arrays as words
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -751,11 +756,12 @@ static int head_prepare(acez_head_plan* h, int rows, int training) {
       W.batch = L;
       W.a_mn = W.b_mn = 1;
       {
-        // 256 x 128 tiles per SM pair: 64 pairs = 128 CTAs, no split-K (default). ACEZ_WGRAD_2CTA_BN=256: 256 x 256 tiles with an
-        // on-chip split-K 2 (cluster of four = two pairs per tile, also 128 CTAs; the tensor pipe runs at 87 % instead of 50 %
-        // per CTA, round-2 cycle counters; the second pair's accumulator travels through distributed shared memory)
+        // 256 x 256 tiles with an on-chip split-K 2 (default): a cluster of four = two pairs per tile, 128 CTAs; the tensor pipe
+        // runs at 87 % per CTA instead of the 50 % of 128-column tiles (round-2 cycle counters) and the second pair's
+        // accumulator travels through distributed shared memory: 171.0 vs 180.6 us per iteration. ACEZ_WGRAD_2CTA_BN=128: 256 x
+        // 128 tiles per pair, 64 pairs, no split
         const char* e = getenv("ACEZ_WGRAD_2CTA_BN");
-        W.bn = (e != nullptr && atoi(e) == 256) ? 256 : 128;
+        W.bn = (e != nullptr && atoi(e) == 128) ? 128 : 256;
       }
       Gemm2Args& g = W.args;
       g.M = kC; g.N = kC; g.k_blocks = (rows + 63) / 64;
@@ -1238,7 +1244,7 @@ static int gather_multi_impl(const void* const* srcs, void* const* dsts, const i
   if (rc) return rc;
   if (rows == 0) return ACEZ_OK;
   const int threads = 256;
-  dim3 grid((rows * 32 + threads - 1) / threads);
+  dim3 grid((rows * 32 + threads - 1) / threads + (sch.enabled ? 1 : 0));
   return launch_pdl(gather_rows_multi_kernel, grid, dim3(threads), 0, reinterpret_cast<cudaStream_t>(stream), false, g, idx, rows,
                     n_arrays, sch);
 }

@@ -131,7 +131,7 @@ class HeadEngine:
         if not self.fused_chain:
             return "gemm_tcgen05_kernel<FWD>"
         if os.environ.get("ACEZ_CHAIN_V4", "1") != "0":
-            return f"head_chain4_kernel<FWD,{2 if os.environ.get('ACEZ_CHAIN_EPI_GROUPS', '2') != '4' else 4}>"
+            return "head_chain4_kernel<FWD,2,SPLIT>" if os.environ.get("ACEZ_CHAIN_EPI_SPLIT", "1") != "0" else "head_chain4_kernel<FWD,2>"
         return "head_chain_kernel<FWD>"
 
     def resize(self, max_rows):
