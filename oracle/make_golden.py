@@ -157,5 +157,33 @@ def main():
     print("wrote", dst, os.path.getsize(dst), "bytes;", len(out), "arrays")
 
 
+def pretrained_encoder_golden():
+    """The reference's own `Encoder` (ace_network.py:14-59) with the weights it ships (`ace_encoder_pretrained.pt`) on two
+    image sizes: pins oracle.ace_ref.encoder_forward on the real weight distribution, not only on random weights. The
+    22 MB weight file is not committed: `__graft_entry__.build()` stages it into the git-ignored `oracle/_ref/`."""
+    sys.path.insert(0, str(REF))
+    import ace_network  # noqa: E402  (the reference's file)
+    torch.set_num_threads(8)
+    esd = torch.load(REF / "ace_encoder_pretrained.pt", map_location="cpu")
+    enc = ace_network.Encoder(out_channels=512)
+    enc.load_state_dict(esd)
+    enc.eval()
+    out = {"meta_torch_version": np.array(torch.__version__),
+           "weights_checksum": np.array(sum(float(v.double().abs().sum()) for v in esd.values()))}
+    for tag, (h, w) in {"96x128": (96, 128), "120x168": (120, 168)}.items():
+        with torch.no_grad():
+            f = enc(ace_ref.synth_image(11, h, w))
+        out[f"encoder_{tag}_shape"] = np.array(f.shape)
+        out[f"encoder_{tag}_sample"] = f.reshape(-1)[::29].numpy().copy()
+        out[f"encoder_{tag}_absmax"] = np.array(float(f.abs().max()))
+    dst = REPO / "tests" / "golden" / "encoder_pretrained_golden.npz"
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--pretrained-encoder" in sys.argv:
+        pretrained_encoder_golden()
+    else:
+        main()
+        pretrained_encoder_golden()

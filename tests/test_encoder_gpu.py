@@ -37,3 +37,28 @@ def test_encoder_fp16_input_and_plan_regrow():
     assert torch.equal(a, b)
     c = eng.forward_nhwc(ace_ref.synth_image(9, 64, 64).cuda())
     assert tuple(c.shape) == (1, 8, 8, 512) and torch.isfinite(c.float()).all()
+
+
+@pytest.mark.parametrize("h,w", [(96, 128), (120, 168), (480, 640)])
+def test_encoder_with_pretrained_weights_matches_oracle(h, w):
+    """The same comparison on the weights the reference ships (`ace_encoder_pretrained.pt`, staged by
+    `__graft_entry__.build()` into the git-ignored oracle/_ref/): real weight statistics, not random ones. The oracle is
+    pinned to the reference's own Encoder on these weights by tests/test_oracle_golden.py."""
+    import os
+    from acezero_b200.encoder import EncoderEngine, out_hw
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = next((p for p in ("/root/reference/ace_encoder_pretrained.pt", os.path.join(here, "oracle", "_ref", "ace_encoder_pretrained.pt"))
+                 if os.path.exists(p)), None)
+    if path is None:
+        pytest.skip("ace_encoder_pretrained.pt not staged (run __graft_entry__.build() in the build container)")
+    esd = torch.load(path, map_location="cpu")
+    eng = EncoderEngine(esd, max_n=1, max_h=h, max_w=w)
+    img = ace_ref.synth_image(11, h, w)
+    f = eng.forward_nhwc(img.cuda()).float().cpu()
+    assert tuple(f.shape) == (1, *out_hw(h, w), 512)
+    with torch.no_grad():
+        ref = ace_ref.encoder_forward(esd, img, emulate_half=True).permute(0, 2, 3, 1)
+    err = (f - ref).abs()
+    scale = ref.abs().max()
+    assert err.max() < 1e-2 * scale, f"max err {err.max():.4f} vs scale {scale:.3f}"
+    assert err.mean() < 1e-3 * scale

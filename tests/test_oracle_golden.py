@@ -80,3 +80,32 @@ def test_encoder_forward_matches_reference(golden, tag, h, w):
     ref = golden[f"encoder_{tag}_sample"]
     got = f.reshape(-1)[::53].numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+
+
+def _pretrained_encoder_state():
+    """The reference's shipped encoder weights: from /root/reference in the build container, from the git-ignored copy
+    `__graft_entry__.build()` stages under oracle/_ref/ elsewhere (the GPU box)."""
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in ("/root/reference/ace_encoder_pretrained.pt", os.path.join(here, "oracle", "_ref", "ace_encoder_pretrained.pt")):
+        if os.path.exists(p):
+            return torch.load(p, map_location="cpu")
+    return None
+
+
+@pytest.mark.parametrize("tag,h,w", [("96x128", 96, 128), ("120x168", 120, 168)])
+def test_encoder_forward_with_pretrained_weights_matches_reference(tag, h, w):
+    """oracle.ace_ref.encoder_forward on the weights the reference ships vs the reference's own Encoder
+    (fixture: oracle/make_golden.py::pretrained_encoder_golden)."""
+    import os
+    esd = _pretrained_encoder_state()
+    if esd is None:
+        pytest.skip("ace_encoder_pretrained.pt not available (neither /root/reference nor oracle/_ref)")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_pretrained_golden.npz"))
+    chk = sum(float(v.double().abs().sum()) for v in esd.values())
+    assert abs(chk - float(g["weights_checksum"])) <= 1e-9 * abs(chk), "not the weight file the fixture was made with"
+    with torch.no_grad():
+        f = ace_ref.encoder_forward(esd, ace_ref.synth_image(11, h, w), emulate_half=False)
+    assert list(f.shape) == list(g[f"encoder_{tag}_shape"])
+    ref = g[f"encoder_{tag}_sample"]
+    np.testing.assert_allclose(f.reshape(-1)[::29].numpy(), ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
