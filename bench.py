@@ -558,7 +558,8 @@ def run_ours(args):
         # one launch = all 8 hidden layers of the forward pass (head_chain.cu)
         gemm_us = e0.elapsed_time(e1) * 1000.0 / (5 * reps)
         achieved_tf = head.L * FLOP_FWD_GEMM / (gemm_us * 1e-6) / 1e12
-        roof_kernel = f"head_chain_kernel<FWD>: {head.L} fused layers of 5120x512x512 (cluster of 2 CTAs per 128-row tile)"
+        roof_kernel = (f"{head.chain_kernel_symbol()}: {head.L} fused layers of 5120x512x512 in one launch (cluster of 4 CTAs = two 128-row "
+                       "tiles x two channel halves, tcgen05 cta_group::2)")
         launches = {"gather": 1, "fwd_chain": 1, "tail": 1, "fc3_reduce": 1,
                     "dgrad_chain": 1, "wgrad_gemm": 1, "adamw": 1}
     else:
