@@ -25,6 +25,39 @@ static constexpr int kC = 512;
 static constexpr size_t kLayerStride = (size_t)kC * kC + kC;
 static constexpr int kMaxRanks = 8;
 
+// Cross-GPU synchronisation INSIDE the kernels (acez_adamw_dp_step; the two-call interface leaves the barriers to the caller):
+// every rank's flag array (symmetric memory, int[kDpFlagInts]) also carries three rows of epoch signals, written by the peers
+// with st.release.sys over NVLink and polled locally with ld.acquire.sys:
+//   [kSigGrads + q]   rank q's gradient of this iteration is complete        (sent by block 0 of q's reduce kernel)
+//   [kSigReduced + q] rank q has reduced its shard, its verdict flag is out  (sent by the last block of q's reduce kernel)
+//   [kSigApplied + q] rank q has written its shard of the new weights        (sent by the last block of q's apply kernel, which
+//                     then waits for everybody's: when the apply kernel completes, every rank's weights have landed here)
+// The epoch (iterations completed) lives in device memory and advances once per step, so a captured CUDA graph replays it.
+static constexpr int kSigGrads = 16, kSigReduced = 24, kSigApplied = 32;
+static constexpr long long kDpWatchdogCycles = 40000000000ll;   // ~20 s: a peer that never signals is a dead job, not a stall
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// thread q < world waits until rank q's signal of row `row` has reached epoch e
+__device__ __forceinline__ void dp_wait_row(const int* my_flags, int row, int q, int e) {
+  const int* p = my_flags + row + q;
+  if (ld_acquire_sys(p) - e >= 0) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) - e < 0) {
+    __nanosleep(40);
+    if (clock64() - t0 > kDpWatchdogCycles) {
+      printf("acez: data-parallel optimiser: rank %d never signalled row %d of epoch %d\n", q, row, e);
+      __trap();
+    }
+  }
+}
+
 struct DpPeers {
   const float* grads[kMaxRanks];   // every rank's flat gradient (+4 spare floats)
   int* flags[kMaxRanks];           // every rank's flag array [world]
@@ -34,8 +67,19 @@ struct DpPeers {
 };
 
 __global__ void adamw_dp_reduce_kernel(const DpPeers P, int world, int rank, size_t n, size_t shard, float* __restrict__ reduced,
-                                       float* __restrict__ local_extras /* = local grads + n: receives the 4 summed spare slots */) {
+                                       float* __restrict__ local_extras /* = local grads + n: receives the 4 summed spare slots */,
+                                       unsigned int* __restrict__ sync_state /* nullable: [0] epoch, [1] block counter */) {
   pdl_wait();
+  const int epoch = sync_state != nullptr ? (int)sync_state[0] + 1 : 0;
+  if (sync_state != nullptr) {
+    // this rank's gradient is complete (stream order / the wait above): tell everybody, then wait for everybody's
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(P.flags[threadIdx.x] + kSigGrads + rank, epoch);
+    }
+    if (threadIdx.x < world) dp_wait_row(P.flags[rank], kSigGrads, threadIdx.x, epoch);
+    __syncthreads();
+  }
   const size_t lo = (size_t)rank * shard;
   const size_t hi = lo + shard < n ? lo + shard : n;
   bool bad = false;
@@ -66,13 +110,28 @@ __global__ void adamw_dp_reduce_kernel(const DpPeers P, int world, int rank, siz
   if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) {
     for (int r = 0; r < world; ++r) *reinterpret_cast<volatile int*>(P.flags[r] + rank) = 1;   // remote stores: every rank learns this shard's verdict
   }
+  if (sync_state != nullptr && threadIdx.x == 0) {
+    __threadfence_system();   // this block's verdict stores before its arrival
+    if (atomicAdd(sync_state + 1, 1u) == gridDim.x - 1) {
+      sync_state[1] = 0u;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys(P.flags[r] + kSigReduced + rank, epoch);
+    }
+  }
 }
 
 __global__ void adamw_dp_apply_kernel(const DpPeers P, int world, int rank, size_t n, size_t shard, const float* __restrict__ reduced,
                                       float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                       const float* __restrict__ hyper, float* __restrict__ scaler_state, int* __restrict__ my_flags,
-                                      int* __restrict__ found_inf_out, float* __restrict__ local_extras, int L, int C3) {
+                                      int* __restrict__ found_inf_out, float* __restrict__ local_extras, int L, int C3,
+                                      unsigned int* __restrict__ sync_state /* nullable: [0] epoch */) {
   pdl_wait();
+  const int epoch = sync_state != nullptr ? (int)sync_state[0] + 1 : 0;
+  if (sync_state != nullptr) {
+    // every rank has reduced its shard: all verdict flags are final, and nobody computes with the old weights any more
+    if (threadIdx.x < world) dp_wait_row(my_flags, kSigReduced, threadIdx.x, epoch);
+    __syncthreads();
+  }
   int found = 0;
   for (int r = 0; r < world; ++r) found |= my_flags[r];
   const float flag_slot = reduced[shard];    // sum of the ranks' +inf markers (local backward overflow)
@@ -164,7 +223,8 @@ __global__ void adamw_dp_apply_kernel(const DpPeers P, int world, int rank, size
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (sync_state != nullptr) __threadfence_system();   // this block's remote weight stores before its arrival
+    else __threadfence();
     unsigned int* cnt = reinterpret_cast<unsigned int*>(scaler_state + 3);
     if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
       if (found) { scaler_state[0] *= 0.5f; scaler_state[1] = 0.f; }
@@ -176,6 +236,14 @@ __global__ void adamw_dp_apply_kernel(const DpPeers P, int world, int rank, size
       *found_inf_out = found;
       for (int r = 0; r < world; ++r) my_flags[r] = 0;   // every block has read them (this is the last block to get here)
       *cnt = 0u;
+      if (sync_state != nullptr) {
+        sync_state[0] = (unsigned int)epoch;
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) st_release_sys(P.flags[r] + kSigApplied + rank, epoch);
+        // the kernel completes only when every rank's shard of the new weights has landed in THIS rank's buffers: whatever
+        // follows in stream order (the next iteration's forward) may read them
+        for (int r = 0; r < world; ++r) dp_wait_row(my_flags, kSigApplied, r, epoch);
+      }
     }
   }
 }
@@ -204,7 +272,7 @@ extern "C" int acez_adamw_dp_reduce(const void* const* peer_grads, void* const* 
   }
   const size_t shard = acez_adamw_dp_shard(n, world);
   const int grid = 2 * sm_count();
-  adamw_dp_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, world, rank, n, shard, reduced_shard, nullptr);
+  adamw_dp_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, world, rank, n, shard, reduced_shard, nullptr, nullptr);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;
 }
@@ -232,7 +300,41 @@ extern "C" int acez_adamw_dp_apply(void* const* peer_w16, void* const* peer_w3h,
   const int grid = 2 * sm_count();
   adamw_dp_apply_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, world, rank, n, shard, reduced_shard, params, exp_avg,
                                                                                   exp_avg_sq, hyper_dev, scaler_state_dev, my_flags,
-                                                                                  found_inf_dev, local_extras, L, C3);
+                                                                                  found_inf_dev, local_extras, L, C3, nullptr);
+  ACEZ_CUDA(cudaGetLastError());
+  return ACEZ_OK;
+}
+
+extern "C" int acez_adamw_dp_step(const void* const* peer_grads, void* const* peer_flags, void* const* peer_w16, void* const* peer_w3h,
+                                  void* const* peer_params, int world, int rank, size_t n, float* reduced_shard, float* params,
+                                  float* exp_avg, float* exp_avg_sq, const float* hyper_dev, float* scaler_state_dev,
+                                  int* found_inf_dev, float* local_extras, unsigned int* sync_state_dev, int L, int C3,
+                                  acez_stream_t stream) {
+  ACEZ_REQUIRE(peer_grads && peer_flags && peer_w16 && peer_w3h && peer_params && reduced_shard && params && exp_avg && exp_avg_sq &&
+                   hyper_dev && scaler_state_dev && found_inf_dev && local_extras && sync_state_dev,
+               "adamw_dp_step: null argument");
+  ACEZ_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world && L >= 1 && (C3 == 3 || C3 == 4),
+               "adamw_dp_step: bad arguments");
+  ACEZ_REQUIRE(n == (size_t)L * kLayerStride + (size_t)C3 * kC + (size_t)C3, "adamw_dp_step: parameter count does not match the head");
+  int rc = acez_device_check();
+  if (rc) return rc;
+  DpPeers P{};
+  for (int r = 0; r < world; ++r) {
+    ACEZ_REQUIRE(peer_grads[r] && peer_flags[r] && peer_w16[r] && peer_w3h[r] && peer_params[r], "adamw_dp_step: null peer pointer %d", r);
+    P.grads[r] = reinterpret_cast<const float*>(peer_grads[r]);
+    P.flags[r] = reinterpret_cast<int*>(peer_flags[r]);
+    P.w16[r] = reinterpret_cast<__half*>(peer_w16[r]);
+    P.w3h[r] = reinterpret_cast<__half*>(peer_w3h[r]);
+    P.params[r] = reinterpret_cast<float*>(peer_params[r]);
+  }
+  const size_t shard = acez_adamw_dp_shard(n, world);
+  // every block of both kernels polls signals: all of them must be able to be resident together with whatever still runs
+  const int grid = sm_count();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adamw_dp_reduce_kernel<<<grid, 256, 0, st>>>(P, world, rank, n, shard, reduced_shard, nullptr, sync_state_dev);
+  ACEZ_CUDA(cudaGetLastError());
+  adamw_dp_apply_kernel<<<grid, 256, 0, st>>>(P, world, rank, n, shard, reduced_shard, params, exp_avg, exp_avg_sq, hyper_dev,
+                                              scaler_state_dev, P.flags[rank], found_inf_dev, local_extras, L, C3, sync_state_dev);
   ACEZ_CUDA(cudaGetLastError());
   return ACEZ_OK;
 }

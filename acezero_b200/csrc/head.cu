@@ -186,16 +186,56 @@ __global__ void gather_rows_multi_kernel(const MultiGather g, const int64_t* __r
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const size_t src_row = (size_t)idx[warp];
-  for (int a = 0; a < n_arrays; ++a) {
+  // Two passes: ALL loads of the row (every array) are issued before the first store, so the row costs one memory round trip
+  // instead of one per array (round 2: 8.6 us for 6.3 MB with the arrays copied one after the other). Register paths: array 0
+  // (the 1 KB feature row) as up to two 16-byte trips of the warp, the small arrays as one 4-byte (<= 128 B rows) or one 2-byte
+  // (<= 64 B rows) trip; anything else takes the plain loop in the second pass.
+  uint4 f16[2];
+  uint32_t v4[8];
+  uint16_t v2[8];
+  const int rb0 = g.row_bytes[0];
+  const bool big0 = (rb0 & 15) == 0 && rb0 <= 1024 && ((reinterpret_cast<uintptr_t>(g.src[0]) | reinterpret_cast<uintptr_t>(g.dst[0])) & 15) == 0;
+  if (big0) {
+    const uint8_t* s = g.src[0] + src_row * rb0;
+    if (lane * 16 < rb0) f16[0] = *reinterpret_cast<const uint4*>(s + lane * 16);
+    if (lane * 16 + 512 < rb0) f16[1] = *reinterpret_cast<const uint4*>(s + lane * 16 + 512);
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (a >= n_arrays || (a == 0 && big0)) continue;
     const int rb = g.row_bytes[a];
     const uint8_t* s = g.src[a] + src_row * rb;
+    if ((rb & 3) == 0 && rb <= 128) {
+      if (lane * 4 < rb) v4[a] = *reinterpret_cast<const uint32_t*>(s + lane * 4);
+    } else if ((rb & 1) == 0 && rb <= 64) {
+      if (lane * 2 < rb) v2[a] = *reinterpret_cast<const uint16_t*>(s + lane * 2);
+    }
+  }
+  if (big0) {
+    uint8_t* d = g.dst[0] + (size_t)warp * rb0;
+    if (lane * 16 < rb0) *reinterpret_cast<uint4*>(d + lane * 16) = f16[0];
+    if (lane * 16 + 512 < rb0) *reinterpret_cast<uint4*>(d + lane * 16 + 512) = f16[1];
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (a >= n_arrays || (a == 0 && big0)) continue;
+    const int rb = g.row_bytes[a];
     uint8_t* d = g.dst[a] + (size_t)warp * rb;
-    if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(g.src[a]) | reinterpret_cast<uintptr_t>(g.dst[a])) & 15) == 0) {
-      for (int o = lane * 16; o < rb; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
-    } else if ((rb & 3) == 0) {
-      for (int o = lane * 4; o < rb; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+    if ((rb & 3) == 0 && rb <= 128) {
+      if (lane * 4 < rb) *reinterpret_cast<uint32_t*>(d + lane * 4) = v4[a];
+    } else if ((rb & 1) == 0 && rb <= 64) {
+      if (lane * 2 < rb) *reinterpret_cast<uint16_t*>(d + lane * 2) = v2[a];
     } else {
-      for (int o = lane * 2; o < rb; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+      const uint8_t* s = g.src[a] + src_row * rb;
+      if ((rb & 15) == 0 && ((reinterpret_cast<uintptr_t>(g.src[a]) | reinterpret_cast<uintptr_t>(g.dst[a])) & 15) == 0) {
+        for (int o = lane * 16; o < rb; o += 512) *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
+      } else if ((rb & 3) == 0) {
+        for (int o = lane * 4; o < rb; o += 128) *reinterpret_cast<uint32_t*>(d + o) = *reinterpret_cast<const uint32_t*>(s + o);
+      } else if ((rb & 1) == 0) {
+        for (int o = lane * 2; o < rb; o += 64) *reinterpret_cast<uint16_t*>(d + o) = *reinterpret_cast<const uint16_t*>(s + o);
+      } else {
+        for (int o = lane; o < rb; o += 32) d[o] = s[o];
+      }
     }
   }
 }

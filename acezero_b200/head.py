@@ -259,7 +259,12 @@ class HeadEngine:
         import torch.distributed as dist
         sm, g = self._symm, self._peer_group
         world, rank = dist.get_world_size(g), dist.get_rank(g)
-        self.dp_flags = sm.empty(8, dtype=torch.int32, device=self.device).zero_()
+        # [0, 8) shard verdicts, [16, 40) three rows of epoch signals written by the peers (csrc/adamw_dp.cu)
+        self.dp_flags = sm.empty(64, dtype=torch.int32, device=self.device).zero_()
+        self.dp_sync_state = torch.zeros(4, dtype=torch.int32, device=self.device)
+        import os
+        # cross-GPU synchronisation inside the two optimiser kernels (default); 0: torch symmetric-memory barriers around them
+        self.dp_signals = os.environ.get("ACEZ_DP_SIGNALS", "1") != "0"
         torch.cuda.synchronize()
         hp = sm.rendezvous(self.params, g)
         hg = sm.rendezvous(self.grads_full, g)
@@ -283,6 +288,13 @@ class HeadEngine:
         P = self.peer
         bar = P["barrier"]
         st = _lib.stream_ptr(stream)
+        if self.dp_signals:
+            _lib.check(self.lib.acez_adamw_dp_step(P["grads"], P["flags"], P["w16"], P["w3h"], P["params"], P["world"], P["rank"],
+                                                   self.n_params, _lib.ptr(P["reduced"]), _lib.ptr(self.params), _lib.ptr(self.exp_avg),
+                                                   _lib.ptr(self.exp_avg_sq), _lib.ptr(self.hyper), _lib.ptr(self.scaler_state),
+                                                   _lib.ptr(self.found_inf), C.c_void_p(self.grads_full.data_ptr() + 4 * self.n_params),
+                                                   _lib.ptr(self.dp_sync_state), self.L, self.C3, st), "acez_adamw_dp_step")
+            return
         bar.barrier(channel=0)
         _lib.check(self.lib.acez_adamw_dp_reduce(P["grads"], P["flags"], P["world"], P["rank"], self.n_params,
                                                  _lib.ptr(P["reduced"]), st), "acez_adamw_dp_reduce")

@@ -163,7 +163,9 @@ class TrainLoop:
         self._dp_peers = world_size > 1 and getattr(head, "_symm", None) is not None and not self.refining
         if self._dp_peers and head.peer is None:
             head.setup_peers()
-        self._dp_peers_graph = os.environ.get("ACEZ_DP_PEERS_GRAPH", "0") == "1"
+        # with the cross-GPU synchronisation inside the optimiser kernels (HeadEngine.dp_signals) the whole iteration is ONE graph;
+        # with torch's barrier kernels around them the optimiser stays eager unless ACEZ_DP_PEERS_GRAPH=1
+        self._dp_peers_graph = (self._dp_peers and getattr(head, "dp_signals", False)) or os.environ.get("ACEZ_DP_PEERS_GRAPH", "0") == "1"
         self._graph_host = None
         self._warm_host = 0
         self.set_buffer(buffer)
@@ -503,7 +505,9 @@ class TrainLoop:
 
     def _step_on_static_batch(self, read_loss):
         """One iteration on whatever the static batch tensors hold (no gather); reads the loss statistics back."""
-        if self.use_graph and self.world == 1:   # (NCCL all-reduces are not captured: data parallel runs this path eagerly)
+        # (NCCL all-reduces are not captured: that data-parallel path runs eagerly; the peer-memory optimiser with in-kernel
+        # signalling is plain kernels on this stream and is captured like the single-GPU iteration)
+        if self.use_graph and (self.world == 1 or (self._dp_peers and self._dp_peers_graph)):
             if self._graph_host is None:
                 if self._warm_host < 2:
                     self._warm_host += 1
@@ -575,7 +579,7 @@ class TrainLoop:
         self._aux.copy_(st[nf:], non_blocking=True)
         self._stage_free[slot].record(cur)
         self._stage_r ^= 1
-        if not read_loss or lag == 0 or self.world > 1:
+        if not read_loss or lag == 0 or (self.world > 1 and not self._dp_peers):
             return self._step_on_static_batch(read_loss)
         if not hasattr(self, "_lag_stats"):
             self._lag_stats = torch.zeros((2, 4), dtype=torch.float32).pin_memory()
@@ -583,7 +587,7 @@ class TrainLoop:
             self._lag_n = 0
         self._step_on_static_batch(False)
         k = self._lag_n & 1
-        self._lag_stats[k].copy_(self.head.stats, non_blocking=True)
+        self._lag_stats[k].copy_(self._dp_reduce_stats() if self.world > 1 else self.head.stats, non_blocking=True)
         self._lag_ev[k].record(cur)
         self._lag_n += 1
         return self._read_lagged(k ^ 1) if self._lag_n > 1 else None
