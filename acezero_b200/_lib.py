@@ -132,7 +132,7 @@ def load():
     lib.acez_adamw_dp_shard.restype = C.c_size_t
     lib.acez_adamw_dp_reduce.argtypes = [vp, vp, i, i, C.c_size_t, vp, vp]
     lib.acez_adamw_dp_apply.argtypes = [vp, vp, vp, i, i, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp]
-    lib.acez_adamw_dp_step.argtypes = [vp, vp, vp, vp, vp, i, i, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp]
+    lib.acez_adamw_dp_step.argtypes = [vp, vp, vp, vp, vp, i, i, C.c_size_t, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, vp]
     lib.acez_head_input_ptr.argtypes = [vp]
     lib.acez_head_input_ptr.restype = vp
     lib.acez_head_plan_fused_chain.argtypes = [vp]

@@ -301,8 +301,8 @@ class TrainLoop:
                         aug_inv=bt["aug_poses_inv"], pose_inv=bt["poses_inv"], P=P,
                         target_crds=bt["target_crds"] if self.use_depth else None, features=None, d_P=d_P,
                         d_Kdiag=d_Kdiag, use_device_scale=True, use_device_loss_weight=True)
-        if self.world > 1:
-            self._dp_pack_flag()
+        if self.world > 1 and not (self._dp_peers and getattr(h, "dp_signals", False)):
+            self._dp_pack_flag()   # (the peer-memory optimiser with in-kernel signalling packs the spare slots itself)
         if part == "fwd_bwd":
             return
         if self._dp_peers:

@@ -702,8 +702,13 @@ def run_ours(args):
         "config": {"workload": "configs[1] 'chess'-shaped: ACE head training (b=5120/GPU, 1 head block, homogeneous, dyntanh, "
                                "one-cycle lr, GradScaler) + register_mapping's DSAC* (64 hyps, 60x80 maps)",
                    "global_batch": B * world, "buffer_rows": BUFFER_ROWS, "parallelism": f"dp{world}",
-                   "gradient_exchange": ("none" if world == 1 else ("NVLink peer memory: reduce-scatter + AdamW + fp16 weight "
-                                         "all-gather in two kernels (csrc/adamw_dp.cu)" if loop._dp_peers else "NCCL all-reduce")),
+                   "gradient_exchange": ("none" if world == 1 else ((
+                       "NVLink peer memory, ONE kernel per step (csrc/adamw_dp.cu): reduce-scatter"
+                       + (" in the NVSwitch (multimem.ld_reduce)" if getattr(head, "dp_multicast", None) is not None else " by peer loads")
+                       + " + global GradScaler verdict + AdamW on the shard + fp16 weights to all ranks"
+                       + (" (multimem.st)" if getattr(head, "dp_multicast", None) is not None else "")
+                       + ", cross-GPU synchronisation by in-kernel epoch signals, whole iteration one CUDA graph")
+                       if loop._dp_peers else "NCCL all-reduce")),
                    "l2": "inputs larger than L2 (1.26 GB patch buffer, fresh random rows gathered every step)"},
         "roofline": {"bound": "tensor", "kernel": roof_kernel,
                      "achieved": achieved_tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",

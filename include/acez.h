@@ -307,11 +307,19 @@ int acez_adamw_dp_apply(void* const* peer_w16, void* const* peer_w3h, void* cons
  * flags as above, [16, 16+G) / [24, 24+G) / [32, 32+G) epoch signals "gradient complete" / "shard reduced" / "weights written",
  * stored by the peers over NVLink (st.release.sys) and polled locally (ld.acquire.sys). sync_state_dev: unsigned[4] of this rank,
  * zero before the first step ([0] = completed steps, [1] = block counter). When the second kernel completes, every rank's shard
- * of the new weights has landed in this rank's buffers. A peer that never signals traps after ~20 s instead of hanging. */
+ * of the new weights has landed in this rank's buffers. A peer that never signals traps after ~20 s instead of hanging.
+ * local_stats_dev (nullable): float[3] loss / inlier / valid sums of this rank's backward pass; when given, the first kernel packs
+ * the four spare slots behind this rank's gradient itself (+inf marker from *found_inf_dev, then the three sums) and the step runs
+ * as ONE kernel when the shard fits a co-resident grid's registers.
+ * multicast (nullable): host array of 4 NVSwitch multicast addresses of the gradient, fp16 hidden weights, fp16 fc3 weights and
+ * parameter buffers (NVLink SHARP): the gradient is then summed inside the switch (multimem.ld_reduce) and the new weights reach
+ * all ranks with one store each (multimem.st); the summation order inside the switch is the hardware's, every element is still
+ * reduced exactly once (by its owner), so all ranks hold identical weights. */
 int acez_adamw_dp_step(const void* const* peer_grads, void* const* peer_flags, void* const* peer_w16, void* const* peer_w3h,
                        void* const* peer_params, int world, int rank, size_t n, float* reduced_shard, float* params,
                        float* exp_avg, float* exp_avg_sq, const float* hyper_dev, float* scaler_state_dev, int* found_inf_dev,
-                       float* local_extras, unsigned int* sync_state_dev, int L, int C3, acez_stream_t stream);
+                       float* local_extras, unsigned int* sync_state_dev, const float* local_stats_dev,
+                       const void* const* multicast, int L, int C3, acez_stream_t stream);
 /* Device pointers of the plan's fp16 weight shadows (which = 0: hidden layers [L][512][512], 1: fc3 [4][512]); they live in the
  * caller's workspace, so a peer's copy sits at the same offset of the peer's workspace. */
 void* acez_head_w16_ptr(acez_head_plan* plan, int which);
