@@ -1,4 +1,5 @@
-// EXPERIMENTAL (round 2; not yet run on hardware, not used by any default path): tcgen05 GEMM with cta_group::2.
+// tcgen05 GEMM with cta_group::2: the batched weight-gradient GEMM of the training step (default since round 2; DESIGN.md
+// section 3.9) and the acez_gemm2cta_f16 entry of the C ABI.
 //
 //   D[z][M,N] (fp32) = A[z] * B[z]      fp16 operands, fp32 accumulation in TMEM, operand layouts as in gemm.cuh
 //
@@ -8,8 +9,8 @@
 //   * ITS HALF OF B (rows n0 + 128 r ..)     : 16 KB - the hardware feeds both tensor cores from both halves
 // i.e. 32 KB per CTA and k-block for 128 x 256 x 64 MACs per CTA: half the shared-memory fill and half the operand reads
 // per MAC of the cta_group::1 kernel with 128 x 128 tiles (round-1 measurement: the batched weight-gradient GEMM and the
-// fused layer chain are bound by the shared-memory port). This file is the probe that validates
-// the 2-CTA primitives in isolation before they go into those kernels:
+// fused layer chain are bound by the shared-memory port). The 2-CTA primitives it uses (validated on
+// hardware in round 2; the layer chain of head_chain4.cu uses the same ones):
 //   - tcgen05.alloc / dealloc .cta_group::2 (same warp index in both CTAs, same destination offset)
 //   - cp.async.bulk.tensor .cta_group::2 : both CTAs' loads complete on the LEADER's (rank 0) full barrier (peer bit cleared)
 //   - tcgen05.mma.cta_group::2 issued by the leader's MMA warp only

@@ -2,13 +2,14 @@
 // pass): ALL hidden 512x512 layers of one pass in ONE kernel launch.
 //
 // The per-layer GEMMs (gemm.cu) are row-tile independent: output rows [m0, m0+128) of layer l+1 depend only on the
-// same rows of layer l. So a 128-row tile never has to leave the chip between layers. One thread-block cluster of two
-// CTAs owns a row tile; CTA c computes output channels [256c, 256c+256) of every layer (128 x 256 x 512 per layer on
-// tcgen05, accumulators double-buffered in TMEM) and the two CTAs exchange their halves of the new activation tile
-// through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster, completing on the peer's mbarrier),
-// 64-column box by box, so the next layer's MMAs start while the epilogue of the current one is still draining.
-// Weights stream from L2 through a TMA ring that runs ahead across layer boundaries. Every new activation tile is
-// also written to HBM (TMA store) because the weight-gradient GEMM contracts over ALL rows and stays a separate kernel.
+// same rows of layer l. So a 128-row tile never has to leave the chip between layers. A thread-block cluster of FOUR CTAs
+// owns two row tiles; the SM pair of a channel half computes output channels [256c, 256c+256) of every layer for both
+// tiles with tcgen05.mma.cta_group::2 (M = 256, N = 256; accumulators double-buffered in TMEM) and the CTAs of a row tile
+// exchange their halves of the new activation tile through distributed shared memory (cp.async.bulk shared::cta ->
+// shared::cluster, completing on the partner's mbarrier), 64-column box by box, so the next layer's MMAs start while the
+// epilogue of the current one is still draining. Weights stream from L2 through a TMA ring that runs ahead across layer
+// boundaries. Every new activation tile is also written to HBM (TMA store) because the weight-gradient GEMM contracts over
+// ALL rows and stays a separate kernel. Kernel: head_chain4.cu; host side (tensor maps, dispatch): head_chain.cu.
 #pragma once
 #include "common.cuh"
 
@@ -42,8 +43,7 @@ struct ChainArgs {
   int n_steps;
   int flags;       // bit 0: relaxed (instead of release / acquire) cluster-scope signalling of the "A buffer free" barrier
                    // bit 6 (kChainFlagResInit): see above
-                   // bits 1..5: TIMING ABLATIONS (results are wrong; ACEZ_CHAIN_ABLATE, tools/probe_chain_time.py):
-                   //   2 no DSMEM exchange, 4 no TMA stores, 8 no weight loads, 16 no epilogue global operands, 32 no box write
+                   // bit 8: consume the k-blocks own boxes first (default; ACEZ_CHAIN_ORDER=arrival clears it)
   int* nonfinite;  // DGRAD: OR-ed with 1 if a stored gradient is inf / nan (nullable)
   long long* dbg;  // nullable: [gridDim.x][kChainDbgSlots] clock64 stamps (ACEZ_CHAIN_DBG=1, tools/probe_chain_time.py)
   ChainStep step[kChainMaxSteps];
@@ -51,10 +51,11 @@ struct ChainArgs {
 
 struct ChainLaunch {
   CUtensorMap tmIn;   // first A tile: [rows, 512], box {64, 128, 1}
-  CUtensorMap tmW;    // W16 [L][512][512]: FWD box {64, 256, 1} (K-major B), DGRAD box {64, 64, 1} (MN-major B)
+  CUtensorMap tmW;    // W16 [L][512][512]: FWD box {64, 256, 1} (K-major B), DGRAD box {64, 64, 1} (MN-major B); the kernel of
+                      // head_chain4.cu encodes its own map (each CTA of a pair stages half a k-block)
   CUtensorMap tmOut;  // [slots][rows][512], box {64, 128, 1}
-  const __half* w16;  // the weight array and layer count tmW was built from (head_chain4.cu encodes its own map lazily, so
-  int n_layers;       // that the default path executes no code of the experimental one)
+  const __half* w16;  // the weight array and layer count the weight map is built from
+  int n_layers;
   ChainArgs args;
   int mode;
 };
@@ -64,7 +65,7 @@ int chain_prepare(ChainLaunch* C, int mode, const __half* in, const __half* W16,
                   long long out_zstride, int out_slots, int rows);
 // pdl: launch with the programmatic-dependent-launch attribute (only when the stream predecessor is a kernel)
 int chain_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl = false);
-int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl);  // cta_group::2 on a cluster of 4 (head_chain4.cu)
+int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl);  // the kernel launch (head_chain4.cu)
 // profiling probe: device buffer for the clock64 stamps of a launch with `ctas` CTAs (nullptr unless ACEZ_CHAIN_DBG=1)
 long long* chain_debug_buffer(int ctas);
 // profiling probe: copies the stamps of the most recent launch with ACEZ_CHAIN_DBG=1 to host memory

@@ -1,23 +1,36 @@
-// EXPERIMENTAL (ACEZ_CHAIN_V4=1; written without GPU time at the end of round 1, not yet run on hardware):
-// the fused layer chain of head_chain.cu on tcgen05 cta_group::2.
+// Fused layer chain of the ACE head on tcgen05 cta_group::2 (the default head path; design: DESIGN.md section 3.8, interface:
+// head_chain.cuh): ALL hidden 512 x 512 layers of one pass (forward: 8, dgrad: 7) in ONE launch.
 //
-// Why: the cta_group::1 chain is bound by the shared-memory port (per layer and CTA 384 KB of UMMA operand reads + 256 KB
-// of weight fill + 4 x 64 KB of box traffic = 896 KB = 7 k cycles at 128 B/clk against 4.1 k cycles of UMMA issue). With
-// cta_group::2 two CTAs of an SM pair share every weight k-block (each stages HALF of it, the hardware feeds both tensor
-// cores from both halves): 128 KB of weight fill and 256 KB of operand reads per layer and CTA = 640 KB = 5 k cycles,
-// and the same 96 KB ring holds twice as many k-blocks in flight.
+// Why cta_group::2: the round-1 chain on cta_group::1 (a cluster of two CTAs per 128-row tile) was bound by the shared-memory
+// port (per layer and CTA 384 KB of UMMA operand reads + 256 KB of weight fill + 4 x 64 KB of box traffic against 4.1 k cycles of
+// UMMA issue). With cta_group::2 the two CTAs of an SM pair share every weight k-block (each stages HALF of it, the hardware feeds
+// both tensor cores from both halves): 128 KB of weight fill and 256 KB of operand reads per layer and CTA, and the same 96 KB ring
+// holds twice as many k-blocks in flight. Measured (round 2): 43-45 us per forward chain against 55.6 us.
 //
 // Decomposition: a cluster of FOUR CTAs owns TWO 128-row tiles. rank = 2 c + r:
 //   r = row tile inside the cluster, c = channel half. Pair P_c = {2c, 2c+1} (an SM pair) runs
 //   tcgen05.mma.cta_group::2 with M = 256 (CTA r contributes its row tile's 128 x 512 A buffer), N = 256 (output channels
 //   [256 c, 256 c + 256) of the layer; CTA r stages weight rows [256 c + 128 r, +128) of every k-block). Accumulators:
-//   each CTA's TMEM holds ITS rows x the pair's 256 channels, double buffered. The epilogue, the box exchange (now with
-//   rank ^ 2: same row tile, other channel half), the TMA stores, the register-resident residual stream and the mask bit
-//   words are those of head_chain.cu (V3 epilogue without the half-box publication).
+//   each CTA's TMEM holds ITS rows x the pair's 256 channels, double buffered.
 // Roles: warp 0 TMA producer (both CTAs: own A tile, own half of every weight k-block, completing on the LEADER's barrier);
 //   warp 1 of the pair leader (r = 0) issues the UMMAs; warp 1 of the other CTA is a RELAY: the leader cannot wait on a
-//   remote mbarrier, so the partner forwards "my k-block j is in place" to the leader's partner_ready[j].
+//   remote mbarrier, so the partner forwards "my k-block j is in place" to the leader's partner_ready[j];
+//   warps 2..9: epilogue, two groups of four warps (one warp per TMEM lane quarter), BOTH groups on the same 64-column box (32
+//   columns each), box after box: TMEM -> registers -> bias / ReLU / residual (or ReLU-mask bits) -> fp16 -> the box of the A buffer
+//   that is k-block (4 c + box) of the NEXT layer; one thread then publishes the box to the local MMA warp (mbarrier), copies it
+//   into the exchange partner's (rank ^ 2: same row tile, other channel half) A buffer (bulk DSMEM copy completing on the partner's
+//   mbarrier) and stores it to HBM (TMA store).
 // tcgen05.commit ... multicast::cluster (mask of the pair) releases weight stages / publishes accumulators to both CTAs.
+//
+// Hazards and how they are ordered (s = step index, one step = one layer):
+//   * MMA s+1 reads box j            after  a_ready[j] phase s+1 (own box: epilogue arrive; partner's box: complete_tx) on BOTH CTAs
+//                                           of the pair (partner_ready[j] relays the other CTA's)
+//   * epilogue s overwrites own box  after  tmem_full[s&1] (all MMAs of step s retired => A_s fully consumed), after the TMA store
+//                                           that last read it (cp.async.bulk.wait_group.read) and after peer_free phase s (the
+//                                           exchange partner consumed the DSMEM copy that read it)
+//   * copy into the partner's box    after  peer_free phase s (= the partner's MMAs of step s retired)
+//   * TMEM buffer s&1 rewritten by MMA s+2: needs every box of epilogue s+1, which follows epilogue s in program order
+// The protocol is model-checked under random interleavings by tools/sim_chain4_protocol.py.
 #include <stdlib.h>
 
 #include "head_chain.cuh"
@@ -205,17 +218,15 @@ __device__ __forceinline__ void c4_dgrad_half(const uint32_t (&vv)[32], uint32_t
   }
 }
 
-// G = number of epilogue groups (each = 4 warps, one per TMEM lane quarter): 2 -> a group drains two 64-column boxes per
-// step in sequence (the round-1 epilogue), 4 -> one box per group, all four boxes of a step in parallel.
-// SPLIT (two groups only): both groups work on the SAME box, each on one 32-column half, box after box: the first box of a
-// step is published after one half-box time instead of one box time, the four boxes come out in index order.
-template <int MODE, int G, bool SPLIT>
-__global__ void __launch_bounds__(64 + 128 * G, 1)
+template <int MODE>
+__global__ void __launch_bounds__(320, 1)
 head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ChainArgs args) {
+  constexpr int G = 2;          // epilogue groups (4 warps each, one per TMEM lane quarter)
+  constexpr bool SPLIT = true;  // both groups on the same box, 32 columns each (the whole-box-per-group and four-group variants
+                                // measured slower in round 2 and were removed)
   constexpr bool kDgrad = (MODE == CHAIN_DGRAD);
-  static_assert(!SPLIT || G == 2, "the split epilogue is written for two groups");
-  constexpr int NB = SPLIT ? 4 : 4 / G;   // boxes a group touches per step (SPLIT: half of each of the four)
+  constexpr int NB = 4;         // boxes a group touches per step (half of each of the four)
   constexpr int kEpiThreads = 128 * G;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -240,7 +251,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   const int n_base = c * CN;                // the pair's output channels of every layer
   const int nb_half = n_base + r * (CN / 2);
   const int n_steps = args.n_steps;
-  const bool own_first = (G == 4) || (args.flags & 256) != 0;   // k-block consumption order (ACEZ_CHAIN_ORDER=own)
+  const bool own_first = (args.flags & 256) != 0;   // k-block consumption order (default; ACEZ_CHAIN_ORDER=arrival clears it)
   long long* dbg = args.dbg != nullptr ? args.dbg + (size_t)blockIdx.x * kChainDbgSlots : nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -374,7 +385,7 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     const bool row_ok = row < args.rows;
     const int etid = threadIdx.x - 64;
     // one issuing thread per group, on different warps / SM sub-partitions
-    const bool issuer = SPLIT ? (lane == 0 && grp == 0 && quarter == 2) : ((lane == 0) && (quarter == (G == 2 ? 2 - 2 * grp : grp)));
+    const bool issuer = lane == 0 && grp == 0 && quarter == 2;   // the one thread that issues the copies of a finished box
     const uint32_t swz = (uint32_t)(rr & 7);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t sA_u32 = smem_u32(sA), sBias_u32 = smem_u32(sBiasF);
@@ -382,12 +393,12 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
     auto bar_all = [&]() { asm volatile("bar.sync 6, %0;" ::"n"(kEpiThreads) : "memory"); };
     uint32_t badbits = 0;
     // residual stream (forward) / skip-path gradient (dgrad) of this thread's row and boxes: stays in registers
-    uint32_t res[NB][SPLIT ? 16 : 32];
+    uint32_t res[NB][16];
 #pragma unroll
     for (int sl = 0; sl < NB; ++sl)
 #pragma unroll
-      for (int t = 0; t < (SPLIT ? 16 : 32); ++t) res[sl][t] = 0u;
-    if (SPLIT && !kDgrad && (args.flags & kChainFlagResInit)) {
+      for (int t = 0; t < 16; ++t) res[sl][t] = 0u;
+    if (!kDgrad && (args.flags & kChainFlagResInit)) {
       // res_0 = the input tile: this thread's row, its 32-column half of each of the CTA's four boxes
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -401,19 +412,6 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         }
       }
     }
-    if (!SPLIT && !kDgrad && (args.flags & kChainFlagResInit)) {
-#pragma unroll
-      for (int sl = 0; sl < NB; ++sl) {
-        const int j = c * 4 + grp + G * sl;
-        c4_wait<0>(&a_ready[j], 0u, (1u << 16) | (0xFFu << 8) | (uint32_t)j);
-        const uint32_t src = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint4 t = lds_128(src + ((((uint32_t)q) ^ swz) << 4));
-          res[sl][4 * q] = t.x; res[sl][4 * q + 1] = t.y; res[sl][4 * q + 2] = t.z; res[sl][4 * q + 3] = t.w;
-        }
-      }
-    }
     for (int s = 0; s < n_steps; ++s) {
       const ChainStep& st = args.step[s];
       const int tbuf = s & 1;
@@ -424,150 +422,70 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
         if (s > 0) bar_all();
         if (etid < CN) sts_f32(sBias_u32 + 4u * (uint32_t)etid, __half2float(__float2half_rn(st.bias != nullptr ? __ldg(st.bias + n_base + etid) : 0.f)));
       }
-      if constexpr (SPLIT) {
-        // ReLU-mask word of this thread's row and half for each box (dgrad): in flight while the accumulator is computed
-        uint32_t mwb[4] = {0u, 0u, 0u, 0u};
-        if (kDgrad && row_ok) {
+      // ReLU-mask word of this thread's row and half for each box (dgrad): in flight while the accumulator is computed
+      uint32_t mwb[4] = {0u, 0u, 0u, 0u};
+      if (kDgrad && row_ok) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) mwb[b] = __ldcg(reinterpret_cast<const uint32_t*>(st.mask_in + (size_t)row * 64 + (c * 4 + b) * 8 + 4 * grp));
-        }
-        if (issuer) {
-          c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));   // see the comment in the other branch
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (dbg) dbg[8 + 8 * s + 5] = clock64();
-        }
-        c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
-        tcgen05_fence_after();
-        if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
-        bar_all();   // bias slice visible; the issuer's permissions hold for every epilogue thread
-        const int res_add = st.res_add, res_save = st.res_save;
-        const bool want_mask = !kDgrad && st.mask_out != nullptr;
-        uint32_t vv[2][32];
-        tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + grp * 32), vv[0]);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int j = c * 4 + b;
-          tmem_ld_wait_for(vv[b & 1]);
-          if (b + 1 < 4) tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + (b + 1) * 64 + grp * 32), vv[(b + 1) & 1]);
-          const uint32_t dst = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
-          if (!kDgrad) {
-            uint32_t word = 0u;
-            const uint32_t bias_addr = sBias_u32 + 4u * (uint32_t)(b * 64);
-            if (res_add) {
-              if (want_mask) c4_fwd_half<true, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
-              else c4_fwd_half<true, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
-            } else {
-              if (want_mask) c4_fwd_half<false, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
-              else c4_fwd_half<false, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
-            }
-            if (want_mask && row_ok) *reinterpret_cast<uint32_t*>(st.mask_out + (size_t)row * 64 + j * 8 + 4 * grp) = word;
-          } else {
-            if (res_add) {
-              if (res_save) c4_dgrad_half<true, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
-              else c4_dgrad_half<true, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
-            } else {
-              if (res_save) c4_dgrad_half<false, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
-              else c4_dgrad_half<false, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
-            }
-          }
-          // box complete once both groups are here. Its TMEM columns are rewritten by the MMAs of step s+2, which are released
-          // (transitively) by the barrier arrival below: order the completed tcgen05.ld before it
-          tcgen05_fence_before();
-          fence_proxy_async();   // publish the half box to the tensor core / copy engines (async proxy)
-          bar_all();
-          if (issuer) {
-            const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
-            if (!last) {
-              mbar_arrive(&a_ready[j]);
-              c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
-            }
-            if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, n_base + b * 64, m0, st.out_slot);
-            tma_store_commit();
-            if (dbg && (b == 0 || b == 2)) dbg[8 + 8 * s + (b == 0 ? 6 : 7)] = clock64();
-          }
-        }
-      } else {
-      // ReLU-mask words of this thread's row for all its boxes (dgrad): in flight while the accumulator is still being computed
-      uint2 mw[NB];
-#pragma unroll
-      for (int sl = 0; sl < NB; ++sl) {
-        mw[sl] = make_uint2(0u, 0u);
-        if (kDgrad && row_ok) mw[sl] = __ldcg(reinterpret_cast<const uint2*>(st.mask_in + (size_t)row * 64 + (c * 4 + grp + G * sl) * 8));
+        for (int b = 0; b < 4; ++b) mwb[b] = __ldcg(reinterpret_cast<const uint32_t*>(st.mask_in + (size_t)row * 64 + (c * 4 + b) * 8 + 4 * grp));
       }
       if (issuer) {
-        // peer_free phase s: the exchange partner's MMAs of step s have retired, i.e. it has consumed the boxes copied to it
-        // during step s-1 (those copies no longer read the boxes rewritten below) and its A buffer may be overwritten.
+        // peer_free phase s: the exchange partner's MMAs of step s have retired, i.e. it has consumed the boxes copied to it during
+        // step s-1 (those copies no longer read the boxes rewritten below) and its A buffer may be overwritten
         c4_wait<2>(peer_free, (uint32_t)(s & 1), (5u << 16) | ((uint32_t)s << 8));
-        // the TMA stores of the previous step (issued one whole step ago) have finished reading this group's boxes
+        // the TMA stores of the previous step (issued one whole step ago) have finished reading the boxes
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (dbg && grp == 0) dbg[8 + 8 * s + 5] = clock64();
+        if (dbg) dbg[8 + 8 * s + 5] = clock64();
       }
       c4_wait<0>(&tmem_full[tbuf], (uint32_t)((s >> 1) & 1), (4u << 16) | ((uint32_t)s << 8));
       tcgen05_fence_after();
       if (dbg && etid == 0) dbg[8 + 8 * s + 4] = clock64();
-      bar_all();   // bias slice visible; the issuers' permissions (above) hold for every thread of their group
+      bar_all();   // bias slice visible; the issuer's permissions hold for every epilogue thread
       const int res_add = st.res_add, res_save = st.res_save;
       const bool want_mask = !kDgrad && st.mask_out != nullptr;
-      // The group's boxes are drained in 32-column halves with the TMEM loads software-pipelined: while the registers of
-      // half p are processed, the load of half p+1 is in flight (TMEM reads are the floor of the epilogue: 128 KB of
-      // accumulators per layer and CTA)
       uint32_t vv[2][32];
-      uint32_t bits_lo = 0u, bits_hi = 0u;
-      tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + grp * 64), vv[0]);
+      tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + grp * 32), vv[0]);
 #pragma unroll
-      for (int p = 0; p < 2 * NB; ++p) {
-        const int sl = p >> 1, hf = p & 1;
-        const int box = grp + G * sl;
-        const int j = c * 4 + box;
-        tmem_ld_wait_for(vv[p & 1]);
-        if (p + 1 < 2 * NB) {
-          const int nbox = grp + G * ((p + 1) >> 1);
-          tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + nbox * 64 + ((p + 1) & 1) * 32), vv[(p + 1) & 1]);
-        }
+      for (int b = 0; b < 4; ++b) {
+        const int j = c * 4 + b;
+        tmem_ld_wait_for(vv[b & 1]);
+        if (b + 1 < 4) tmem_ld_32x32(t_row + (uint32_t)(tbuf * CN + (b + 1) * 64 + grp * 32), vv[(b + 1) & 1]);
         const uint32_t dst = sA_u32 + (uint32_t)(j * kBoxBytes + rr * 128);
         if (!kDgrad) {
           uint32_t word = 0u;
-          const uint32_t bias_addr = sBias_u32 + 4u * (uint32_t)(box * 64);
+          const uint32_t bias_addr = sBias_u32 + 4u * (uint32_t)(b * 64);
           if (res_add) {
-            if (want_mask) c4_fwd_half<true, true>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
-            else c4_fwd_half<true, false>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
+            if (want_mask) c4_fwd_half<true, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+            else c4_fwd_half<true, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
           } else {
-            if (want_mask) c4_fwd_half<false, true>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
-            else c4_fwd_half<false, false>(vv[p & 1], &res[sl][16 * hf], hf, bias_addr, dst, swz, word);
+            if (want_mask) c4_fwd_half<false, true>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
+            else c4_fwd_half<false, false>(vv[b & 1], res[b], grp, bias_addr, dst, swz, word);
           }
-          if (hf == 0) bits_lo = word;
-          else bits_hi = word;
+          if (want_mask && row_ok) *reinterpret_cast<uint32_t*>(st.mask_out + (size_t)row * 64 + j * 8 + 4 * grp) = word;
         } else {
-          const uint32_t mword = hf == 0 ? mw[sl].x : mw[sl].y;
           if (res_add) {
-            if (res_save) c4_dgrad_half<true, true>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
-            else c4_dgrad_half<true, false>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
+            if (res_save) c4_dgrad_half<true, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+            else c4_dgrad_half<true, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
           } else {
-            if (res_save) c4_dgrad_half<false, true>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
-            else c4_dgrad_half<false, false>(vv[p & 1], &res[sl][16 * hf], hf, mword, dst, swz, badbits);
+            if (res_save) c4_dgrad_half<false, true>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
+            else c4_dgrad_half<false, false>(vv[b & 1], res[b], grp, mwb[b], dst, swz, badbits);
           }
         }
-        if (hf == 1) {
-          // box complete. Its TMEM columns are rewritten by the MMAs of step s+2, which are released (transitively) by the
-          // barrier arrivals below: order the completed tcgen05.ld before them
-          tcgen05_fence_before();
-          if (want_mask && row_ok) *reinterpret_cast<uint2*>(st.mask_out + (size_t)row * 64 + j * 8) = make_uint2(bits_lo, bits_hi);
-          bits_lo = 0u; bits_hi = 0u;
-          fence_proxy_async();   // publish the box to the tensor core / copy engines (async proxy)
-          bar_group();
-          if (issuer) {
-            const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
-            if (!last) {
-              mbar_arrive(&a_ready[j]);
-              c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
-            }
-            if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, n_base + box * 64, m0, st.out_slot);
-            tma_store_commit();
-            if (dbg && grp == 0) dbg[8 + 8 * s + (sl == 0 ? 6 : 7)] = clock64();
+        // box complete once both groups are here. Its TMEM columns are rewritten by the MMAs of step s+2, which are released
+        // (transitively) by the barrier arrival below: order the completed tcgen05.ld before it
+        tcgen05_fence_before();
+        fence_proxy_async();   // publish the half box to the tensor core / copy engines (async proxy)
+        bar_all();
+        if (issuer) {
+          const uint32_t box_addr = smem_u32(sA + j * kBoxBytes);
+          if (!last) {
+            mbar_arrive(&a_ready[j]);
+            c4_dsmem_copy(c4_mapa(box_addr, (uint32_t)xpeer), box_addr, kBoxBytes, c4_mapa(smem_u32(&a_ready[j]), (uint32_t)xpeer));
           }
+          if (st.out_slot >= 0) tma_store_3d(&tmOut, sA + j * kBoxBytes, n_base + b * 64, m0, st.out_slot);
+          tma_store_commit();
+          if (dbg && (b == 0 || b == 2)) dbg[8 + 8 * s + (b == 0 ? 6 : 7)] = clock64();
         }
       }
-          }
     }
     if (issuer) tma_store_wait_all();
     if (kDgrad && args.nonfinite != nullptr) {
@@ -585,9 +503,9 @@ head_chain4_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
   }
 }
 
-template <int MODE, int G, bool SPLIT>
+template <int MODE>
 static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
-  auto kern = head_chain4_kernel<MODE, G, SPLIT>;
+  auto kern = head_chain4_kernel<MODE>;
   static bool configured = false;
   if (!configured) {
     ACEZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4));
@@ -606,7 +524,7 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pd
   const int clusters = (tiles + 1) / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(4 * clusters);
-  cfg.blockDim = dim3(64 + 128 * G);
+  cfg.blockDim = dim3(320);
   cfg.dynamicSmemBytes = kSmem4;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -634,26 +552,8 @@ static int chain4_launch_mode(const ChainLaunch& C, cudaStream_t stream, bool pd
 
 int chain4_launch(const ChainLaunch& C, cudaStream_t stream, bool pdl) {
   ACEZ_REQUIRE(C.args.n_steps >= 1 && C.args.n_steps <= kChainMaxSteps, "chain4_launch: %d steps", C.args.n_steps);
-  static const int groups = [] {
-    const char* e = getenv("ACEZ_CHAIN_EPI_GROUPS");   // 2 (default): two boxes per epilogue group; 4: one box per group
-    return (e != nullptr && atoi(e) == 4) ? 4 : 2;
-  }();
-  static const bool split = [] {
-    // both epilogue groups on the same box, half each: the first box of a step is out after half a box time (default, 45.4 vs
-    // 48.3 us per forward chain); ACEZ_CHAIN_EPI_SPLIT=0: each group drains two whole boxes
-    const char* e = getenv("ACEZ_CHAIN_EPI_SPLIT");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  if (groups == 2 && split) {
-    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2, true>(C, stream, pdl);
-    return chain4_launch_mode<CHAIN_DGRAD, 2, true>(C, stream, pdl);
-  }
-  if (groups == 2) {
-    if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 2, false>(C, stream, pdl);
-    return chain4_launch_mode<CHAIN_DGRAD, 2, false>(C, stream, pdl);
-  }
-  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD, 4, false>(C, stream, pdl);
-  return chain4_launch_mode<CHAIN_DGRAD, 4, false>(C, stream, pdl);
+  if (C.mode == CHAIN_FWD) return chain4_launch_mode<CHAIN_FWD>(C, stream, pdl);
+  return chain4_launch_mode<CHAIN_DGRAD>(C, stream, pdl);
 }
 
 }  // namespace acez

@@ -127,12 +127,7 @@ class HeadEngine:
 
     def chain_kernel_symbol(self):
         """Name of the kernel that runs the forward pass over the hidden layers (for profile bookkeeping in bench.py)."""
-        import os
-        if not self.fused_chain:
-            return "gemm_tcgen05_kernel<FWD>"
-        if os.environ.get("ACEZ_CHAIN_V4", "1") != "0":
-            return "head_chain4_kernel<FWD,2,SPLIT>" if os.environ.get("ACEZ_CHAIN_EPI_SPLIT", "1") != "0" else "head_chain4_kernel<FWD,2>"
-        return "head_chain_kernel<FWD>"
+        return "head_chain4_kernel<FWD>" if self.fused_chain else "gemm_tcgen05_kernel<FWD>"
 
     def resize(self, max_rows):
         if max_rows > self.max_rows:

@@ -1,7 +1,7 @@
-"""Timing probe of the fused layer-chain kernels (head_chain.cu): CUDA-event timings of the forward chain and of the full
+"""Timing probe of the fused layer-chain kernels (head_chain4.cu): CUDA-event timings of the forward chain and of the full
 forward + tail + backward, plus the in-kernel clock64 timeline of one launch (ACEZ_CHAIN_DBG=1 is set here).
 
-    [ACEZ_CHAIN_XCHG=st] python tools/probe_chain_time.py
+    python tools/probe_chain_time.py
 """
 import ctypes as C
 import os
@@ -58,17 +58,13 @@ def show(st, cta, n_steps, title):
 
 
 def main():
-    print(f"XCHG={os.environ.get('ACEZ_CHAIN_XCHG', 'bulk')}", flush=True)
     bt = {k: v.to(dev) for k, v in ace_ref.synth_batch(5, B).items()}
-    # (relaxed handshake, ablation bits): 2 no DSMEM exchange, 4 no TMA stores, 8 no weight loads, 16 no epilogue global
-    # operands (residual / mask / xtra ...), 32 no box write. Ablated runs compute garbage: timing only.
-    combos = [(0, 0), (1, 0), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (1, 2 | 4), (1, 2 | 4 | 16), (1, 2 | 4 | 16 | 32),
-              (1, 2 | 4 | 8 | 16 | 32)]
+    # (relaxed handshake, unused): one combination; ACEZ_PROBE_COMBOS="0:0" times the release / acquire handshake instead
+    combos = [(1, 0)]
     if os.environ.get("ACEZ_PROBE_COMBOS"):   # e.g. "1:0,1:16"
         combos = [tuple(int(x) for x in c.split(":")) for c in os.environ["ACEZ_PROBE_COMBOS"].split(",")]
     for relaxed, abl in combos:
         os.environ["ACEZ_CHAIN_RELAXED"] = str(relaxed)
-        os.environ["ACEZ_CHAIN_ABLATE"] = str(abl)
         head = HeadEngine(1, True, (0, 0, 0), max_rows=B, training=True)
         head.load_state(ace_ref.make_head_state(200, 1, True))
         assert head.fused_chain
@@ -96,7 +92,7 @@ def main():
         tot_d = st[:, 1] - st[:, 0]
         print(f"relaxed={relaxed} ablate={abl:2d}: forward chain {t_f:7.1f} us  fwd+tail+bwd {t_a:7.1f} us | median CTA cycles "
               f"fwd {int(np.median(tot_f))} dgrad {int(np.median(tot_d))}", flush=True)
-        if abl == 0 and relaxed == 1 or abl == (2 | 4 | 16):
+        if True:
             show(st_f, 0, head.L, "fwd")
             show(st, 0, head.L - 1, "dgrad")
         del head
