@@ -26,30 +26,38 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
              base_seed=1305, max_tries=1000000, max_estimates=-1, micro_batch=16, rank=0, world_size=1,
              device="cuda"):
     """Returns a list of dicts {file, index, pose (4x4 cam->world numpy), inliers, focal} in processing order."""
-    pending, results = [], []
+    # pending: chunks (images [b,1,H,W] on the host - pinned when the loader pins -, K [b,3,3] host, file names, dataset indices)
+    # of ONE image size; results: per micro-batch (files, indices, focals, poses [n,4,4] device, inliers [n] device)
+    pending, n_pending, done = [], 0, []
     stats = {"images": 0, "seconds": 0.0}
     t0 = time.time()
 
     def flush():
+        nonlocal n_pending
         if not pending:
             return
-        # image by image from the loader's (pinned) tensors straight into the device batch: asynchronous copies, no host-side cat
-        imgs = torch.empty((len(pending),) + tuple(pending[0][0].shape[1:]), dtype=pending[0][0].dtype, device=device)
-        for k, p in enumerate(pending):
-            imgs[k].copy_(p[0][0], non_blocking=True)
-        K = torch.stack([p[1] for p in pending], 0)
-        f = K[:, 0, 0].contiguous()
+        n = n_pending
+        # the loader's chunks straight into the device batch: one asynchronous copy per chunk, no host-side cat of the images
+        imgs = torch.empty((n,) + tuple(pending[0][0].shape[1:]), dtype=pending[0][0].dtype, device=device)
+        o = 0
+        for img, _, _, _ in pending:
+            imgs[o:o + img.shape[0]].copy_(img, non_blocking=True)
+            o += img.shape[0]
+        K = torch.cat([p[1] for p in pending], 0).float()                 # host, n x 3 x 3
+        assert torch.allclose(K[:, 0, 0], K[:, 1, 1]), "a single focal length is supported (register_mapping.py:219)"
+        # focal / principal point from the HOST copy of K: one small upload per micro-batch, no device read-back per image
+        cam = torch.stack([K[:, 0, 0], K[:, 0, 2], K[:, 1, 2]], 0).contiguous().to(device, non_blocking=True)
         with torch.no_grad():
-            sc = network(imgs).float().contiguous()                   # [n,3,h,w] stays on the device
+            sc = network(imgs).float().contiguous()                       # [n,3,h,w] stays on the device
         # ONE DSAC* launch pair per micro-batch in any image order (the loader of register_mapping.py:147 shuffles):
         # the RNG of image j is keyed by its dataset index through the per-image key array of the C ABI
-        idx = [int(p[3]) for p in pending]
-        poses, inl = dsac.forward_rgb_batch(sc, f, K[:, 0, 2].contiguous(), K[:, 1, 2].contiguous(), hypotheses,
-                                            threshold, inlier_alpha, max_pixel_error, network.OUTPUT_SUBSAMPLE,
-                                            base_seed, max_tries, image_index=idx)
-        for j, p in enumerate(pending):
-            results.append({"file": p[2], "index": int(p[3]), "pose": poses[j], "inliers": inl[j], "focal": p[4]})
+        files = [f for p in pending for f in p[2]]
+        idx = [i for p in pending for i in p[3]]
+        poses, inl = dsac.forward_rgb_batch(sc, cam[0], cam[1], cam[2], hypotheses, threshold, inlier_alpha, max_pixel_error,
+                                            network.OUTPUT_SUBSAMPLE, base_seed, max_tries, image_index=idx)
+        done.append((files, idx, [float(x) for x in K[:, 0, 0]], poses, inl))
         pending.clear()
+        n_pending = 0
 
     def batches():
         for item in loader:
@@ -62,27 +70,33 @@ def register(network, loader, hypotheses=64, threshold=10.0, inlier_alpha=100.0,
     count = 0
     for image, _, _, _, K, _, _, filenames, indices in batches():
         B = image.shape[0]
-        for b in range(B):
-            i = int(indices[b]) if torch.is_tensor(indices) else int(indices)
-            if i % world_size != rank:
-                continue
-            Kb = K[b]
-            assert torch.allclose(Kb[0, 0], Kb[1, 1]), "a single focal length is supported (register_mapping.py:219)"
-            # focal from the CPU copy of K (no device read-back per image)
-            focal = float(Kb[0, 0])
-            item = (image[b:b + 1], Kb.to(device, non_blocking=True),
-                    filenames[b] if not isinstance(filenames, str) else filenames, i, focal)
-            if pending and (pending[0][0].shape != item[0].shape or len(pending) >= micro_batch):
+        ind = [int(x) for x in indices] if torch.is_tensor(indices) else [int(indices)]
+        names = [filenames] * B if isinstance(filenames, str) else list(filenames)
+        keep = [b for b in range(B) if ind[b] % world_size == rank]
+        if 0 < max_estimates and count + len(keep) > max_estimates:
+            keep = keep[:max(0, max_estimates - count)]
+        if keep:
+            if len(keep) < B:
+                sel = torch.tensor(keep)
+                image, K = image[sel], K[sel]
+            if pending and (pending[0][0].shape[1:] != image.shape[1:] or n_pending + len(keep) > micro_batch):
                 flush()
-            pending.append(item)
-            count += 1
+            pending.append((image, K, [names[b] for b in keep], [ind[b] for b in keep]))
+            n_pending += len(keep)
+            count += len(keep)
         if 0 < max_estimates <= count:
             break
     flush()
-    torch.cuda.synchronize()
-    for r in results:   # one device->host transfer at the end
-        r["pose"] = r["pose"].cpu().numpy()
-        r["inliers"] = int(r["inliers"])
+    results = []
+    if done:
+        # ONE device->host transfer for all poses / inlier counts at the end
+        poses = torch.cat([d[3] for d in done], 0).cpu().numpy()
+        inl = torch.cat([d[4] for d in done], 0).cpu().numpy()
+        k = 0
+        for files, idx, focals, _, _ in done:
+            for j in range(len(idx)):
+                results.append({"file": files[j], "index": idx[j], "pose": poses[k], "inliers": int(inl[k]), "focal": focals[j]})
+                k += 1
     stats["images"] = len(results)
     stats["seconds"] = time.time() - t0
     return results, stats

@@ -352,7 +352,7 @@ def run_pipeline(dev, H=480, W=640, focal=525.0, iterations=5000):
 
     # what register_mapping.py builds: shuffled, batches of 8 collated by worker processes and pinned (the reference runs 12
     # workers, register_mapping.py:8,147); the workers persist across the timed passes
-    ld = DataLoader(test, shuffle=True, num_workers=4, persistent_workers=True, generator=gen, batch_size=8,
+    ld = DataLoader(test, shuffle=True, num_workers=12, persistent_workers=True, generator=gen, batch_size=8,
                     collate_fn=collate_same_size, pin_memory=True)
     register(net, ld, hypotheses=64, max_tries=16, device=dev)   # warm-up (starts the workers)
     torch.cuda.synchronize()
@@ -371,7 +371,7 @@ def run_pipeline(dev, H=480, W=640, focal=525.0, iterations=5000):
     del ld
     return {
         "what": f"64 rendered {H}x{W} frames (f = {focal}): TrainerACE.train (buffer fill + {iterations} iterations) then "
-                "registration.register on 64 held-out views through a shuffled DataLoader with 4 workers (host images in, host "
+                "registration.register on 64 held-out views through a shuffled DataLoader with 12 workers (host images in, host "
                 f"poses out); the encoder has {enc_kind}",
         "buffer_fill_images_per_s": timing["images_encoded"] / timing["buffer_s"],
         "buffer_fill_s": timing["buffer_s"], "images_encoded": timing["images_encoded"],
