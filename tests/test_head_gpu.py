@@ -220,75 +220,3 @@ def test_host_batch_paths_match_device_buffer_path():
     np.testing.assert_allclose(losses[3], losses[0], rtol=2e-3)
     np.testing.assert_allclose(losses[4], losses[0], rtol=2e-3)
 
-
-def _dp_step_world1(eng, variant):
-    """acez_adamw_dp_step with world = 1 on plain (non-symmetric) memory: the gradient 'exchange' is with itself, every signal is
-    sent to and polled from the rank's own flag array. variant: 'fused' (one kernel) or 'two' (ACEZ_DP_FUSED=0 path is selected
-    by passing no statistics pointer: reduce + apply kernels)."""
-    import ctypes as C
-    from acezero_b200 import _lib
-    lib = eng.lib
-    n = eng.n_params
-    shard = int(lib.acez_adamw_dp_shard(n, 1))
-    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
-    sync = torch.zeros(4, dtype=torch.int32, device="cuda")
-    reduced = torch.zeros(shard + 4, device="cuda")
-    arr = lambda p: (C.c_void_p * 1)(int(p))
-    w16 = int(lib.acez_head_w16_ptr(eng.plan, 0))
-    w3h = int(lib.acez_head_w16_ptr(eng.plan, 1))
-    stats = _lib.ptr(eng.stats) if variant == "fused" else None
-    for _ in range(2):   # two steps: the epoch counter and the self-resetting block counters must carry over
-        rc = lib.acez_adamw_dp_step(arr(eng.grads_full.data_ptr()), arr(flags.data_ptr()), arr(w16), arr(w3h), arr(eng.params.data_ptr()),
-                                    1, 0, n, _lib.ptr(reduced), _lib.ptr(eng.params), _lib.ptr(eng.exp_avg), _lib.ptr(eng.exp_avg_sq),
-                                    _lib.ptr(eng.hyper), _lib.ptr(eng.scaler_state), _lib.ptr(eng.found_inf),
-                                    C.c_void_p(eng.grads_full.data_ptr() + 4 * n), _lib.ptr(sync), stats, None, eng.L, eng.C3,
-                                    _lib.stream_ptr())
-        _lib.check(rc, "acez_adamw_dp_step")
-    torch.cuda.synchronize()
-    return int(sync[0]), flags
-
-
-@pytest.mark.parametrize("variant", ["fused", "two"])
-def test_dp_optimizer_kernel_on_one_rank_matches_adamw_kernel(variant):
-    """csrc/adamw_dp.cu on ONE GPU (world = 1): the data-parallel optimiser step - gradient 'reduction', fp16-range check, global
-    verdict, AdamW on the shard, fp16 weight shadows, GradScaler.update(), epoch signals - must reproduce acez_adamw_step (same
-    GradScaler decisions exactly, parameters and moments to one ulp), including a skipped step after an overflow. (The multi-rank behaviour is covered by tools/check_dp.py under torchrun.)"""
-    from acezero_b200.head import HeadEngine
-    sd = ace_ref.make_head_state(200, 1, True)
-    g = torch.Generator(device="cuda").manual_seed(11)
-    engs = []
-    for _ in range(2):
-        e = HeadEngine(1, True, (0.0, 0.0, 0.0), max_rows=256, training=True)
-        e.load_state(sd)
-        e.scaler_state[0] = 1024.0
-        engs.append(e)
-    a, b = engs
-    grad = torch.randn(a.n_params, device="cuda", generator=g) * 30.0
-    for overflow in (False, True):
-        gg = grad.clone()
-        if overflow:
-            gg[12345] = 70000.0          # beyond the fp16 range: GradScaler must skip the step and halve the scale
-        for e in (a, b):
-            e.grads_full.zero_()
-            e.grads_full[:e.n_params] = gg
-            e.found_inf.zero_()
-            e.stats.zero_()
-        # reference: the single-GPU kernel with its own check pass (mode 1: the flag is NOT complete yet), twice
-        for _ in range(2):
-            a.adamw_step(use_scaler=True, flag_complete=False)
-        epoch, _ = _dp_step_world1(b, variant)
-        torch.cuda.synchronize()
-        assert epoch == 2
-        assert torch.equal(a.scaler_state[:3], b.scaler_state[:3]), (a.scaler_state, b.scaler_state)
-        assert int(a.found_inf) == int(b.found_inf) == int(overflow)
-        # (two different kernels: the compiler may contract the update's multiply-adds differently, so one ulp is allowed)
-        for name in ("params", "exp_avg", "exp_avg_sq"):
-            torch.testing.assert_close(getattr(b, name), getattr(a, name), rtol=2e-6, atol=1e-10, msg=name)
-        # the fp16 shadows the GEMMs read
-        import ctypes as C
-        for which, cnt in ((0, a.L * 512 * 512), (1, a.C3 * 512)):
-            pa = int(a.lib.acez_head_w16_ptr(a.plan, which)) - a.workspace.data_ptr()
-            pb = int(b.lib.acez_head_w16_ptr(b.plan, which)) - b.workspace.data_ptr()
-            wa = a.workspace[pa:pa + 2 * cnt].view(torch.float16)
-            wb = b.workspace[pb:pb + 2 * cnt].view(torch.float16)
-            torch.testing.assert_close(wb.float(), wa.float(), rtol=2e-3, atol=1e-7, msg=f"fp16 shadow {which}")   # one fp16 ulp
