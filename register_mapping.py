@@ -67,6 +67,9 @@ def main(argv=None):
     from acezero_b200 import launch
     # the fast registration check of a seed trial (ace_zero_util.py:242-259: --max_estimates 1000) stays on one leased GPU
     small_job = opt.max_estimates > 0
+    if launch.requested_gpus(opt.gpus) == 1:
+        from acezero_b200 import worker   # opt-in persistent stage worker (ACEZ_WORKER), see train_ace.py
+        worker.try_forward("register_mapping", argv)
     launch.maybe_self_launch(Path(__file__).resolve(), argv, launch.requested_gpus(opt.gpus), small_job=small_job)
     import torch
     rank, world = launch.select_device(small_job=small_job)

@@ -84,6 +84,11 @@ def main(argv=None):
     n_gpus = launch.requested_gpus(o.gpus)
     if o.batch_size % max(n_gpus, 1) != 0:
         raise ValueError(f"batch_size {o.batch_size} is not divisible by {n_gpus} GPUs")
+    if n_gpus == 1:
+        # opt-in (ACEZ_WORKER): hand the stage to the persistent worker process instead of paying interpreter start, torch import,
+        # CUDA context and kernel set-up once per stage (acezero_b200/worker.py); a no-op without the switch or without a worker
+        from acezero_b200 import worker
+        worker.try_forward("train_ace", argv)
     launch.maybe_self_launch(Path(__file__).resolve(), argv, n_gpus, small_job=small_job)
     import torch
     rank, world = launch.select_device(small_job=small_job)
