@@ -160,3 +160,26 @@ def test_dp_shard_partition(lib):
         s = lib.acez_adamw_dp_shard(n, g)
         assert s % 8 == 0 and g * s >= n and (g - 1) * s < n
     assert (512 * 512 + 512) % 8 == 0 and (512 * 512) % 8 == 0
+
+
+def test_dp_optimizer_protocol_model_check():
+    """The cross-GPU protocol of the one-kernel data-parallel optimiser step (csrc/adamw_dp.cu: epoch signals, verdict exchange,
+    weight pushes, fences) under random interleavings and delivery orders of the remote stores: gradients are read only while they
+    belong to the iteration, weights are never overwritten under a computing owner and are complete before the next forward, no
+    signal wait passes on a stale epoch, the verdict is global, no deadlock (tools/sim_dp_protocol.py). The checker has teeth:
+    without the final wait for everybody's "weights written" signal it must find the stale-weights violation."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sim_dp_protocol", ROOT / "tools" / "sim_dp_protocol.py")
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    for G in (2, 4):
+        for seed in range(12):
+            sim.Sim(G, 3, 3, seed).run()
+    src = (ROOT / "tools" / "sim_dp_protocol.py").read_text()
+    broken = src.replace('            for q in range(G):\n                yield from self.wait_row(me, "applied", q, e)\n', "")
+    assert broken != src
+    ns = {}
+    exec(compile(broken, "sim_dp_protocol_broken", "exec"), ns)
+    with pytest.raises(AssertionError):
+        for seed in range(8):
+            ns["Sim"](3, 3, 3, seed).run()
