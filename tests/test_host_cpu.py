@@ -183,3 +183,16 @@ def test_dp_optimizer_protocol_model_check():
     with pytest.raises(AssertionError):
         for seed in range(8):
             ns["Sim"](3, 3, 3, seed).run()
+
+
+def test_header_is_plain_c():
+    """include/acez.h is the FFI boundary: it must compile as C99 (plain pointers and sizes, no C++ / torch types) and as C++."""
+    import shutil
+    import subprocess
+    hdr = str(ROOT / "include" / "acez.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    for cmd in (["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", hdr],
+                ["g++", "-x", "c++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
